@@ -1,0 +1,208 @@
+/* sscg_b200.h — C ABI of libsscg_b200.so: the B200 (sm_100a) kernels behind the reference's
+ * network boundary `arch.define_Gen / define_Dis / set_grad` (reference arch/__init__.py:1-3).
+ *
+ * The reference has no FFI of its own (it is pure Python over torch.nn); each entry point below
+ * replaces one family of ATen/cuDNN calls that the reference's modules issue on the hot path
+ * (SURVEY.md §2.3 K1-K19).  Plain pointers and sizes only: every pointer is a DEVICE pointer
+ * unless its name ends in `_host`; every function enqueues on `stream` (a cudaStream_t passed as
+ * void*) and returns immediately.  Return value: 0 on success, non-zero on failure — the message
+ * is available from sscg_last_error().  No hidden allocation, no global mutable state besides the
+ * last-error string and the lazily resolved driver entry point for tensor-map encoding.
+ *
+ * Layout vocabulary: activations are NHWC bf16 ("planes" of one sample are H x W x Cpitch); a
+ * "view" is (ptr, N, H, W, C, sN, sH, sW) with element strides, which lets one buffer carry an
+ * explicit reflect halo while another kernel reads only its interior (zero fill outside).
+ */
+#ifndef SSCG_B200_H
+#define SSCG_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SSCG_MAX_TAPS 64
+
+/* activation codes */
+#define SSCG_ACT_NONE 0
+#define SSCG_ACT_RELU 1
+#define SSCG_ACT_LRELU 2
+#define SSCG_ACT_TANH 3
+
+/* halo modes */
+#define SSCG_PAD_NONE 0
+#define SSCG_PAD_ZERO 1
+#define SSCG_PAD_REFLECT 2
+
+typedef struct SscgTap {
+    int8_t dh, dw;  /* input pixel = out pixel * stride + (dh, dw) + (org_h, org_w) */
+    int16_t brow;   /* weight slab index: weight rows [brow*Co_pad, (brow+1)*Co_pad) */
+} SscgTap;
+
+/* NHWC bf16 view (element strides). C is the extent of the innermost (contiguous) dimension that a
+ * K-block may address: the channel pitch in regular mode, the padded (kw,c) window in window mode. */
+typedef struct SscgView {
+    const void* ptr;
+    int32_t N, H, W, C;
+    int64_t sN, sH, sW;
+} SscgView;
+
+/* ---------------------------------------------------------------------------------------------
+ * sscg_conv_igemm — implicit-GEMM convolution on tcgen05 tensor cores (TMA-fed, TMEM accumulate).
+ * Replaces: nn.Conv2d / nn.ConvTranspose2d forward (reference arch/ops.py:40-57,63,68;
+ * arch/generators.py:74-90; arch/discriminators.py:45-58) and their cuDNN dgrad (K17), with the
+ * reflection pad (arch/ops.py:62,67; generators.py:73,84,89) folded into the operand view and the
+ * InstanceNorm statistics (arch/ops.py:11) accumulated in the epilogue.
+ *
+ *   Y[n, ho, wo, co] = act( bias[co] + sum_{tap, k} X[n, ho*stride+tap.dh+org_h, wo*stride+tap.dw+org_w, k]
+ *                                                   * Wt[tap.brow*Co_pad + co, k] )
+ * Pixels outside the X view read as zero.  With n_phases == 4 the output is produced as four
+ * interleaved sub-grids (ho = 2i+ph, wo = 2j+pw; phase p = 2*ph+pw uses taps
+ * [phase_start[p], phase_start[p+1])) — the sub-pixel form of a stride-2 transposed convolution.
+ * split == 3 selects the bf16x3 parity mode: X and Wt are given as hi/lo bf16 planes and the
+ * product is accumulated as hi*hi + lo*hi + hi*lo in fp32.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct SscgConvArgs {
+    SscgView x;            /* activation view (hi plane) */
+    const void* x_lo;      /* lo plane (same strides) or NULL */
+    int32_t stride;        /* 1 or 2 */
+    int32_t Kc;            /* K elements per tap; multiple of 64; <= x.C */
+    int32_t org_h, org_w;
+    int32_t n_phases;      /* 1 or 4 */
+    int32_t phase_start[5];
+    SscgTap taps[SSCG_MAX_TAPS];
+    const void* w;         /* bf16 [w_rows][Kc] (K-major), hi plane */
+    const void* w_lo;      /* lo plane or NULL */
+    int32_t w_rows;
+    int32_t Co_pad;        /* output channels incl. padding; multiple of BN */
+    int32_t split;         /* 1 (bf16) or 3 (bf16x3) */
+    void* y;               /* output: bf16 (y_fp32 == 0) or fp32 (y_fp32 == 1), NHWC-like */
+    int32_t y_fp32;
+    int64_t y_sN, y_sH, y_sW;   /* element strides; channel stride is 1 */
+    int32_t y_oh, y_ow;    /* output written at (ho + y_oh, wo + y_ow) */
+    int32_t Ho, Wo;        /* output extents (all phases together) */
+    const float* bias;     /* [Co_pad] or NULL */
+    int32_t act;           /* SSCG_ACT_* applied in the epilogue */
+    float slope;
+    float* stats;          /* [N][Co_pad][2] fp32 (sum, sum of squares), accumulated atomically; or NULL */
+    int32_t TH, TW;        /* output tile, TH*TW == 128 */
+    int32_t BN;            /* N tile: 16, 32, 64, 128 or 256 */
+} SscgConvArgs;
+
+int sscg_conv_igemm(const SscgConvArgs* a, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * sscg_conv_wgrad — weight gradient as a pixel-contraction GEMM on tcgen05 (both operands MN-major).
+ * Replaces: cuDNN wgrad of the same convolutions (K17).
+ *   dWt[tap.brow*Co_pad + co, k] += sum_{n, ho, wo} dY[n, ho, wo, co] * X[n, ho*stride+tap.dh+org_h, ..., k]
+ * dWt is fp32 [w_rows][Kc], accumulated with red.global.add (split-K over samples / pixel tiles).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct SscgWgradArgs {
+    SscgView dy;           /* output-gradient view [N][Ho][Wo][Co_pad] (hi plane); zero outside */
+    const void* dy_lo;
+    SscgView x;            /* forward activation view (hi plane) */
+    const void* x_lo;
+    int32_t stride, Kc, org_h, org_w;
+    int32_t n_taps;
+    SscgTap taps[SSCG_MAX_TAPS];
+    int32_t Co_pad;        /* multiple of 64 */
+    int32_t split;
+    float* dw;             /* fp32 [w_rows][Kc] */
+    int32_t w_rows;
+    int32_t TH, TW;        /* pixel block, TH*TW == 64 */
+    int32_t BN;            /* K-column tile of dWt: 64, 128 or 256 (divides Kc) */
+    int32_t ksplit;        /* number of CTAs sharing one (tap, co-tile, k-tile) */
+} SscgWgradArgs;
+
+int sscg_conv_wgrad(const SscgWgradArgs* a, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Elementwise / reduction kernels around the GEMMs.
+ * ------------------------------------------------------------------------------------------- */
+
+/* sscg_pack_nchw: NCHW fp32 -> NHWC bf16 with channel padding and an explicit halo.
+ * Replaces the layout change + nn.ReflectionPad2d(3) at the generator stem (generators.py:73) and
+ * the zero padding of the PatchGAN stem (discriminators.py:45).  dst extents (H+2*pad, W+2*pad). */
+int sscg_pack_nchw(const float* src, int32_t N, int32_t C, int32_t H, int32_t W, void* dst, void* dst_lo,
+                   int32_t Cp, int32_t pad, int32_t pad_mode, void* stream);
+
+/* sscg_onehot_pack: int64 label map [N][1][H][W] -> one-hot NHWC bf16 with halo (utils.py:314-350
+ * make_one_hot fused with the stem's layout change). */
+int sscg_onehot_pack(const int64_t* labels, int32_t N, int32_t C, int32_t H, int32_t W, void* dst, void* dst_lo,
+                     int32_t Cp, int32_t pad, int32_t pad_mode, void* stream);
+
+/* sscg_unpack_nhwc: NHWC fp32 [N][H][W][Cp] -> NCHW fp32 [N][C][H][W] (module output boundary). */
+int sscg_unpack_nhwc(const float* src, int32_t N, int32_t C, int32_t H, int32_t W, int32_t Cp, float* dst,
+                     void* stream);
+
+/* sscg_in_apply: y = dropout(act(instance_norm(raw))) (+ residual), written with a halo for the next
+ * convolution.  Replaces nn.InstanceNorm2d + ReLU/LeakyReLU + Dropout + residual add + the next
+ * layer's ReflectionPad2d (ops.py:11,44,50,57,62-74).
+ *   raw:   [N][H][W][C] bf16 (raw_fp32 == 0) or fp32
+ *   stats: [N][C][2] (sum, sumsq) from the conv epilogue, or NULL for "no norm"
+ *   res:   optional residual view (bf16 hi/lo), added after norm/act
+ *   dst:   bf16 [N][H+2p][W+2p][C] (+ lo plane when dst_lo != NULL)
+ *   dropout: p = 0.5 when drop_seed != 0 (keep mask = hash(seed, element index); scale 2). */
+typedef struct SscgApplyArgs {
+    const void* raw; int32_t raw_fp32;
+    const float* stats; float eps;
+    int32_t N, H, W, C;
+    int32_t act; float slope;
+    uint64_t drop_seed;
+    SscgView res; const void* res_lo;
+    void* dst; void* dst_lo;
+    int32_t pad, pad_mode;
+} SscgApplyArgs;
+int sscg_in_apply(const SscgApplyArgs* a, void* stream);
+
+/* sscg_in_bwd_prep / sscg_in_bwd_apply: backward of the same chain.
+ * prep:  dZ = act'(Z) * dropmask * ( fold_halo(dYp) + skip ), Z = instance_norm(raw) recomputed;
+ *        writes dZ (and optionally the folded sum G for the residual skip path), accumulates
+ *        bstats[n][c] = (sum dZ, sum dZ*Z).  With stats == NULL (no norm) dZ is the final dRaw and
+ *        bstats[.][c][0] is the bias gradient contribution.
+ * apply: dRaw = rstd * (dZ - mean(dZ) - Z * mean(dZ*Z)). */
+typedef struct SscgBwdArgs {
+    const void* raw; int32_t raw_fp32;
+    const float* stats; float eps;
+    int32_t N, H, W, C;
+    int32_t act; float slope;
+    uint64_t drop_seed;
+    SscgView dyp; int32_t dyp_fp32;   /* gradient w.r.t. the padded consumer buffer; interior offset = pad */
+    int32_t pad, pad_mode;
+    SscgView skip; int32_t skip_fp32; /* optional extra gradient on the unpadded output (residual path) */
+    void* g_out; int32_t g_fp32;      /* optional: folded dYp + skip, [N][H][W][C] */
+    void* dz; int32_t dz_fp32;        /* [N][H][W][C] */
+    void* dz_lo;                      /* lo plane when dZ is the final dRaw in split mode */
+    float* bstats;                    /* [N][C][2] */
+} SscgBwdArgs;
+int sscg_in_bwd_prep(const SscgBwdArgs* a, void* stream);
+int sscg_in_bwd_apply(const SscgBwdArgs* a, void* draw, void* draw_lo, void* stream);
+
+/* weight preparation: fp32 master weights -> bf16 GEMM operand slabs (see DESIGN.md "weight slabs") */
+typedef struct SscgWprepArgs {
+    const float* w;        /* Conv2d: [Co][Ci][KH][KW]; ConvTranspose2d: [Ci][Co][KH][KW] */
+    int32_t transposed;    /* source is ConvTranspose2d layout */
+    int32_t Co, Ci, KH, KW;
+    int32_t mode;          /* 0: fwd regular  [tap][Co_pad][Kc(ci)]
+                              1: fwd window   [kh][Co_pad][Kc(kw*Cp+ci)]
+                              2: dgrad regular [tap][Ci_pad][Kc(co)]  (taps indexed as in the source)
+                            */
+    int32_t Cp;            /* channel pitch of the activation in window mode */
+    int32_t rows_pad;      /* Co_pad (mode 0,1) or Ci_pad (mode 2) */
+    int32_t Kc;
+    void* dst; void* dst_lo;
+} SscgWprepArgs;
+int sscg_wprep(const SscgWprepArgs* a, void* stream);
+/* inverse mapping for gradients: fp32 slab [rows][Kc] -> += into the parameter-shaped gradient */
+int sscg_wgrad_unpack(const SscgWprepArgs* a, const float* slab, float* grad, float scale, void* stream);
+
+/* utility */
+int sscg_fill_zero(void* ptr, int64_t bytes, void* stream);
+const char* sscg_last_error(void);
+int sscg_device_error(void);   /* reads (and clears) the device-side protocol error flag; 0 = none */
+int sscg_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SSCG_B200_H */

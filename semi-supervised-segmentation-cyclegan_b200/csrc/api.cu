@@ -1,0 +1,94 @@
+// api.cu — unity translation unit of libsscg_b200.so: shared host helpers + all kernels.
+// Built by csrc/build.sh (nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo).
+#include "sscg_common.cuh"
+
+namespace sscg {
+
+static thread_local char g_err[512] = "";
+
+int set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return 1;
+}
+
+PFN_encodeTiled get_encode_tiled() {
+    static PFN_encodeTiled fn = nullptr;
+    if (fn) return fn;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+    if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !p) {
+        set_error("cuTensorMapEncodeTiled entry point unavailable: %s", cudaGetErrorString(e));
+        return nullptr;
+    }
+    fn = reinterpret_cast<PFN_encodeTiled>(p);
+    return fn;
+}
+
+int encode_view_4d(CUtensorMap* tm, const SscgView& v, const void* ptr, const uint32_t box[4], const uint32_t es[4]) {
+    PFN_encodeTiled enc = get_encode_tiled();
+    if (!enc) return 1;
+    cuuint64_t dims[4] = {(cuuint64_t)v.C, (cuuint64_t)v.W, (cuuint64_t)v.H, (cuuint64_t)v.N};
+    cuuint64_t strides[3] = {(cuuint64_t)v.sW * 2, (cuuint64_t)v.sH * 2, (cuuint64_t)v.sN * 2};
+    cuuint32_t b[4] = {box[0], box[1], box[2], box[3]};
+    cuuint32_t s[4] = {es[0], es[1], es[2], es[3]};
+    if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (strides[0] & 15) || (strides[1] & 15) || (strides[2] & 15))
+        return set_error("tensor map: view pointer/strides must be 16-byte aligned (ptr=%p sW=%lld sH=%lld sN=%lld)", ptr,
+                         (long long)v.sW, (long long)v.sH, (long long)v.sN);
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, b, s,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return set_error("cuTensorMapEncodeTiled(4d) failed: %d dims=(%llu,%llu,%llu,%llu) strides=(%llu,%llu,%llu) "
+                         "box=(%u,%u,%u,%u) es=(%u,%u,%u,%u)",
+                         (int)r, dims[0], dims[1], dims[2], dims[3], strides[0], strides[1], strides[2], b[0], b[1], b[2],
+                         b[3], s[0], s[1], s[2], s[3]);
+    return 0;
+}
+
+int encode_2d(CUtensorMap* tm, const void* ptr, int cols, int rows, int box_cols, int box_rows) {
+    PFN_encodeTiled enc = get_encode_tiled();
+    if (!enc) return 1;
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+    cuuint32_t b[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+    cuuint32_t s[2] = {1, 1};
+    if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (strides[0] & 15))
+        return set_error("tensor map: matrix pointer/pitch must be 16-byte aligned");
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, b, s,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return set_error("cuTensorMapEncodeTiled(2d) failed: %d dims=(%llu,%llu) box=(%u,%u)", (int)r, dims[0], dims[1],
+                         b[0], b[1]);
+    return 0;
+}
+
+}  // namespace sscg
+
+extern "C" const char* sscg_last_error(void) { return sscg::g_err; }
+extern "C" int sscg_version(void) { return 100; }
+
+extern "C" int sscg_device_error(void) {
+    unsigned int v = 0;
+    cudaError_t e = cudaMemcpyFromSymbol(&v, sscg::g_sscg_dev_error, sizeof(v));
+    if (e != cudaSuccess) return -1;
+    if (v) {
+        unsigned int z = 0;
+        cudaMemcpyToSymbol(sscg::g_sscg_dev_error, &z, sizeof(z));
+    }
+    return (int)v;
+}
+
+extern "C" int sscg_fill_zero(void* ptr, int64_t bytes, void* stream) {
+    cudaError_t e = cudaMemsetAsync(ptr, 0, (size_t)bytes, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return sscg::set_error("fill_zero: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+#include "conv_igemm.cu"
+#include "conv_wgrad.cu"
+#include "elementwise.cu"

@@ -1,0 +1,371 @@
+// conv_igemm.cu — implicit-GEMM convolution for sm_100a.
+//
+// One CTA computes a 128-pixel x BN-channel output tile.  Roles (192 threads):
+//   warp 0      : TMA producer — per K-block one 4-D box of the NHWC activation view (the box *is*
+//                 the im2col slice: TH x TW pixels x 64 channels of one filter tap, zero-filled
+//                 outside the view, element-strided for stride-2 convolutions) and one 2-D box of
+//                 the weight slab, both landing in 128B-swizzled shared memory.
+//   warp 1      : TMEM allocation + single-thread tcgen05.mma issue (fp32 accumulators in TMEM),
+//                 tcgen05.commit releases pipeline stages and signals the epilogue.
+//   warps 2..5  : epilogue — tcgen05.ld the accumulator, optional bias/activation, InstanceNorm
+//                 partial statistics (warp-shuffle transpose-reduce per channel, one atomicAdd per
+//                 channel per CTA), vectorised NHWC store.
+//
+// Replaces (reference): nn.Conv2d / nn.ConvTranspose2d forward + cuDNN dgrad at
+// arch/ops.py:40-57,63,68; arch/generators.py:74-90; arch/discriminators.py:45-58, with
+// nn.ReflectionPad2d (ops.py:62,67; generators.py:73,84,89) folded into the operand view and the
+// statistics of nn.InstanceNorm2d (ops.py:11) fused into the epilogue.
+#include "sscg_common.cuh"
+
+namespace sscg {
+
+struct ConvDev {
+    int N, Ho, Wo;
+    int n_phases;
+    int phase_start[5];
+    SscgTap taps[SSCG_MAX_TAPS];
+    int stride, org_h, org_w;
+    int kcb;        // 64-wide K blocks per tap
+    int Co_pad;
+    int TH, TW, tw_shift;
+    int tiles_h, tiles_w;
+    void* y;
+    int y_fp32;
+    long long y_sN, y_sH, y_sW;
+    int y_oh, y_ow;
+    const float* bias;
+    int act;
+    float slope;
+    float* stats;
+};
+
+constexpr int kTileM = 128;
+constexpr int kABytes = kTileM * 128;   // 128 pixels x 64 bf16
+
+template <int BN, int SPLIT>
+struct IgemmCfg {
+    static constexpr int kPlanes = (SPLIT == 3) ? 2 : 1;
+    static constexpr int kBBytes = BN * 128;
+    static constexpr int kStageBytes = kPlanes * (kABytes + kBBytes);
+    static constexpr int kMaxStages = (200 * 1024) / kStageBytes;
+    static constexpr int kStages = kMaxStages > 6 ? 6 : kMaxStages;
+    static constexpr int kTmemCols = BN < 32 ? 32 : BN;
+    static constexpr int kStatBytes = 4 * BN * 2 * 4;
+    static constexpr int kSmemBytes = 1024 /*align slack*/ + kStages * kStageBytes + kStatBytes + 256;
+};
+
+template <int BN, int SPLIT>
+__global__ void __launch_bounds__(192, 1)
+conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
+                  const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo,
+                  const __grid_constant__ ConvDev p) {
+    using Cfg = IgemmCfg<BN, SPLIT>;
+    constexpr int kStages = Cfg::kStages;
+    constexpr int kPlanes = Cfg::kPlanes;
+
+    // ---- tile coordinates -------------------------------------------------------------------
+    const int phase = blockIdx.z;
+    const int os = (p.n_phases == 4) ? 2 : 1;
+    const int ph = (p.n_phases == 4) ? (phase >> 1) : 0;
+    const int pw = (p.n_phases == 4) ? (phase & 1) : 0;
+    const int Hph = (p.Ho - ph + os - 1) / os;
+    const int Wph = (p.Wo - pw + os - 1) / os;
+    int t = blockIdx.x;
+    const int tj = t % p.tiles_w; t /= p.tiles_w;
+    const int ti = t % p.tiles_h; t /= p.tiles_h;
+    const int n = t;
+    const int i0 = ti * p.TH, j0 = tj * p.TW;
+    if (i0 >= Hph || j0 >= Wph) return;   // whole CTA exits before touching barriers / TMEM
+    const int n0 = blockIdx.y * BN;
+    const int tap0 = p.phase_start[phase];
+    const int ntaps = p.phase_start[phase + 1] - tap0;
+    const int nkb = ntaps * p.kcb;
+
+    // ---- shared memory carve-up ----------------------------------------------------------------
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    float* s_stat = reinterpret_cast<float*>(smem + kStages * Cfg::kStageBytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes + Cfg::kStatBytes);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + kStages;
+    uint64_t* tmem_full_bar = bars + 2 * kStages;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        if (SPLIT == 3) { tma_prefetch_desc(&tmAlo); tma_prefetch_desc(&tmBlo); }
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(smem_u32(&full_bar[s]), 1);
+            mbar_init(smem_u32(&empty_bar[s]), 1);
+        }
+        mbar_init(smem_u32(tmem_full_bar), 1);
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(smem_u32(tmem_ptr_smem), Cfg::kTmemCols);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    if (warp == 0) {
+        // ================================ TMA producer ==========================================
+        if (lane == 0) {
+            int stage = 0; uint32_t par = 0;
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int tp = kb / p.kcb, cb = kb - tp * p.kcb;
+                const SscgTap tap = p.taps[tap0 + tp];
+                mbar_wait(smem_u32(&empty_bar[stage]), par ^ 1, 1);
+                const uint32_t fb = smem_u32(&full_bar[stage]);
+                mbar_arrive_expect_tx(fb, Cfg::kStageBytes);
+                uint8_t* st = smem + stage * Cfg::kStageBytes;
+                const int cw = j0 * p.stride + tap.dw + p.org_w;
+                const int ch = i0 * p.stride + tap.dh + p.org_h;
+                const int brow = tap.brow * p.Co_pad + n0;
+                tma_load_4d(smem_u32(st), &tmA, fb, cb * 64, cw, ch, n);
+                tma_load_2d(smem_u32(st + kPlanes * kABytes), &tmB, fb, cb * 64, brow);
+                if (SPLIT == 3) {
+                    tma_load_4d(smem_u32(st + kABytes), &tmAlo, fb, cb * 64, cw, ch, n);
+                    tma_load_2d(smem_u32(st + kPlanes * kABytes + Cfg::kBBytes), &tmBlo, fb, cb * 64, brow);
+                }
+                if (++stage == kStages) { stage = 0; par ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================ MMA issuer ============================================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(kTileM, BN < 16 ? 16 : BN, 0, 0);
+            int stage = 0; uint32_t par = 0;
+            uint32_t acc = 0;
+            for (int kb = 0; kb < nkb; ++kb) {
+                mbar_wait(smem_u32(&full_bar[stage]), par, 2);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+                const uint32_t sb = sa + kPlanes * kABytes;
+                const uint64_t da = make_smem_desc_sw128(sa, 0, 1024);
+                const uint64_t db = make_smem_desc_sw128(sb, 0, 1024);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {   // 4 x (K = 16) per 64-wide K block; +32 B per step
+                    umma_bf16(tmem_base, da + 2 * k, db + 2 * k, idesc, acc);
+                    acc = 1;
+                    if (SPLIT == 3) {
+                        const uint64_t dalo = make_smem_desc_sw128(sa + kABytes, 0, 1024);
+                        const uint64_t dblo = make_smem_desc_sw128(sb + Cfg::kBBytes, 0, 1024);
+                        umma_bf16(tmem_base, dalo + 2 * k, db + 2 * k, idesc, 1);
+                        umma_bf16(tmem_base, da + 2 * k, dblo + 2 * k, idesc, 1);
+                    }
+                }
+                umma_commit(smem_u32(&empty_bar[stage]));   // stage reusable once these MMAs retire
+                if (++stage == kStages) { stage = 0; par ^= 1; }
+            }
+            umma_commit(smem_u32(tmem_full_bar));           // accumulator complete
+        }
+    } else {
+        // ================================ epilogue ==============================================
+        const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
+        const int m = quad * 32 + lane;            // accumulator row = pixel within the tile
+        const int pi = m >> p.tw_shift, pj = m & (p.TW - 1);
+        const int i = i0 + pi, j = j0 + pj;
+        const bool valid = (i < Hph) && (j < Wph);
+        const int ho = i * os + ph, wo = j * os + pw;
+        const long long yoff = (long long)n * p.y_sN + (long long)(ho + p.y_oh) * p.y_sH +
+                               (long long)(wo + p.y_ow) * p.y_sW + n0;
+        mbar_wait(smem_u32(tmem_full_bar), 0, 3);
+        tc_fence_after();
+        constexpr int kChunks = (BN + 31) / 32;
+#pragma unroll 1
+        for (int c = 0; c < kChunks; ++c) {
+            uint32_t r[32];
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + c * 32;
+            if (BN >= 32) {
+                tmem_ld_32x32(taddr, r);
+            } else {
+                tmem_ld_32x16(taddr, r);
+#pragma unroll
+                for (int q = 16; q < 32; ++q) r[q] = 0;
+            }
+            tmem_ld_wait();
+            float v[32];
+#pragma unroll
+            for (int q = 0; q < 32; ++q) v[q] = __uint_as_float(r[q]);
+            if (p.bias != nullptr) {
+#pragma unroll
+                for (int q = 0; q < 32; ++q) v[q] += __ldg(p.bias + n0 + c * 32 + q);
+            }
+            if (p.act == SSCG_ACT_RELU) {
+#pragma unroll
+                for (int q = 0; q < 32; ++q) v[q] = fmaxf(v[q], 0.f);
+            } else if (p.act == SSCG_ACT_LRELU) {
+#pragma unroll
+                for (int q = 0; q < 32; ++q) v[q] = v[q] > 0.f ? v[q] : v[q] * p.slope;
+            } else if (p.act == SSCG_ACT_TANH) {
+#pragma unroll
+                for (int q = 0; q < 32; ++q) v[q] = tanhf(v[q]);
+            }
+            constexpr int kCols = BN >= 32 ? 32 : BN;
+            if (p.y_fp32) {
+                if (valid) {
+                    float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.y) + yoff + c * 32);
+#pragma unroll
+                    for (int q = 0; q < kCols / 4; ++q)
+                        dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                }
+            } else {
+                uint32_t pk[16];
+#pragma unroll
+                for (int q = 0; q < 16; ++q) pk[q] = pack_bf16x2(v[2 * q], v[2 * q + 1]);
+                if (valid) {
+                    uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.y) + yoff + c * 32);
+#pragma unroll
+                    for (int q = 0; q < kCols / 8; ++q)
+                        dst[q] = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+                }
+                if (p.stats != nullptr) {   // statistics of the values as stored
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) {
+                        v[2 * q] = __uint_as_float(pk[q] << 16);
+                        v[2 * q + 1] = __uint_as_float(pk[q] & 0xffff0000u);
+                    }
+                }
+            }
+            if (p.stats != nullptr) {
+                float s1[32], s2[32];
+#pragma unroll
+                for (int q = 0; q < 32; ++q) {
+                    const float x = valid ? v[q] : 0.f;
+                    s1[q] = x;
+                    s2[q] = x * x;
+                }
+                // transpose-reduce over the 32 lanes (pixels): lane L ends with column L's sum
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) {
+                    const bool up = (lane & off) != 0;
+#pragma unroll
+                    for (int q = 0; q < off; ++q) {
+                        const float send1 = up ? s1[q] : s1[q + off];
+                        const float keep1 = up ? s1[q + off] : s1[q];
+                        s1[q] = keep1 + __shfl_xor_sync(0xffffffffu, send1, off);
+                        const float send2 = up ? s2[q] : s2[q + off];
+                        const float keep2 = up ? s2[q + off] : s2[q];
+                        s2[q] = keep2 + __shfl_xor_sync(0xffffffffu, send2, off);
+                    }
+                }
+                const int col = c * 32 + lane;
+                if (col < BN) {
+                    s_stat[(quad * BN + col) * 2 + 0] = s1[0];
+                    s_stat[(quad * BN + col) * 2 + 1] = s2[0];
+                }
+            }
+        }
+        if (p.stats != nullptr) {
+            named_bar_sync(1, 128);
+            const int e = threadIdx.x - 64;   // 0..127
+            for (int col = e; col < BN; col += 128) {
+                float a = 0.f, b = 0.f;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    a += s_stat[(q * BN + col) * 2 + 0];
+                    b += s_stat[(q * BN + col) * 2 + 1];
+                }
+                float* dst = p.stats + ((long long)n * p.Co_pad + n0 + col) * 2;
+                atomicAdd(dst, a);
+                atomicAdd(dst + 1, b);
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+template <int BN, int SPLIT>
+static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmAlo, const CUtensorMap& tmB,
+                        const CUtensorMap& tmBlo, const ConvDev& d, dim3 grid, cudaStream_t stream) {
+    using Cfg = IgemmCfg<BN, SPLIT>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel<BN, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             Cfg::kSmemBytes);
+        if (e != cudaSuccess) return set_error("conv_igemm: cudaFuncSetAttribute(smem=%d): %s", Cfg::kSmemBytes,
+                                               cudaGetErrorString(e));
+        configured = true;
+    }
+    conv_igemm_kernel<BN, SPLIT><<<grid, 192, Cfg::kSmemBytes, stream>>>(tmA, tmAlo, tmB, tmBlo, d);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error("conv_igemm<%d,%d> launch: %s", BN, SPLIT, cudaGetErrorString(e));
+    return 0;
+}
+
+}  // namespace sscg
+
+using namespace sscg;
+
+extern "C" int sscg_conv_igemm(const SscgConvArgs* a, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (a->TH * a->TW != 128 || (a->TW & (a->TW - 1))) return set_error("conv_igemm: TH*TW must be 128, TW a power of two");
+    if (a->Kc % 64) return set_error("conv_igemm: Kc=%d must be a multiple of 64", a->Kc);   // x.C < Kc: zero-filled
+    if (a->stride != 1 && a->stride != 2) return set_error("conv_igemm: stride must be 1 or 2");
+    if (a->n_phases != 1 && a->n_phases != 4) return set_error("conv_igemm: n_phases must be 1 or 4");
+    if (a->Co_pad % a->BN) return set_error("conv_igemm: Co_pad=%d not a multiple of BN=%d", a->Co_pad, a->BN);
+    if (a->split != 1 && a->split != 3) return set_error("conv_igemm: split must be 1 or 3");
+    if (a->split == 3 && (!a->x_lo || !a->w_lo)) return set_error("conv_igemm: split=3 needs lo planes");
+    if (a->phase_start[a->n_phases] > SSCG_MAX_TAPS) return set_error("conv_igemm: too many taps");
+    if (a->stride * a->TW > 256 || a->stride * a->TH > 256) return set_error("conv_igemm: box too large");
+
+    CUtensorMap tmA, tmAlo, tmB, tmBlo;
+    const uint32_t boxA[4] = {64u, (uint32_t)(a->TW * a->stride), (uint32_t)(a->TH * a->stride), 1u};
+    const uint32_t esA[4] = {1u, (uint32_t)a->stride, (uint32_t)a->stride, 1u};
+    if (int rc = encode_view_4d(&tmA, a->x, a->x.ptr, boxA, esA)) return rc;
+    tmAlo = tmA;
+    if (a->split == 3)
+        if (int rc = encode_view_4d(&tmAlo, a->x, a->x_lo, boxA, esA)) return rc;
+    if (int rc = encode_2d(&tmB, a->w, a->Kc, a->w_rows, 64, a->BN)) return rc;
+    tmBlo = tmB;
+    if (a->split == 3)
+        if (int rc = encode_2d(&tmBlo, a->w_lo, a->Kc, a->w_rows, 64, a->BN)) return rc;
+
+    ConvDev d;
+    d.N = a->x.N; d.Ho = a->Ho; d.Wo = a->Wo;
+    d.n_phases = a->n_phases;
+    for (int i = 0; i < 5; ++i) d.phase_start[i] = a->phase_start[i];
+    for (int i = 0; i < SSCG_MAX_TAPS; ++i) d.taps[i] = a->taps[i];
+    d.stride = a->stride; d.org_h = a->org_h; d.org_w = a->org_w;
+    d.kcb = a->Kc / 64;
+    d.Co_pad = a->Co_pad;
+    d.TH = a->TH; d.TW = a->TW;
+    d.tw_shift = 0; while ((1 << d.tw_shift) < a->TW) ++d.tw_shift;
+    const int os = a->n_phases == 4 ? 2 : 1;
+    const int Hph = (a->Ho + os - 1) / os, Wph = (a->Wo + os - 1) / os;
+    d.tiles_h = (Hph + a->TH - 1) / a->TH;
+    d.tiles_w = (Wph + a->TW - 1) / a->TW;
+    d.y = a->y; d.y_fp32 = a->y_fp32;
+    d.y_sN = a->y_sN; d.y_sH = a->y_sH; d.y_sW = a->y_sW; d.y_oh = a->y_oh; d.y_ow = a->y_ow;
+    d.bias = a->bias; d.act = a->act; d.slope = a->slope; d.stats = a->stats;
+
+    dim3 grid((unsigned)(d.tiles_h * d.tiles_w * d.N), (unsigned)(a->Co_pad / a->BN), (unsigned)a->n_phases);
+#define SSCG_DISPATCH(BN_)                                                                       \
+    case BN_:                                                                                     \
+        return a->split == 3 ? launch_igemm<BN_, 3>(tmA, tmAlo, tmB, tmBlo, d, grid, stream)      \
+                             : launch_igemm<BN_, 1>(tmA, tmAlo, tmB, tmBlo, d, grid, stream);
+    switch (a->BN) {
+        SSCG_DISPATCH(16)
+        SSCG_DISPATCH(32)
+        SSCG_DISPATCH(64)
+        SSCG_DISPATCH(128)
+        SSCG_DISPATCH(256)
+        default: return set_error("conv_igemm: unsupported BN=%d", a->BN);
+    }
+#undef SSCG_DISPATCH
+}

@@ -1,0 +1,259 @@
+// conv_wgrad.cu — weight gradient of the convolutions as a pixel-contraction GEMM on tcgen05.
+//
+//   dWt[tap][co][k] += sum over pixels  dY[pixel][co] * X[pixel*stride + tap][k]
+//
+// GEMM view: M = output channels (128 per CTA), N = BN columns of the K axis of the weight slab,
+// contraction over pixels in blocks of 64.  Both operands are "MN-major" for the tensor core: a TMA
+// box of TH x TW pixels x 64 channels lands as 64 rows (pixels = GEMM-K) of 128 B (64 channels =
+// GEMM-M or -N), 128B-swizzled, which is exactly the canonical MN-major SWIZZLE_128B atom.
+// Split-K over (sample, pixel tile) ranges; partial sums are combined with red.global.add.f32.
+//
+// Replaces (reference): the cuDNN wgrad that autograd runs for every nn.Conv2d / ConvTranspose2d of
+// arch/ops.py:40-57,63,68, arch/generators.py:74-90, arch/discriminators.py:45-58 during
+// gen_loss.backward() / discriminator_loss.backward() (model.py:472,539).
+#include "sscg_common.cuh"
+
+namespace sscg {
+
+struct WgradDev {
+    int N;
+    int tiles_h, tiles_w;   // pixel blocks per sample
+    int TH, TW;
+    int stride, org_h, org_w;
+    SscgTap taps[SSCG_MAX_TAPS];
+    int Co_pad, Kc, n_ktiles;
+    int ksplit;
+    float* dw;
+};
+
+constexpr int kWgAtomBytes = 64 * 128;   // 64 pixels x 64 channels bf16
+
+template <int BN, int SPLIT>
+struct WgradCfg {
+    static constexpr int kPlanes = (SPLIT == 3) ? 2 : 1;
+    static constexpr int kAAtoms = 2;           // M = 128
+    static constexpr int kBAtoms = BN / 64;
+    static constexpr int kStageBytes = kPlanes * (kAAtoms + kBAtoms) * kWgAtomBytes;
+    static constexpr int kMaxStages = (200 * 1024) / kStageBytes;
+    static constexpr int kStages = kMaxStages > 6 ? 6 : kMaxStages;
+    static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + 256;
+};
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
+                 : "memory");
+}
+
+template <int BN, int SPLIT>
+__global__ void __launch_bounds__(192, 1)
+conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ CUtensorMap tmDyLo,
+                  const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmXLo,
+                  const __grid_constant__ WgradDev p) {
+    using Cfg = WgradCfg<BN, SPLIT>;
+    constexpr int kStages = Cfg::kStages;
+    constexpr int kPlanes = Cfg::kPlanes;
+    constexpr int kBAtoms = Cfg::kBAtoms;
+
+    const int split = blockIdx.x;
+    const int mt = blockIdx.y / p.n_ktiles;        // 128-wide output-channel tile
+    const int kt = blockIdx.y - mt * p.n_ktiles;   // BN-wide K tile
+    const SscgTap tap = p.taps[blockIdx.z];
+    const int m0 = mt * 128;
+    const int a_atoms = (p.Co_pad - m0) >= 128 ? 2 : 1;   // Co_pad is a multiple of 64
+
+    const int blocks_per_sample = p.tiles_h * p.tiles_w;
+    const int total_blocks = p.N * blocks_per_sample;
+    const int per = (total_blocks + p.ksplit - 1) / p.ksplit;
+    const int pb0 = split * per;
+    const int pb1 = min(total_blocks, pb0 + per);
+    if (pb0 >= pb1) return;
+    const int nkb = pb1 - pb0;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + kStages;
+    uint64_t* tmem_full_bar = bars + 2 * kStages;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmDy);
+        tma_prefetch_desc(&tmX);
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(smem_u32(&full_bar[s]), 1);
+            mbar_init(smem_u32(&empty_bar[s]), 1);
+        }
+        mbar_init(smem_u32(tmem_full_bar), 1);
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(smem_u32(tmem_ptr_smem), BN < 32 ? 32 : BN);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    // stage layout: [A hi atoms (2)] [B hi atoms] [A lo atoms (2)] [B lo atoms]
+    constexpr int kAOff = 0;
+    constexpr int kBOff = 2 * kWgAtomBytes;
+    constexpr int kLoOff = (2 + kBAtoms) * kWgAtomBytes;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0; uint32_t par = 0;
+            const uint32_t tx = kPlanes * (a_atoms + kBAtoms) * kWgAtomBytes;
+            for (int kb = 0; kb < nkb; ++kb) {
+                int b = pb0 + kb;
+                const int n = b / blocks_per_sample; b -= n * blocks_per_sample;
+                const int ti = b / p.tiles_w, tj = b - ti * p.tiles_w;
+                const int i0 = ti * p.TH, j0 = tj * p.TW;
+                mbar_wait(smem_u32(&empty_bar[stage]), par ^ 1, 4);
+                const uint32_t fb = smem_u32(&full_bar[stage]);
+                mbar_arrive_expect_tx(fb, tx);
+                uint8_t* st = smem + stage * Cfg::kStageBytes;
+                const int cw = j0 * p.stride + tap.dw + p.org_w;
+                const int ch = i0 * p.stride + tap.dh + p.org_h;
+                for (int a = 0; a < a_atoms; ++a)
+                    tma_load_4d(smem_u32(st + kAOff + a * kWgAtomBytes), &tmDy, fb, m0 + a * 64, j0, i0, n);
+#pragma unroll
+                for (int q = 0; q < kBAtoms; ++q)
+                    tma_load_4d(smem_u32(st + kBOff + q * kWgAtomBytes), &tmX, fb, kt * BN + q * 64, cw, ch, n);
+                if (SPLIT == 3) {
+                    for (int a = 0; a < a_atoms; ++a)
+                        tma_load_4d(smem_u32(st + kLoOff + kAOff + a * kWgAtomBytes), &tmDyLo, fb, m0 + a * 64, j0, i0, n);
+#pragma unroll
+                    for (int q = 0; q < kBAtoms; ++q)
+                        tma_load_4d(smem_u32(st + kLoOff + kBOff + q * kWgAtomBytes), &tmXLo, fb, kt * BN + q * 64, cw, ch, n);
+                }
+                if (++stage == kStages) { stage = 0; par ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(128, BN, 1, 1);
+            int stage = 0; uint32_t par = 0;
+            uint32_t acc = 0;
+            for (int kb = 0; kb < nkb; ++kb) {
+                mbar_wait(smem_u32(&full_bar[stage]), par, 5);
+                tc_fence_after();
+                const uint32_t st = smem_u32(smem + stage * Cfg::kStageBytes);
+                // MN-major: LBO = stride between 64-wide channel atoms, SBO = stride between 8-pixel groups
+                const uint64_t da = make_smem_desc_sw128(st + kAOff, kWgAtomBytes, 1024);
+                const uint64_t db = make_smem_desc_sw128(st + kBOff, kWgAtomBytes, 1024);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {   // 16 pixels per MMA: +2048 B
+                    umma_bf16(tmem_base, da + 128 * k, db + 128 * k, idesc, acc);
+                    acc = 1;
+                    if (SPLIT == 3) {
+                        const uint64_t dalo = make_smem_desc_sw128(st + kLoOff + kAOff, kWgAtomBytes, 1024);
+                        const uint64_t dblo = make_smem_desc_sw128(st + kLoOff + kBOff, kWgAtomBytes, 1024);
+                        umma_bf16(tmem_base, dalo + 128 * k, db + 128 * k, idesc, 1);
+                        umma_bf16(tmem_base, da + 128 * k, dblo + 128 * k, idesc, 1);
+                    }
+                }
+                umma_commit(smem_u32(&empty_bar[stage]));
+                if (++stage == kStages) { stage = 0; par ^= 1; }
+            }
+            umma_commit(smem_u32(tmem_full_bar));
+        }
+    } else {
+        const int quad = warp & 3;
+        const int m = quad * 32 + lane;
+        const int co = m0 + m;
+        const bool valid = (m < a_atoms * 64);
+        mbar_wait(smem_u32(tmem_full_bar), 0, 6);
+        tc_fence_after();
+        float* drow = p.dw + ((long long)tap.brow * p.Co_pad + co) * p.Kc + kt * BN;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+            uint32_t r[32];
+            tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + c * 32, r);
+            tmem_ld_wait();
+            if (valid) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    red_add_v4(drow + c * 32 + 4 * q, __uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
+                               __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, BN < 32 ? 32 : BN);
+    }
+}
+
+template <int BN, int SPLIT>
+static int launch_wgrad(const CUtensorMap& tmDy, const CUtensorMap& tmDyLo, const CUtensorMap& tmX,
+                        const CUtensorMap& tmXLo, const WgradDev& d, dim3 grid, cudaStream_t stream) {
+    using Cfg = WgradCfg<BN, SPLIT>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(conv_wgrad_kernel<BN, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             Cfg::kSmemBytes);
+        if (e != cudaSuccess) return set_error("conv_wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        configured = true;
+    }
+    conv_wgrad_kernel<BN, SPLIT><<<grid, 192, Cfg::kSmemBytes, stream>>>(tmDy, tmDyLo, tmX, tmXLo, d);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error("conv_wgrad<%d,%d> launch: %s", BN, SPLIT, cudaGetErrorString(e));
+    return 0;
+}
+
+}  // namespace sscg
+
+using namespace sscg;
+
+extern "C" int sscg_conv_wgrad(const SscgWgradArgs* a, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (a->TH * a->TW != 64) return set_error("conv_wgrad: TH*TW must be 64");
+    if (a->Kc % a->BN || a->BN % 64) return set_error("conv_wgrad: BN=%d must be a multiple of 64 dividing Kc=%d", a->BN, a->Kc);
+    if (a->Co_pad % 64) return set_error("conv_wgrad: Co_pad=%d must be a multiple of 64", a->Co_pad);
+    // dy.C < Co_pad and x.C < Kc are allowed: the TMA box zero-fills channels outside the view.
+    if (a->split == 3 && (!a->dy_lo || !a->x_lo)) return set_error("conv_wgrad: split=3 needs lo planes");
+    if (a->n_taps < 1 || a->n_taps > SSCG_MAX_TAPS) return set_error("conv_wgrad: bad n_taps");
+    if (a->ksplit < 1) return set_error("conv_wgrad: ksplit must be >= 1");
+
+    CUtensorMap tmDy, tmDyLo, tmX, tmXLo;
+    const uint32_t boxDy[4] = {64u, (uint32_t)a->TW, (uint32_t)a->TH, 1u};
+    const uint32_t es1[4] = {1u, 1u, 1u, 1u};
+    const uint32_t boxX[4] = {64u, (uint32_t)(a->TW * a->stride), (uint32_t)(a->TH * a->stride), 1u};
+    const uint32_t esX[4] = {1u, (uint32_t)a->stride, (uint32_t)a->stride, 1u};
+    if (int rc = encode_view_4d(&tmDy, a->dy, a->dy.ptr, boxDy, es1)) return rc;
+    if (int rc = encode_view_4d(&tmX, a->x, a->x.ptr, boxX, esX)) return rc;
+    tmDyLo = tmDy; tmXLo = tmX;
+    if (a->split == 3) {
+        if (int rc = encode_view_4d(&tmDyLo, a->dy, a->dy_lo, boxDy, es1)) return rc;
+        if (int rc = encode_view_4d(&tmXLo, a->x, a->x_lo, boxX, esX)) return rc;
+    }
+    WgradDev d;
+    d.N = a->dy.N;
+    d.TH = a->TH; d.TW = a->TW;
+    d.tiles_h = (a->dy.H + a->TH - 1) / a->TH;
+    d.tiles_w = (a->dy.W + a->TW - 1) / a->TW;
+    d.stride = a->stride; d.org_h = a->org_h; d.org_w = a->org_w;
+    for (int i = 0; i < SSCG_MAX_TAPS; ++i) d.taps[i] = a->taps[i];
+    d.Co_pad = a->Co_pad; d.Kc = a->Kc; d.n_ktiles = a->Kc / a->BN;
+    d.ksplit = a->ksplit; d.dw = a->dw;
+    const int m_tiles = (a->Co_pad + 127) / 128;
+    dim3 grid((unsigned)a->ksplit, (unsigned)(m_tiles * d.n_ktiles), (unsigned)a->n_taps);
+#define SSCG_WG(BN_)                                                                          \
+    case BN_:                                                                                  \
+        return a->split == 3 ? launch_wgrad<BN_, 3>(tmDy, tmDyLo, tmX, tmXLo, d, grid, stream) \
+                             : launch_wgrad<BN_, 1>(tmDy, tmDyLo, tmX, tmXLo, d, grid, stream);
+    switch (a->BN) {
+        SSCG_WG(64)
+        SSCG_WG(128)
+        SSCG_WG(256)
+        default: return set_error("conv_wgrad: unsupported BN=%d", a->BN);
+    }
+#undef SSCG_WG
+}

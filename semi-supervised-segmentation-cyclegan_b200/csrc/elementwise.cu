@@ -1,0 +1,521 @@
+// elementwise.cu — the HBM-bound passes around the tensor-core GEMMs: layout packing at the module
+// boundary, InstanceNorm apply (+activation, dropout, residual, halo write), the matching backward
+// reductions, and weight-slab preparation.  All of them move 16-byte (8 x bf16) vectors per thread
+// with the channel axis innermost, so a warp touches whole 128-byte lines.
+#include "sscg_common.cuh"
+
+namespace sscg {
+
+// ---------------------------------------------------------------------------------------------
+// small helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int reflect_idx(int q, int n) {   // torch ReflectionPad semantics
+    if (q < 0) q = -q;
+    if (q >= n) q = 2 * (n - 1) - q;
+    return q;
+}
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+// 8 keep-bits for the 8 channels of one vector; element id = vector index in the unpadded tensor
+__device__ __forceinline__ uint32_t drop_bits(uint64_t seed, uint64_t vec_index) {
+    return static_cast<uint32_t>(splitmix64(seed ^ (vec_index * 0xD1342543DE82EF95ull)) >> 24) & 0xffu;
+}
+__device__ __forceinline__ void load8(const void* base, bool fp32, long long off, float (&v)[8]) {
+    if (fp32) {
+        const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + off);
+        const float4 a = p[0], b = p[1];
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+        const uint4 u = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(base) + off);
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            v[2 * q] = __uint_as_float(w[q] << 16);
+            v[2 * q + 1] = __uint_as_float(w[q] & 0xffff0000u);
+        }
+    }
+}
+// bf16 hi (+ optional lo) planes
+__device__ __forceinline__ void load8_hilo(const void* hi, const void* lo, long long off, float (&v)[8]) {
+    load8(hi, false, off, v);
+    if (lo != nullptr) {
+        float l[8];
+        load8(lo, false, off, l);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] += l[q];
+    }
+}
+__device__ __forceinline__ void store8_bf16(void* hi, void* lo, long long off, const float (&v)[8]) {
+    uint32_t h[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) h[q] = pack_bf16x2(v[2 * q], v[2 * q + 1]);
+    *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(hi) + off) = make_uint4(h[0], h[1], h[2], h[3]);
+    if (lo != nullptr) {
+        uint32_t l[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float r0 = v[2 * q] - __uint_as_float(h[q] << 16);
+            const float r1 = v[2 * q + 1] - __uint_as_float(h[q] & 0xffff0000u);
+            l[q] = pack_bf16x2(r0, r1);
+        }
+        *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(lo) + off) = make_uint4(l[0], l[1], l[2], l[3]);
+    }
+}
+__device__ __forceinline__ void store8_f32(void* dst, long long off, const float (&v)[8]) {
+    float4* p = reinterpret_cast<float4*>(reinterpret_cast<float*>(dst) + off);
+    p[0] = make_float4(v[0], v[1], v[2], v[3]);
+    p[1] = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void load_norm(const float* stats, float eps, long long sidx, float inv_cnt, float (&mean)[8],
+                                          float (&rstd)[8]) {
+    const float4* sp = reinterpret_cast<const float4*>(stats + sidx * 2);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const float4 s = sp[q];
+        const float m0 = s.x * inv_cnt, m1 = s.z * inv_cnt;
+        mean[2 * q] = m0;
+        mean[2 * q + 1] = m1;
+        rstd[2 * q] = rsqrtf(fmaxf(s.y * inv_cnt - m0 * m0, 0.f) + eps);
+        rstd[2 * q + 1] = rsqrtf(fmaxf(s.w * inv_cnt - m1 * m1, 0.f) + eps);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// pack: NCHW fp32 (or int64 labels -> one-hot) -> NHWC bf16 with halo
+// ---------------------------------------------------------------------------------------------
+template <bool ONEHOT>
+__global__ void pack_kernel(const float* __restrict__ src, const long long* __restrict__ labels, int N, int C, int H,
+                            int W, __nv_bfloat16* __restrict__ dst, __nv_bfloat16* __restrict__ dst_lo, int Cp, int pad,
+                            int pad_mode) {
+    const int Hp = H + 2 * pad, Wp = W + 2 * pad;
+    const long long total = (long long)N * Hp * Wp;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int wp = idx % Wp;
+        const int hp = (idx / Wp) % Hp;
+        const int n = idx / ((long long)Wp * Hp);
+        int h = hp - pad, w = wp - pad;
+        bool zero = false;
+        if (pad_mode == SSCG_PAD_REFLECT) {
+            h = reflect_idx(h, H);
+            w = reflect_idx(w, W);
+        } else if (h < 0 || h >= H || w < 0 || w >= W) {
+            zero = true;
+        }
+        __nv_bfloat16* d = dst + idx * Cp;
+        __nv_bfloat16* dl = dst_lo ? dst_lo + idx * Cp : nullptr;
+        int lab = -1;
+        if (ONEHOT && !zero) lab = (int)labels[((long long)n * H + h) * W + w];
+        for (int c0 = 0; c0 < Cp; c0 += 8) {
+            float v[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int c = c0 + q;
+                float x = 0.f;
+                if (!zero && c < C) {
+                    if (ONEHOT) x = (c == lab) ? 1.f : 0.f;
+                    else x = src[(((long long)n * C + c) * H + h) * W + w];
+                }
+                v[q] = x;
+            }
+            store8_bf16(d, dl, c0, v);
+        }
+    }
+}
+
+__global__ void unpack_kernel(const float* __restrict__ src, int N, int C, int H, int W, int Cp,
+                              float* __restrict__ dst) {
+    const long long total = (long long)N * H * W;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int w = idx % W;
+        const int h = (idx / W) % H;
+        const int n = idx / ((long long)W * H);
+        const float* s = src + idx * Cp;
+        for (int c = 0; c < C; ++c) dst[(((long long)n * C + c) * H + h) * W + w] = s[c];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// InstanceNorm apply (+ act, dropout, residual) with halo write
+// ---------------------------------------------------------------------------------------------
+struct ApplyDev {
+    SscgApplyArgs a;
+    int CH;        // 8-channel vectors per pixel
+    int rows;      // pixels per pass per block
+    int iters;     // passes per block
+};
+
+__global__ void __launch_bounds__(256) in_apply_kernel(const __grid_constant__ ApplyDev p) {
+    const SscgApplyArgs& a = p.a;
+    const int n = blockIdx.y;
+    const int chunk = threadIdx.x % p.CH;
+    const int row = threadIdx.x / p.CH;
+    if (row >= p.rows) return;
+    const int Hp = a.H + 2 * a.pad, Wp = a.W + 2 * a.pad;
+    const int c0 = chunk * 8;
+    float mean[8], rstd[8];
+    if (a.stats != nullptr) {
+        load_norm(a.stats, a.eps, (long long)n * a.C + c0, 1.f / (float)(a.H * a.W), mean, rstd);
+    }
+    const long long npix = (long long)Hp * Wp;
+    long long pix = (long long)blockIdx.x * p.rows * p.iters + row;
+    for (int it = 0; it < p.iters; ++it, pix += p.rows) {
+        if (pix >= npix) break;
+        const int wp = pix % Wp, hp = pix / Wp;
+        int h = hp - a.pad, w = wp - a.pad;
+        const long long doff = (((long long)n * Hp + hp) * Wp + wp) * a.C + c0;
+        float v[8];
+        if (a.pad_mode == SSCG_PAD_REFLECT) {
+            h = reflect_idx(h, a.H);
+            w = reflect_idx(w, a.W);
+        } else if (h < 0 || h >= a.H || w < 0 || w >= a.W) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[q] = 0.f;
+            store8_bf16(a.dst, a.dst_lo, doff, v);
+            continue;
+        }
+        const long long spix = ((long long)n * a.H + h) * a.W + w;
+        load8(a.raw, a.raw_fp32 != 0, spix * a.C + c0, v);
+        if (a.stats != nullptr) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[q] = (v[q] - mean[q]) * rstd[q];
+        }
+        if (a.act == SSCG_ACT_RELU) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[q] = fmaxf(v[q], 0.f);
+        } else if (a.act == SSCG_ACT_LRELU) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[q] = v[q] > 0.f ? v[q] : v[q] * a.slope;
+        }
+        if (a.drop_seed != 0) {
+            const uint32_t bits = drop_bits(a.drop_seed, (unsigned long long)spix * p.CH + chunk);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[q] = ((bits >> q) & 1u) ? 2.f * v[q] : 0.f;
+        }
+        if (a.res.ptr != nullptr) {
+            float r[8];
+            load8_hilo(a.res.ptr, a.res_lo, (long long)n * a.res.sN + (long long)h * a.res.sH + (long long)w * a.res.sW + c0, r);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[q] += r[q];
+        }
+        store8_bf16(a.dst, a.dst_lo, doff, v);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward: dZ and the two per-plane reductions, then dRaw
+// ---------------------------------------------------------------------------------------------
+struct BwdDev {
+    SscgBwdArgs a;
+    void* draw; void* draw_lo;
+    int CH, rows, iters;
+};
+
+// positions of the padded gradient buffer that fold onto source index s (reflect) — at most 3
+__device__ __forceinline__ int fold_positions(int s, int n, int pad, int mode, int (&q)[3]) {
+    int cnt = 0;
+    q[cnt++] = s + pad;
+    if (mode == SSCG_PAD_REFLECT) {
+        if (s >= 1 && s <= pad) q[cnt++] = pad - s;
+        if (s <= n - 2 && s >= n - 1 - pad) q[cnt++] = pad + 2 * (n - 1) - s;
+    }
+    return cnt;
+}
+
+__global__ void __launch_bounds__(256) in_bwd_prep_kernel(const __grid_constant__ BwdDev p) {
+    const SscgBwdArgs& a = p.a;
+    __shared__ float s_red[256 * 2 + 16];
+    const int n = blockIdx.y;
+    const int chunk = threadIdx.x % p.CH;
+    const int row = threadIdx.x / p.CH;
+    const bool active = row < p.rows;
+    const int c0 = chunk * 8;
+    float mean[8], rstd[8];
+    const bool norm = a.stats != nullptr;
+    if (norm && active) load_norm(a.stats, a.eps, (long long)n * a.C + c0, 1.f / (float)(a.H * a.W), mean, rstd);
+    float acc1[8], acc2[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc1[q] = acc2[q] = 0.f;
+    const long long npix = (long long)a.H * a.W;
+    long long pix = (long long)blockIdx.x * p.rows * p.iters + row;
+    if (active) {
+        for (int it = 0; it < p.iters; ++it, pix += p.rows) {
+            if (pix >= npix) break;
+            const int w = pix % a.W, h = pix / a.W;
+            const long long spix = (long long)n * npix + pix;
+            float g[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) g[q] = 0.f;
+            if (a.dyp.ptr != nullptr) {
+                int hq[3], wq[3];
+                const int nh = fold_positions(h, a.H, a.pad, a.pad_mode, hq);
+                const int nw = fold_positions(w, a.W, a.pad, a.pad_mode, wq);
+                for (int x = 0; x < nh; ++x)
+                    for (int y = 0; y < nw; ++y) {
+                        float t[8];
+                        load8(a.dyp.ptr, a.dyp_fp32 != 0,
+                              (long long)n * a.dyp.sN + (long long)hq[x] * a.dyp.sH + (long long)wq[y] * a.dyp.sW + c0, t);
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) g[q] += t[q];
+                    }
+            }
+            if (a.skip.ptr != nullptr) {
+                float t[8];
+                load8(a.skip.ptr, a.skip_fp32 != 0,
+                      (long long)n * a.skip.sN + (long long)h * a.skip.sH + (long long)w * a.skip.sW + c0, t);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) g[q] += t[q];
+            }
+            const long long off = spix * a.C + c0;
+            if (a.g_out != nullptr) {
+                if (a.g_fp32) store8_f32(a.g_out, off, g);
+                else store8_bf16(a.g_out, nullptr, off, g);
+            }
+            if (a.drop_seed != 0) {
+                const uint32_t bits = drop_bits(a.drop_seed, (unsigned long long)spix * p.CH + chunk);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) g[q] = ((bits >> q) & 1u) ? 2.f * g[q] : 0.f;
+            }
+            float z[8];
+            if (norm || a.act != SSCG_ACT_NONE) {
+                load8(a.raw, a.raw_fp32 != 0, off, z);
+                if (norm) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) z[q] = (z[q] - mean[q]) * rstd[q];
+                }
+                if (a.act == SSCG_ACT_RELU) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) g[q] = z[q] > 0.f ? g[q] : 0.f;
+                } else if (a.act == SSCG_ACT_LRELU) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) g[q] = z[q] > 0.f ? g[q] : g[q] * a.slope;
+                } else if (a.act == SSCG_ACT_TANH) {   // raw holds y = tanh(.)
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) g[q] = g[q] * (1.f - z[q] * z[q]);
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) z[q] = 0.f;
+            }
+            if (a.dz_fp32) store8_f32(a.dz, off, g);
+            else store8_bf16(a.dz, a.dz_lo, off, g);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                acc1[q] += g[q];
+                acc2[q] += g[q] * z[q];
+            }
+        }
+    }
+    if (a.bstats == nullptr) return;
+    // block reduction over the pixel rows that share a channel vector, then one atomic per channel
+    for (int q = 0; q < 8; ++q) {
+        __syncthreads();
+        s_red[threadIdx.x * 2] = active ? acc1[q] : 0.f;
+        s_red[threadIdx.x * 2 + 1] = active ? acc2[q] : 0.f;
+        __syncthreads();
+        if (threadIdx.x < p.CH) {
+            float s1 = 0.f, s2 = 0.f;
+            for (int r = 0; r < p.rows; ++r) {
+                s1 += s_red[(r * p.CH + threadIdx.x) * 2];
+                s2 += s_red[(r * p.CH + threadIdx.x) * 2 + 1];
+            }
+            float* dst = a.bstats + ((long long)n * a.C + threadIdx.x * 8 + q) * 2;
+            atomicAdd(dst, s1);
+            atomicAdd(dst + 1, s2);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) in_bwd_apply_kernel(const __grid_constant__ BwdDev p) {
+    const SscgBwdArgs& a = p.a;
+    const int n = blockIdx.y;
+    const int chunk = threadIdx.x % p.CH;
+    const int row = threadIdx.x / p.CH;
+    if (row >= p.rows) return;
+    const int c0 = chunk * 8;
+    const float inv_cnt = 1.f / (float)(a.H * a.W);
+    float mean[8], rstd[8], m1[8], m2[8];
+    load_norm(a.stats, a.eps, (long long)n * a.C + c0, inv_cnt, mean, rstd);
+    {
+        const float4* bp = reinterpret_cast<const float4*>(a.bstats + ((long long)n * a.C + c0) * 2);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float4 s = bp[q];
+            m1[2 * q] = s.x * inv_cnt; m2[2 * q] = s.y * inv_cnt;
+            m1[2 * q + 1] = s.z * inv_cnt; m2[2 * q + 1] = s.w * inv_cnt;
+        }
+    }
+    const long long npix = (long long)a.H * a.W;
+    long long pix = (long long)blockIdx.x * p.rows * p.iters + row;
+    for (int it = 0; it < p.iters; ++it, pix += p.rows) {
+        if (pix >= npix) break;
+        const long long off = ((long long)n * npix + pix) * a.C + c0;
+        float z[8], g[8];
+        load8(a.raw, a.raw_fp32 != 0, off, z);
+        load8(a.dz, a.dz_fp32 != 0, off, g);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const float zz = (z[q] - mean[q]) * rstd[q];
+            g[q] = rstd[q] * (g[q] - m1[q] - zz * m2[q]);
+        }
+        store8_bf16(p.draw, p.draw_lo, off, g);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight slabs
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ long long wslab_src_index(const SscgWprepArgs& a, int t, int r, int k) {
+    int co, ci, kh, kw;
+    if (a.mode == 1) {
+        kh = t; kw = k / a.Cp; ci = k - kw * a.Cp; co = r;
+        if (kw >= a.KW) return -1;
+    } else {
+        kh = t / a.KW; kw = t - kh * a.KW;
+        if (a.mode == 0) { co = r; ci = k; } else { ci = r; co = k; }
+    }
+    if (co >= a.Co || ci >= a.Ci) return -1;
+    return a.transposed ? ((((long long)ci * a.Co + co) * a.KH + kh) * a.KW + kw)
+                        : ((((long long)co * a.Ci + ci) * a.KH + kh) * a.KW + kw);
+}
+__device__ __forceinline__ int wslab_ntaps(const SscgWprepArgs& a) { return a.mode == 1 ? a.KH : a.KH * a.KW; }
+
+__global__ void wprep_kernel(const __grid_constant__ SscgWprepArgs a) {
+    const long long total = (long long)wslab_ntaps(a) * a.rows_pad * a.Kc;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int k = idx % a.Kc;
+        const int r = (idx / a.Kc) % a.rows_pad;
+        const int t = idx / ((long long)a.Kc * a.rows_pad);
+        const long long s = wslab_src_index(a, t, r, k);
+        const float v = s >= 0 ? a.w[s] : 0.f;
+        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        reinterpret_cast<__nv_bfloat16*>(a.dst)[idx] = h;
+        if (a.dst_lo != nullptr)
+            reinterpret_cast<__nv_bfloat16*>(a.dst_lo)[idx] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
+}
+
+__global__ void wgrad_unpack_kernel(const __grid_constant__ SscgWprepArgs a, const float* __restrict__ slab,
+                                    float* __restrict__ grad, float scale) {
+    const long long total = (long long)wslab_ntaps(a) * a.rows_pad * a.Kc;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int k = idx % a.Kc;
+        const int r = (idx / a.Kc) % a.rows_pad;
+        const int t = idx / ((long long)a.Kc * a.rows_pad);
+        const long long s = wslab_src_index(a, t, r, k);
+        if (s >= 0) grad[s] += scale * slab[idx];
+    }
+}
+
+static inline int ew_grid(long long total, int block) {
+    long long g = (total + block - 1) / block;
+    if (g > 148 * 16) g = 148 * 16;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+// rows/iters choice for the (C/8)-vector x pixel-row block layout
+static void vec_layout(int C, long long npix, int& CH, int& rows, int& iters, int& gridx) {
+    CH = C / 8;
+    rows = 256 / CH;
+    if (rows < 1) rows = 1;
+    iters = 8;
+    long long per_block = (long long)rows * iters;
+    gridx = (int)((npix + per_block - 1) / per_block);
+    if (gridx < 1) gridx = 1;
+}
+
+}  // namespace sscg
+
+using namespace sscg;
+
+#define SSCG_CHECK_LAUNCH(name)                                                             \
+    do {                                                                                    \
+        cudaError_t e_ = cudaGetLastError();                                                \
+        if (e_ != cudaSuccess) return set_error(name " launch: %s", cudaGetErrorString(e_)); \
+    } while (0)
+
+extern "C" int sscg_pack_nchw(const float* src, int32_t N, int32_t C, int32_t H, int32_t W, void* dst, void* dst_lo,
+                              int32_t Cp, int32_t pad, int32_t pad_mode, void* stream) {
+    if (Cp % 8 || Cp < C) return set_error("pack_nchw: Cp=%d must be a multiple of 8 and >= C=%d", Cp, C);
+    const long long total = (long long)N * (H + 2 * pad) * (W + 2 * pad);
+    pack_kernel<false><<<ew_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        src, nullptr, N, C, H, W, reinterpret_cast<__nv_bfloat16*>(dst), reinterpret_cast<__nv_bfloat16*>(dst_lo), Cp, pad,
+        pad_mode);
+    SSCG_CHECK_LAUNCH("pack_nchw");
+    return 0;
+}
+
+extern "C" int sscg_onehot_pack(const int64_t* labels, int32_t N, int32_t C, int32_t H, int32_t W, void* dst,
+                                void* dst_lo, int32_t Cp, int32_t pad, int32_t pad_mode, void* stream) {
+    if (Cp % 8 || Cp < C) return set_error("onehot_pack: Cp=%d must be a multiple of 8 and >= C=%d", Cp, C);
+    const long long total = (long long)N * (H + 2 * pad) * (W + 2 * pad);
+    pack_kernel<true><<<ew_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        nullptr, reinterpret_cast<const long long*>(labels), N, C, H, W, reinterpret_cast<__nv_bfloat16*>(dst),
+        reinterpret_cast<__nv_bfloat16*>(dst_lo), Cp, pad, pad_mode);
+    SSCG_CHECK_LAUNCH("onehot_pack");
+    return 0;
+}
+
+extern "C" int sscg_unpack_nhwc(const float* src, int32_t N, int32_t C, int32_t H, int32_t W, int32_t Cp, float* dst,
+                                void* stream) {
+    const long long total = (long long)N * H * W;
+    unpack_kernel<<<ew_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, N, C, H, W, Cp, dst);
+    SSCG_CHECK_LAUNCH("unpack_nhwc");
+    return 0;
+}
+
+extern "C" int sscg_in_apply(const SscgApplyArgs* a, void* stream) {
+    if (a->C % 8 || a->C > 2048) return set_error("in_apply: C=%d must be a multiple of 8 (<= 2048)", a->C);
+    ApplyDev d;
+    d.a = *a;
+    int gridx;
+    vec_layout(a->C, (long long)(a->H + 2 * a->pad) * (a->W + 2 * a->pad), d.CH, d.rows, d.iters, gridx);
+    in_apply_kernel<<<dim3(gridx, a->N), 256, 0, static_cast<cudaStream_t>(stream)>>>(d);
+    SSCG_CHECK_LAUNCH("in_apply");
+    return 0;
+}
+
+extern "C" int sscg_in_bwd_prep(const SscgBwdArgs* a, void* stream) {
+    if (a->C % 8 || a->C > 2048) return set_error("in_bwd_prep: C=%d must be a multiple of 8 (<= 2048)", a->C);
+    BwdDev d;
+    d.a = *a; d.draw = nullptr; d.draw_lo = nullptr;
+    int gridx;
+    vec_layout(a->C, (long long)a->H * a->W, d.CH, d.rows, d.iters, gridx);
+    in_bwd_prep_kernel<<<dim3(gridx, a->N), 256, 0, static_cast<cudaStream_t>(stream)>>>(d);
+    SSCG_CHECK_LAUNCH("in_bwd_prep");
+    return 0;
+}
+
+extern "C" int sscg_in_bwd_apply(const SscgBwdArgs* a, void* draw, void* draw_lo, void* stream) {
+    if (a->C % 8 || a->C > 2048) return set_error("in_bwd_apply: C=%d must be a multiple of 8 (<= 2048)", a->C);
+    if (!a->stats || !a->bstats) return set_error("in_bwd_apply: needs stats and bstats");
+    BwdDev d;
+    d.a = *a; d.draw = draw; d.draw_lo = draw_lo;
+    int gridx;
+    vec_layout(a->C, (long long)a->H * a->W, d.CH, d.rows, d.iters, gridx);
+    in_bwd_apply_kernel<<<dim3(gridx, a->N), 256, 0, static_cast<cudaStream_t>(stream)>>>(d);
+    SSCG_CHECK_LAUNCH("in_bwd_apply");
+    return 0;
+}
+
+extern "C" int sscg_wprep(const SscgWprepArgs* a, void* stream) {
+    const long long total = (long long)(a->mode == 1 ? a->KH : a->KH * a->KW) * a->rows_pad * a->Kc;
+    wprep_kernel<<<ew_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(*a);
+    SSCG_CHECK_LAUNCH("wprep");
+    return 0;
+}
+
+extern "C" int sscg_wgrad_unpack(const SscgWprepArgs* a, const float* slab, float* grad, float scale, void* stream) {
+    const long long total = (long long)(a->mode == 1 ? a->KH : a->KH * a->KW) * a->rows_pad * a->Kc;
+    wgrad_unpack_kernel<<<ew_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(*a, slab, grad, scale);
+    SSCG_CHECK_LAUNCH("wgrad_unpack");
+    return 0;
+}

@@ -1,0 +1,200 @@
+"""Host-side builders for the C-ABI argument blocks, plus thin launch wrappers.
+
+torch is used here only for device memory (tensor.data_ptr()) and the current stream; every
+arithmetic kernel lives in libsscg_b200.so.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+from .geometry import TapTable, pick_tile
+
+SLACK = 1024  # zeroed elements appended to every activation buffer (window reads run past the end)
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t, byte_off=0):
+    if t is None:
+        return None
+    return t.data_ptr() + byte_off
+
+
+class ActBuf:
+    """NHWC activation buffer [N][H+2*pad][W+2*pad][C] (bf16 hi plane, optional lo plane, or fp32)."""
+
+    def __init__(self, N, H, W, Cc, pad=0, device="cuda", split=False, fp32=False):
+        self.N, self.H, self.W, self.C, self.pad = N, H, W, Cc, pad
+        self.Hp, self.Wp = H + 2 * pad, W + 2 * pad
+        self.fp32 = fp32
+        n = N * self.Hp * self.Wp * Cc + SLACK
+        dt = torch.float32 if fp32 else torch.bfloat16
+        self.hi = torch.zeros(n, dtype=dt, device=device)
+        self.lo = torch.zeros(n, dtype=dt, device=device) if (split and not fp32) else None
+        self.esize = 4 if fp32 else 2
+
+    # element strides
+    @property
+    def sW(self):
+        return self.C
+
+    @property
+    def sH(self):
+        return self.Wp * self.C
+
+    @property
+    def sN(self):
+        return self.Hp * self.Wp * self.C
+
+    def _off(self, interior):
+        return (self.pad * self.sH + self.pad * self.sW) * self.esize if interior else 0
+
+    def view(self, interior=False, lo=False):
+        """Full (padded extents) or interior (H x W extents, zero fill outside) view."""
+        t = self.lo if lo else self.hi
+        H, W = (self.H, self.W) if interior else (self.Hp, self.Wp)
+        return L.make_view(_ptr(t, self._off(interior)), self.N, H, W, self.C, self.sN, self.sH, self.sW)
+
+    def lo_ptr(self, interior=False):
+        return _ptr(self.lo, self._off(interior)) if self.lo is not None else None
+
+    def window_view(self, kwpad, lo=False):
+        """Row-window view over the padded buffer: inner extent = kwpad contiguous (kw, c) elements."""
+        t = self.lo if lo else self.hi
+        return L.make_view(_ptr(t), self.N, self.Hp, self.Wp, kwpad, self.sN, self.sH, self.sW)
+
+    def as_nhwc(self, interior=True):
+        """torch view [N, H(p), W(p), C] of the hi plane (tests / debugging)."""
+        t = self.hi[: self.N * self.Hp * self.Wp * self.C].view(self.N, self.Hp, self.Wp, self.C)
+        if interior and self.pad:
+            t = t[:, self.pad:self.pad + self.H, self.pad:self.pad + self.W, :]
+        return t
+
+    def as_nhwc_f32(self, interior=True):
+        t = self.as_nhwc(interior).float()
+        if self.lo is not None:
+            l = self.lo[: self.N * self.Hp * self.Wp * self.C].view(self.N, self.Hp, self.Wp, self.C)
+            if interior and self.pad:
+                l = l[:, self.pad:self.pad + self.H, self.pad:self.pad + self.W, :]
+            t = t + l.float()
+        return t
+
+
+def fill_taps(dst_taps, table: TapTable):
+    assert len(table.taps) <= L.SSCG_MAX_TAPS, "too many taps"
+    for i, (dh, dw, brow) in enumerate(table.taps):
+        dst_taps[i].dh, dst_taps[i].dw, dst_taps[i].brow = dh, dw, brow
+
+
+def conv_args(xview, x_lo, table: TapTable, Kc, w, w_lo, w_rows, Co_pad, y_ptr, y_fp32, y_strides, y_off, Ho, Wo,
+              bias=None, act=L.ACT_NONE, slope=0.2, stats=None, BN=None, tile=None, split=1):
+    a = L.ConvArgs()
+    a.x = xview
+    a.x_lo = x_lo
+    a.stride, a.Kc, a.org_h, a.org_w = table.stride, Kc, table.org_h, table.org_w
+    a.n_phases = table.n_phases
+    for i in range(5):
+        a.phase_start[i] = table.phase_start[i]
+    fill_taps(a.taps, table)
+    a.w, a.w_lo, a.w_rows, a.Co_pad = _ptr(w), _ptr(w_lo), w_rows, Co_pad
+    a.split = split
+    a.y, a.y_fp32 = y_ptr, 1 if y_fp32 else 0
+    a.y_sN, a.y_sH, a.y_sW = y_strides
+    a.y_oh, a.y_ow = y_off
+    a.Ho, a.Wo = Ho, Wo
+    a.bias = _ptr(bias)
+    a.act, a.slope = act, slope
+    a.stats = _ptr(stats)
+    if tile is None:
+        w_phase = (Wo + 1) // 2 if table.n_phases == 4 else Wo
+        tile = pick_tile(w_phase, 128)
+    a.TH, a.TW = tile
+    a.BN = BN if BN is not None else (Co_pad if Co_pad <= 256 else 256)
+    return a
+
+
+def wgrad_args(dyview, dy_lo, xview, x_lo, table: TapTable, Kc, Co_pad, dw, w_rows, BN=None, tile=None, ksplit=None,
+               split=1):
+    assert table.n_phases == 1
+    a = L.WgradArgs()
+    a.dy, a.dy_lo, a.x, a.x_lo = dyview, dy_lo, xview, x_lo
+    a.stride, a.Kc, a.org_h, a.org_w = table.stride, Kc, table.org_h, table.org_w
+    a.n_taps = len(table.taps)
+    fill_taps(a.taps, table)
+    a.Co_pad, a.split = Co_pad, split
+    a.dw, a.w_rows = _ptr(dw), w_rows
+    if tile is None:
+        tile = pick_tile(dyview.W, 64)
+    a.TH, a.TW = tile
+    if BN is None:
+        BN = 256 if Kc % 256 == 0 else (128 if Kc % 128 == 0 else 64)
+    a.BN = BN
+    if ksplit is None:
+        blocks = dyview.N * ((dyview.H + a.TH - 1) // a.TH) * ((dyview.W + a.TW - 1) // a.TW)
+        ctas = len(table.taps) * ((Co_pad + 127) // 128) * (Kc // BN)
+        ksplit = max(1, min(blocks, (148 * 2 + ctas - 1) // ctas))
+    a.ksplit = ksplit
+    return a
+
+
+def run_conv(a):
+    L.check(L.lib().sscg_conv_igemm(C.byref(a), _stream()), "sscg_conv_igemm")
+
+
+def run_wgrad(a):
+    L.check(L.lib().sscg_conv_wgrad(C.byref(a), _stream()), "sscg_conv_wgrad")
+
+
+def run_apply(a):
+    L.check(L.lib().sscg_in_apply(C.byref(a), _stream()), "sscg_in_apply")
+
+
+def run_bwd_prep(a):
+    L.check(L.lib().sscg_in_bwd_prep(C.byref(a), _stream()), "sscg_in_bwd_prep")
+
+
+def run_bwd_apply(a, draw, draw_lo=None):
+    L.check(L.lib().sscg_in_bwd_apply(C.byref(a), _ptr(draw), _ptr(draw_lo), _stream()), "sscg_in_bwd_apply")
+
+
+def wprep_args(w, transposed, Co, Ci, KH, KW, mode, Cp, rows_pad, Kc, dst, dst_lo=None):
+    a = L.WprepArgs()
+    a.w, a.transposed = _ptr(w), 1 if transposed else 0
+    a.Co, a.Ci, a.KH, a.KW = Co, Ci, KH, KW
+    a.mode, a.Cp, a.rows_pad, a.Kc = mode, Cp, rows_pad, Kc
+    a.dst, a.dst_lo = _ptr(dst), _ptr(dst_lo)
+    return a
+
+
+def run_wprep(a):
+    L.check(L.lib().sscg_wprep(C.byref(a), _stream()), "sscg_wprep")
+
+
+def run_wgrad_unpack(a, slab, grad, scale=1.0):
+    L.check(L.lib().sscg_wgrad_unpack(C.byref(a), _ptr(slab), _ptr(grad), C.c_float(scale), _stream()),
+            "sscg_wgrad_unpack")
+
+
+def pack_nchw(src, dst: ActBuf, pad_mode):
+    N, Cc, H, W = src.shape
+    assert src.dtype == torch.float32 and src.is_contiguous()
+    L.check(L.lib().sscg_pack_nchw(_ptr(src), N, Cc, H, W, _ptr(dst.hi), _ptr(dst.lo), dst.C, dst.pad, pad_mode,
+                                   _stream()), "sscg_pack_nchw")
+
+
+def onehot_pack(labels, Cc, dst: ActBuf, pad_mode):
+    N, one, H, W = labels.shape
+    assert labels.dtype == torch.int64 and labels.is_contiguous() and one == 1
+    L.check(L.lib().sscg_onehot_pack(_ptr(labels), N, Cc, H, W, _ptr(dst.hi), _ptr(dst.lo), dst.C, dst.pad, pad_mode,
+                                     _stream()), "sscg_onehot_pack")
+
+
+def unpack_nhwc(src_f32, N, Cc, H, W, Cp, dst):
+    L.check(L.lib().sscg_unpack_nhwc(_ptr(src_f32), N, Cc, H, W, Cp, _ptr(dst), _stream()), "sscg_unpack_nhwc")
+
+
+def device_error():
+    return L.lib().sscg_device_error()

@@ -1,0 +1,421 @@
+"""Kernel-level parity cases: each function runs one C-ABI kernel configuration on cuda:0 and returns
+(max_abs_err, ref_scale, tolerance) against a plain PyTorch fp32 computation of the same operator
+(TF32 disabled) on the same bf16-rounded operands.  Used by tests/test_kernels_gpu.py and by
+tools/kernel_probe.py (which isolates every case in a subprocess so a trap cannot hide the rest).
+"""
+import torch
+import torch.nn.functional as F
+
+import sscg_b200  # noqa: F401
+from sscg_b200 import _lib as L
+from sscg_b200 import geometry as G
+from sscg_b200 import kernels as K
+
+DEV = "cuda"
+
+
+def _setup():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(1234)
+
+
+def _bf(x):
+    return x.to(torch.bfloat16).float()
+
+
+def _fill_act(buf: K.ActBuf, x_nchw, pad_mode):
+    """Write an NCHW fp32 tensor (already bf16-representable) into buf with halo (torch side)."""
+    N, Cc, H, W = x_nchw.shape
+    p = buf.pad
+    if p:
+        mode = "reflect" if pad_mode == L.PAD_REFLECT else "constant"
+        xp = F.pad(x_nchw, (p, p, p, p), mode=mode)
+    else:
+        xp = x_nchw
+    t = torch.zeros(N, buf.Hp, buf.Wp, buf.C, device=DEV)
+    t[..., :Cc] = xp.permute(0, 2, 3, 1)
+    buf.hi[: t.numel()].copy_(t.reshape(-1).to(torch.bfloat16))
+
+
+def _wslab(w, transposed, mode, Cp, rows_pad, Kc, KH, KW, Co, Ci, split=False):
+    ntaps = KH if mode == 1 else KH * KW
+    dst = torch.zeros(ntaps * rows_pad * Kc, dtype=torch.bfloat16, device=DEV)
+    dst_lo = torch.zeros_like(dst) if split else None
+    a = K.wprep_args(w, transposed, Co, Ci, KH, KW, mode, Cp, rows_pad, Kc, dst, dst_lo)
+    K.run_wprep(a)
+    return dst, dst_lo, a
+
+
+def _result(got, ref, tol):
+    err = (got - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    return err, scale, tol
+
+
+# ------------------------------------------------------------------------------------------------
+def case_conv_fwd(N=2, H=16, W=16, Cin=64, Cout=64, k=3, stride=1, pad=1, reflect=True, explicit=True,
+                  out_fp32=True, bias=False, act=L.ACT_NONE, stats=False, split=1):
+    """Conv2d forward, regular mode. explicit=True: halo materialised in the buffer (org 0);
+    explicit=False: interior view + zero fill (org = -pad)."""
+    _setup()
+    x = torch.randn(N, Cin, H, W, device=DEV)
+    w = torch.randn(Cout, Cin, k, k, device=DEV) * 0.05
+    b = torch.randn(Cout, device=DEV) if bias else None
+    if split == 1:
+        x, w = _bf(x), _bf(w)
+    Cp = G.pad_in_channels(Cin)
+    Kc = G.round_up(Cp, 64)
+    Co_pad = G.pad_out_channels(Cout)
+    buf = K.ActBuf(N, H, W, Cp, pad if explicit else 0, DEV, split=(split == 3))
+    if split == 3:
+        K.pack_nchw(x.contiguous(), buf, L.PAD_REFLECT if reflect else L.PAD_ZERO)
+    else:
+        _fill_act(buf, x, L.PAD_REFLECT if reflect else L.PAD_ZERO)
+    slab, slab_lo, _ = _wslab(w, False, 0, 0, Co_pad, Kc, k, k, Cout, Cin, split == 3)
+    Ho, Wo = G.conv_out(H, k, stride, pad), G.conv_out(W, k, stride, pad)
+    y = torch.zeros(N, Ho, Wo, Co_pad, device=DEV, dtype=torch.float32 if out_fp32 else torch.bfloat16)
+    st = torch.zeros(N, Co_pad, 2, device=DEV) if stats else None
+    bias_pad = None
+    if bias:
+        bias_pad = torch.zeros(Co_pad, device=DEV)
+        bias_pad[:Cout] = b
+    table = G.taps_conv_fwd(k, k, stride, 0 if explicit else -pad)
+    view = buf.view(interior=False) if explicit else buf.view(interior=True)
+    a = K.conv_args(view, buf.lo_ptr(interior=not explicit), table, Kc, slab, slab_lo, k * k * Co_pad, Co_pad,
+                    y.data_ptr(), out_fp32, (Ho * Wo * Co_pad, Wo * Co_pad, Co_pad), (0, 0), Ho, Wo, bias=bias_pad,
+                    act=act, stats=st, split=split)
+    K.run_conv(a)
+    torch.cuda.synchronize()
+    xp = F.pad(x, (pad,) * 4, mode="reflect" if reflect else "constant") if pad else x
+    ref = F.conv2d(xp, w, b, stride=stride)
+    if act == L.ACT_RELU:
+        ref = F.relu(ref)
+    elif act == L.ACT_LRELU:
+        ref = F.leaky_relu(ref, 0.2)
+    elif act == L.ACT_TANH:
+        ref = torch.tanh(ref)
+    got = y.float()[..., :Cout].permute(0, 3, 1, 2)
+    err, scale, tol = _result(got, ref, 2e-4)
+    if not out_fp32:
+        tol = scale * 2.0 ** -8     # one bf16 rounding of the stored value
+    if split == 3:
+        tol = 1e-4
+    if stats:
+        src = got if out_fp32 else got
+        s1 = src.sum(dim=(2, 3))
+        s2 = (src * src).sum(dim=(2, 3))
+        e1 = (st[:, :Cout, 0] - s1).abs().max().item() / max(1.0, s1.abs().max().item())
+        e2 = (st[:, :Cout, 1] - s2).abs().max().item() / max(1.0, s2.abs().max().item())
+        err = max(err, e1 * scale, e2 * scale)
+    return err, scale, tol
+
+
+def case_conv_window(N=2, H=16, W=16, Cin=3, Cout=64, k=7, stride=1, pad=3, reflect=True):
+    """Row-window mode (small Cin): stem 7x7 / PatchGAN 4x4 s2 first layer."""
+    _setup()
+    x = _bf(torch.randn(N, Cin, H, W, device=DEV))
+    w = _bf(torch.randn(Cout, Cin, k, k, device=DEV) * 0.05)
+    Cp = G.pad_in_channels(Cin)
+    if k * Cp <= 64 and 64 % Cp == 0:
+        pass
+    kwpad = G.round_up(k * Cp, 64)
+    Co_pad = G.pad_out_channels(Cout)
+    buf = K.ActBuf(N, H, W, Cp, pad, DEV)
+    _fill_act(buf, x, L.PAD_REFLECT if reflect else L.PAD_ZERO)
+    slab, _, _ = _wslab(w, False, 1, Cp, Co_pad, kwpad, k, k, Cout, Cin)
+    Ho, Wo = G.conv_out(H, k, stride, pad), G.conv_out(W, k, stride, pad)
+    y = torch.zeros(N, Ho, Wo, Co_pad, device=DEV)
+    table = G.taps_conv_fwd_window(k, stride, 0)
+    a = K.conv_args(buf.window_view(kwpad), None, table, kwpad, slab, None, k * Co_pad, Co_pad, y.data_ptr(), True,
+                    (Ho * Wo * Co_pad, Wo * Co_pad, Co_pad), (0, 0), Ho, Wo)
+    K.run_conv(a)
+    torch.cuda.synchronize()
+    xp = F.pad(x, (pad,) * 4, mode="reflect" if reflect else "constant")
+    ref = F.conv2d(xp, w, None, stride=stride)
+    return _result(y[..., :Cout].permute(0, 3, 1, 2), ref, 2e-4)
+
+
+def case_convT_fwd(N=2, H=8, W=8, Cin=128, Cout=64):
+    """ConvTranspose2d(k3, s2, p1, op1) forward as four gather phases."""
+    _setup()
+    x = _bf(torch.randn(N, Cin, H, W, device=DEV))
+    w = _bf(torch.randn(Cin, Cout, 3, 3, device=DEV) * 0.05)
+    Co_pad = G.pad_out_channels(Cout)
+    buf = K.ActBuf(N, H, W, Cin, 1, DEV)   # explicit (reflect) halo that must NOT be read
+    _fill_act(buf, x, L.PAD_REFLECT)
+    slab, _, _ = _wslab(w, True, 0, 0, Co_pad, Cin, 3, 3, Cout, Cin)
+    Ho, Wo = 2 * H, 2 * W
+    y = torch.zeros(N, Ho, Wo, Co_pad, device=DEV)
+    table = G.taps_convT_fwd(3, 3, 2, 1)
+    a = K.conv_args(buf.view(interior=True), None, table, Cin, slab, None, 9 * Co_pad, Co_pad, y.data_ptr(), True,
+                    (Ho * Wo * Co_pad, Wo * Co_pad, Co_pad), (0, 0), Ho, Wo)
+    K.run_conv(a)
+    torch.cuda.synchronize()
+    ref = F.conv_transpose2d(x, w, None, stride=2, padding=1, output_padding=1)
+    return _result(y[..., :Cout].permute(0, 3, 1, 2), ref, 2e-4)
+
+
+def case_conv_dgrad(N=2, H=16, W=16, Cin=64, Cout=128, k=3, stride=1, pad=1):
+    """Gradient w.r.t. the (zero-padded, implicit halo) input of a Conv2d."""
+    _setup()
+    Ho, Wo = G.conv_out(H, k, stride, pad), G.conv_out(W, k, stride, pad)
+    dy = _bf(torch.randn(N, Cout, Ho, Wo, device=DEV))
+    w = _bf(torch.randn(Cout, Cin, k, k, device=DEV) * 0.05)
+    Kc = G.round_up(Cout, 64)
+    Ci_pad = G.pad_out_channels(Cin)
+    buf = K.ActBuf(N, Ho, Wo, G.pad_in_channels(Cout), 0, DEV)
+    _fill_act(buf, dy, L.PAD_ZERO)
+    slab, _, _ = _wslab(w, False, 2, 0, Ci_pad, Kc, k, k, Cout, Cin)
+    dx = torch.zeros(N, H, W, Ci_pad, device=DEV)
+    table = G.taps_conv_dgrad(k, k, stride, -pad)
+    a = K.conv_args(buf.view(interior=True), None, table, Kc, slab, None, k * k * Ci_pad, Ci_pad, dx.data_ptr(), True,
+                    (H * W * Ci_pad, W * Ci_pad, Ci_pad), (0, 0), H, W)
+    K.run_conv(a)
+    torch.cuda.synchronize()
+    ref = torch.nn.grad.conv2d_input((N, Cin, H, W), w, dy, stride=stride, padding=pad)
+    return _result(dx[..., :Cin].permute(0, 3, 1, 2), ref, 2e-4)
+
+
+def case_conv_wgrad(N=2, H=16, W=16, Cin=64, Cout=128, k=3, stride=1, pad=1, ksplit=None):
+    _setup()
+    Ho, Wo = G.conv_out(H, k, stride, pad), G.conv_out(W, k, stride, pad)
+    x = _bf(torch.randn(N, Cin, H, W, device=DEV))
+    dy = _bf(torch.randn(N, Cout, Ho, Wo, device=DEV))
+    Cp = G.pad_in_channels(Cin)
+    Kc = G.round_up(Cp, 64)
+    Co_pad = G.round_up(Cout, 64)
+    xb = K.ActBuf(N, H, W, Cp, 0, DEV)
+    _fill_act(xb, x, L.PAD_ZERO)
+    dyb = K.ActBuf(N, Ho, Wo, G.pad_in_channels(Cout), 0, DEV)
+    _fill_act(dyb, dy, L.PAD_ZERO)
+    dw = torch.zeros(k * k * Co_pad * Kc, device=DEV)
+    table = G.taps_conv_fwd(k, k, stride, -pad)
+    a = K.wgrad_args(dyb.view(interior=True), None, xb.view(interior=True), None, table, Kc, Co_pad, dw,
+                     k * k * Co_pad, ksplit=ksplit)
+    K.run_wgrad(a)
+    grad = torch.zeros(Cout, Cin, k, k, device=DEV)
+    ua = K.wprep_args(grad, False, Cout, Cin, k, k, 0, 0, Co_pad, Kc, None)
+    K.run_wgrad_unpack(ua, dw, grad)
+    torch.cuda.synchronize()
+    ref = torch.nn.grad.conv2d_weight(x, (Cout, Cin, k, k), dy, stride=stride, padding=pad)
+    return _result(grad, ref, 2e-4 * (N * Ho * Wo) ** 0.5)
+
+
+def case_wgrad_window(N=2, H=16, W=16, Cin=3, Cout=64, k=7, pad=3):
+    _setup()
+    x = _bf(torch.randn(N, Cin, H, W, device=DEV))
+    dy = _bf(torch.randn(N, Cout, H, W, device=DEV))
+    Cp = G.pad_in_channels(Cin)
+    kwpad = G.round_up(k * Cp, 64)
+    Co_pad = G.round_up(Cout, 64)
+    xb = K.ActBuf(N, H, W, Cp, pad, DEV)
+    _fill_act(xb, x, L.PAD_REFLECT)
+    dyb = K.ActBuf(N, H, W, Co_pad, 0, DEV)
+    _fill_act(dyb, dy, L.PAD_ZERO)
+    dw = torch.zeros(k * Co_pad * kwpad, device=DEV)
+    table = G.taps_conv_fwd_window(k, 1, 0)
+    a = K.wgrad_args(dyb.view(interior=True), None, xb.window_view(kwpad), None, table, kwpad, Co_pad, dw, k * Co_pad)
+    K.run_wgrad(a)
+    grad = torch.zeros(Cout, Cin, k, k, device=DEV)
+    ua = K.wprep_args(grad, False, Cout, Cin, k, k, 1, Cp, Co_pad, kwpad, None)
+    K.run_wgrad_unpack(ua, dw, grad)
+    torch.cuda.synchronize()
+    xp = F.pad(x, (pad,) * 4, mode="reflect")
+    ref = torch.nn.grad.conv2d_weight(xp, (Cout, Cin, k, k), dy, stride=1, padding=0)
+    return _result(grad, ref, 2e-4 * (N * H * W) ** 0.5)
+
+
+def case_convT_bwd(N=2, H=8, W=8, Cin=128, Cout=64):
+    """ConvTranspose2d dgrad (strided gather over dY) and wgrad (roles swapped)."""
+    _setup()
+    x = _bf(torch.randn(N, Cin, H, W, device=DEV))
+    w = _bf(torch.randn(Cin, Cout, 3, 3, device=DEV) * 0.05)
+    dy = _bf(torch.randn(N, Cout, 2 * H, 2 * W, device=DEV))
+    xr = x.clone().requires_grad_(True)
+    wr = w.clone().requires_grad_(True)
+    F.conv_transpose2d(xr, wr, None, stride=2, padding=1, output_padding=1).backward(dy)
+    Kc = G.round_up(Cout, 64)
+    Ci_pad = G.pad_out_channels(Cin)
+    dyb = K.ActBuf(N, 2 * H, 2 * W, G.pad_in_channels(Cout), 0, DEV)
+    _fill_act(dyb, dy, L.PAD_ZERO)
+    xb = K.ActBuf(N, H, W, Cin, 0, DEV)
+    _fill_act(xb, x, L.PAD_ZERO)
+    slab, _, _ = _wslab(w, True, 2, 0, Ci_pad, Kc, 3, 3, Cout, Cin)
+    dx = torch.zeros(N, H, W, Ci_pad, device=DEV)
+    table = G.taps_convT_dgrad(3, 3, 2, 1)
+    a = K.conv_args(dyb.view(interior=True), None, table, Kc, slab, None, 9 * Ci_pad, Ci_pad, dx.data_ptr(), True,
+                    (H * W * Ci_pad, W * Ci_pad, Ci_pad), (0, 0), H, W)
+    K.run_conv(a)
+    # wgrad: "dy" role = x (M = Cin), "x" role = dY (strided), slab [tap][Ci_pad][Kc = Cout]
+    Ci_pad64 = G.round_up(Cin, 64)
+    dw = torch.zeros(9 * Ci_pad64 * Kc, device=DEV)
+    wa = K.wgrad_args(xb.view(interior=True), None, dyb.view(interior=True), None, table, Kc, Ci_pad64, dw,
+                      9 * Ci_pad64)
+    K.run_wgrad(wa)
+    grad = torch.zeros(Cin, Cout, 3, 3, device=DEV)
+    ua = K.wprep_args(grad, True, Cout, Cin, 3, 3, 2, 0, Ci_pad64, Kc, None)
+    K.run_wgrad_unpack(ua, dw, grad)
+    torch.cuda.synchronize()
+    e1 = _result(dx[..., :Cin].permute(0, 3, 1, 2), xr.grad, 2e-4)
+    e2 = _result(grad, wr.grad, 2e-4 * (N * H * W) ** 0.5)
+    # normalise both to one verdict (ratio to tolerance)
+    worst = max(e1[0] / e1[2], e2[0] / e2[2])
+    return worst, 1.0, 1.0
+
+
+def case_apply_fwd(N=2, H=12, W=12, Cc=64, pad=1, reflect=True, act=L.ACT_RELU, residual=False, norm=True):
+    """InstanceNorm + activation (+ residual) + halo write vs torch."""
+    _setup()
+    raw = _bf(torch.randn(N, Cc, H, W, device=DEV) * 2 + 0.5)
+    rawb = raw.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+    st = torch.stack([raw.sum(dim=(2, 3)), (raw * raw).sum(dim=(2, 3))], dim=-1).contiguous()
+    dst = K.ActBuf(N, H, W, Cc, pad, DEV)
+    a = L.ApplyArgs()
+    a.raw, a.raw_fp32 = rawb.data_ptr(), 0
+    a.stats, a.eps = (st.data_ptr() if norm else None), 1e-5
+    a.N, a.H, a.W, a.C = N, H, W, Cc
+    a.act, a.slope, a.drop_seed = act, 0.2, 0
+    resb = None
+    if residual:
+        res = _bf(torch.randn(N, Cc, H, W, device=DEV))
+        resb = K.ActBuf(N, H, W, Cc, 1, DEV)
+        _fill_act(resb, res, L.PAD_REFLECT)
+        a.res = resb.view(interior=True)
+    a.dst, a.dst_lo = dst.hi.data_ptr(), None
+    a.pad, a.pad_mode = pad, (L.PAD_REFLECT if reflect else L.PAD_ZERO)
+    K.run_apply(a)
+    torch.cuda.synchronize()
+    ref = F.instance_norm(raw, eps=1e-5) if norm else raw
+    if act == L.ACT_RELU:
+        ref = F.relu(ref)
+    elif act == L.ACT_LRELU:
+        ref = F.leaky_relu(ref, 0.2)
+    if residual:
+        ref = ref + res
+    if pad:
+        ref = F.pad(ref, (pad,) * 4, mode="reflect" if reflect else "constant")
+    got = dst.as_nhwc(interior=False).float().permute(0, 3, 1, 2)
+    return _result(got, ref, 2e-2)
+
+
+def case_apply_bwd(N=2, H=12, W=12, Cc=64, pad=1, act=L.ACT_RELU, skip=True):
+    """Backward of pad(act(IN(raw))) (+ skip gradient): dRaw vs autograd."""
+    _setup()
+    raw = _bf(torch.randn(N, Cc, H, W, device=DEV) * 2 + 0.5)
+    dyp = _bf(torch.randn(N, Cc, H + 2 * pad, W + 2 * pad, device=DEV))
+    sk = _bf(torch.randn(N, Cc, H, W, device=DEV)) if skip else None
+    rr = raw.clone().requires_grad_(True)
+    z = F.instance_norm(rr, eps=1e-5)
+    y = F.relu(z) if act == L.ACT_RELU else (F.leaky_relu(z, 0.2) if act == L.ACT_LRELU else z)
+    yp = F.pad(y, (pad,) * 4, mode="reflect") if pad else y
+    loss = (yp * dyp).sum()
+    if skip:
+        loss = loss + (y * sk).sum()
+    loss.backward()
+    rawb = raw.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+    st = torch.stack([raw.sum(dim=(2, 3)), (raw * raw).sum(dim=(2, 3))], dim=-1).contiguous()
+    dypb = K.ActBuf(N, H, W, Cc, pad, DEV)
+    t = dyp.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+    dypb.hi[: t.numel()].copy_(t.reshape(-1))
+    a = L.BwdArgs()
+    a.raw, a.raw_fp32 = rawb.data_ptr(), 0
+    a.stats, a.eps = st.data_ptr(), 1e-5
+    a.N, a.H, a.W, a.C = N, H, W, Cc
+    a.act, a.slope, a.drop_seed = act, 0.2, 0
+    a.dyp, a.dyp_fp32 = dypb.view(interior=False), 0
+    a.pad, a.pad_mode = pad, L.PAD_REFLECT if pad else L.PAD_NONE
+    if skip:
+        skb = sk.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+        a.skip = L.make_view(skb.data_ptr(), N, H, W, Cc, H * W * Cc, W * Cc, Cc)
+        a.skip_fp32 = 0
+    dz = torch.zeros(N, H, W, Cc, device=DEV)
+    bst = torch.zeros(N, Cc, 2, device=DEV)
+    a.dz, a.dz_fp32, a.dz_lo = dz.data_ptr(), 1, None
+    a.bstats = bst.data_ptr()
+    K.run_bwd_prep(a)
+    draw = torch.zeros(N, H, W, Cc, device=DEV, dtype=torch.bfloat16)
+    K.run_bwd_apply(a, draw)
+    torch.cuda.synchronize()
+    return _result(draw.float().permute(0, 3, 1, 2), rr.grad, 2e-2)
+
+
+def case_pack_unpack(N=2, Cc=21, H=10, W=12, pad=3):
+    _setup()
+    x = torch.randn(N, Cc, H, W, device=DEV)
+    Cp = G.pad_in_channels(Cc)
+    buf = K.ActBuf(N, H, W, Cp, pad, DEV)
+    K.pack_nchw(x.contiguous(), buf, L.PAD_REFLECT)
+    torch.cuda.synchronize()
+    ref = F.pad(_bf(x), (pad,) * 4, mode="reflect")
+    got = buf.as_nhwc(interior=False).float()[..., :Cc].permute(0, 3, 1, 2)
+    e1 = (got - ref).abs().max().item()
+    lab = torch.randint(0, Cc, (N, 1, H, W), device=DEV)
+    buf2 = K.ActBuf(N, H, W, Cp, pad, DEV)
+    K.onehot_pack(lab, Cc, buf2, L.PAD_REFLECT)
+    oh = torch.zeros(N, Cc, H, W, device=DEV).scatter_(1, lab, 1.0)
+    ref2 = F.pad(oh, (pad,) * 4, mode="reflect")
+    got2 = buf2.as_nhwc(interior=False).float()[..., :Cc].permute(0, 3, 1, 2)
+    e2 = (got2 - ref2).abs().max().item()
+    src = torch.randn(N, H, W, 32, device=DEV)
+    dst = torch.zeros(N, Cc, H, W, device=DEV)
+    K.unpack_nhwc(src, N, Cc, H, W, 32, dst)
+    torch.cuda.synchronize()
+    e3 = (dst - src[..., :Cc].permute(0, 3, 1, 2)).abs().max().item()
+    return max(e1, e2, e3), 1.0, 1e-6
+
+
+CASES = {
+    # forward conv, regular mode
+    "fwd_3x3_reflect_64": lambda: case_conv_fwd(),
+    "fwd_3x3_reflect_256": lambda: case_conv_fwd(N=2, H=16, W=16, Cin=256, Cout=256),
+    "fwd_3x3_zero_oob": lambda: case_conv_fwd(reflect=False, explicit=False),
+    "fwd_3x3_s2": lambda: case_conv_fwd(Cin=64, Cout=128, stride=2, reflect=False, explicit=False),
+    "fwd_4x4_s2": lambda: case_conv_fwd(Cin=64, Cout=128, k=4, stride=2, reflect=False, explicit=False),
+    "fwd_4x4_s1_odd": lambda: case_conv_fwd(H=10, W=10, Cin=128, Cout=512, k=4, stride=1, reflect=False,
+                                            explicit=False),
+    "fwd_4x4_s1_cout1": lambda: case_conv_fwd(H=9, W=9, Cin=128, Cout=1, k=4, stride=1, reflect=False,
+                                              explicit=False, bias=True),
+    "fwd_7x7_head21": lambda: case_conv_fwd(Cin=64, Cout=21, k=7, pad=3, bias=True),
+    "fwd_7x7_head3_tanh": lambda: case_conv_fwd(Cin=64, Cout=3, k=7, pad=3, bias=True, act=L.ACT_TANH),
+    "fwd_bf16_stats": lambda: case_conv_fwd(Cin=128, Cout=256, out_fp32=False, stats=True),
+    "fwd_bf16_lrelu_bias": lambda: case_conv_fwd(Cin=64, Cout=64, out_fp32=False, bias=True, act=L.ACT_LRELU),
+    "fwd_wide_image": lambda: case_conv_fwd(N=1, H=8, W=256, Cin=64, Cout=64),
+    "fwd_split3": lambda: case_conv_fwd(Cin=128, Cout=128, split=3),
+    # window mode
+    "win_stem_c3": lambda: case_conv_window(),
+    "win_stem_c21": lambda: case_conv_window(Cin=21),
+    "win_stem_c1": lambda: case_conv_window(Cin=1),
+    "win_d0_c3": lambda: case_conv_window(Cin=3, k=4, stride=2, pad=1, reflect=False),
+    "win_d0_c21": lambda: case_conv_window(Cin=21, k=4, stride=2, pad=1, reflect=False),
+    # transposed conv
+    "convT_fwd": lambda: case_convT_fwd(),
+    "convT_fwd_256": lambda: case_convT_fwd(Cin=256, Cout=128),
+    "convT_bwd": lambda: case_convT_bwd(),
+    # dgrad
+    "dgrad_3x3_s1": lambda: case_conv_dgrad(),
+    "dgrad_3x3_s2": lambda: case_conv_dgrad(stride=2),
+    "dgrad_4x4_s2": lambda: case_conv_dgrad(k=4, stride=2),
+    "dgrad_4x4_s1_odd": lambda: case_conv_dgrad(H=10, W=10, k=4, stride=1),
+    "dgrad_7x7_small_cout": lambda: case_conv_dgrad(Cin=64, Cout=21, k=7, pad=3),
+    "dgrad_to_c3": lambda: case_conv_dgrad(Cin=3, Cout=64, k=7, pad=3),
+    # wgrad
+    "wgrad_3x3_s1": lambda: case_conv_wgrad(),
+    "wgrad_3x3_s1_256": lambda: case_conv_wgrad(Cin=256, Cout=256),
+    "wgrad_3x3_s2": lambda: case_conv_wgrad(stride=2),
+    "wgrad_4x4_s2": lambda: case_conv_wgrad(k=4, stride=2),
+    "wgrad_4x4_s1_odd": lambda: case_conv_wgrad(H=10, W=10, k=4, stride=1),
+    "wgrad_cout21": lambda: case_conv_wgrad(Cin=64, Cout=21, k=7, pad=3),
+    "wgrad_ksplit1": lambda: case_conv_wgrad(ksplit=1),
+    "wgrad_window_c3": lambda: case_wgrad_window(),
+    "wgrad_window_c21": lambda: case_wgrad_window(Cin=21),
+    # elementwise
+    "apply_fwd_relu_reflect": lambda: case_apply_fwd(),
+    "apply_fwd_res": lambda: case_apply_fwd(act=L.ACT_NONE, residual=True),
+    "apply_fwd_lrelu_zero": lambda: case_apply_fwd(Cc=128, pad=1, reflect=False, act=L.ACT_LRELU),
+    "apply_fwd_c512": lambda: case_apply_fwd(Cc=512, H=7, W=7, pad=0, act=L.ACT_LRELU),
+    "apply_bwd_relu": lambda: case_apply_bwd(),
+    "apply_bwd_nopad": lambda: case_apply_bwd(pad=0, act=L.ACT_LRELU, skip=False),
+    "apply_bwd_pad3": lambda: case_apply_bwd(pad=3, act=L.ACT_RELU, skip=False),
+    "pack_unpack": lambda: case_pack_unpack(),
+}
