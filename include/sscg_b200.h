@@ -124,7 +124,7 @@ int sscg_conv_wgrad(const SscgWgradArgs* a, void* stream);
  * Replaces the layout change + nn.ReflectionPad2d(3) at the generator stem (generators.py:73) and
  * the zero padding of the PatchGAN stem (discriminators.py:45).  dst extents (H+2*pad, W+2*pad). */
 int sscg_pack_nchw(const float* src, int32_t N, int32_t C, int32_t H, int32_t W, void* dst, void* dst_lo,
-                   int32_t Cp, int32_t pad, int32_t pad_mode, void* stream);
+                   int32_t dst_fp32, int32_t Cp, int32_t pad, int32_t pad_mode, void* stream);
 
 /* sscg_onehot_pack: int64 label map [N][1][H][W] -> one-hot NHWC bf16 with halo (utils.py:314-350
  * make_one_hot fused with the stem's layout change). */
@@ -134,6 +134,16 @@ int sscg_onehot_pack(const int64_t* labels, int32_t N, int32_t C, int32_t H, int
 /* sscg_unpack_nhwc: NHWC fp32 [N][H][W][Cp] -> NCHW fp32 [N][C][H][W] (module output boundary). */
 int sscg_unpack_nhwc(const float* src, int32_t N, int32_t C, int32_t H, int32_t W, int32_t Cp, float* dst,
                      void* stream);
+
+/* sscg_unpack_fold: gradient of the boundary pack — padded NHWC (bf16 or fp32) [N][H+2p][W+2p][Cp] ->
+ * NCHW fp32 [N][C][H][W], folding halo gradients back onto their source pixels (backward of
+ * nn.ReflectionPad2d / zero padding at generators.py:73, discriminators.py:45). */
+int sscg_unpack_fold(const void* src, int32_t src_fp32, int32_t N, int32_t C, int32_t H, int32_t W, int32_t Cp,
+                     int32_t pad, int32_t pad_mode, float* dst, void* stream);
+
+/* sscg_bias_grad: grad[c] += scale * sum_n bstats[n][c][0] (bias gradient of a conv that is not
+ * followed by InstanceNorm: head conv generators.py:85,90; PatchGAN stem/tail discriminators.py:45,58). */
+int sscg_bias_grad(const float* bstats, int32_t N, int32_t C, int32_t Cp, float* grad, float scale, void* stream);
 
 /* sscg_in_apply: y = dropout(act(instance_norm(raw))) (+ residual), written with a halo for the next
  * convolution.  Replaces nn.InstanceNorm2d + ReLU/LeakyReLU + Dropout + residual add + the next

@@ -98,7 +98,10 @@ _SIGNATURES = {
     "sscg_conv_igemm": [C.POINTER(ConvArgs), C.c_void_p],
     "sscg_conv_wgrad": [C.POINTER(WgradArgs), C.c_void_p],
     "sscg_pack_nchw": [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
-                       C.c_int32, C.c_int32, C.c_void_p],
+                       C.c_int32, C.c_int32, C.c_int32, C.c_void_p],
+    "sscg_unpack_fold": [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                         C.c_int32, C.c_void_p, C.c_void_p],
+    "sscg_bias_grad": [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_float, C.c_void_p],
     "sscg_onehot_pack": [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
                          C.c_int32, C.c_int32, C.c_void_p],
     "sscg_unpack_nhwc": [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p],

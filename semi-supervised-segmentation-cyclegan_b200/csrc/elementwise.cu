@@ -89,8 +89,10 @@ __device__ __forceinline__ void load_norm(const float* stats, float eps, long lo
 // ---------------------------------------------------------------------------------------------
 template <bool ONEHOT>
 __global__ void pack_kernel(const float* __restrict__ src, const long long* __restrict__ labels, int N, int C, int H,
-                            int W, __nv_bfloat16* __restrict__ dst, __nv_bfloat16* __restrict__ dst_lo, int Cp, int pad,
-                            int pad_mode) {
+                            int W, void* __restrict__ dst_, void* __restrict__ dst_lo_, int Cp, int pad,
+                            int pad_mode, int dst_fp32) {
+    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(dst_);
+    __nv_bfloat16* dst_lo = reinterpret_cast<__nv_bfloat16*>(dst_lo_);
     const int Hp = H + 2 * pad, Wp = W + 2 * pad;
     const long long total = (long long)N * Hp * Wp;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
@@ -107,7 +109,7 @@ __global__ void pack_kernel(const float* __restrict__ src, const long long* __re
             zero = true;
         }
         __nv_bfloat16* d = dst + idx * Cp;
-        __nv_bfloat16* dl = dst_lo ? dst_lo + idx * Cp : nullptr;
+        __nv_bfloat16* dl = (dst_lo && !dst_fp32) ? dst_lo + idx * Cp : nullptr;
         int lab = -1;
         if (ONEHOT && !zero) lab = (int)labels[((long long)n * H + h) * W + w];
         for (int c0 = 0; c0 < Cp; c0 += 8) {
@@ -122,10 +124,15 @@ __global__ void pack_kernel(const float* __restrict__ src, const long long* __re
                 }
                 v[q] = x;
             }
-            store8_bf16(d, dl, c0, v);
+            if (dst_fp32) store8_f32(dst_, idx * Cp + c0, v);
+            else store8_bf16(d, dl, c0, v);
         }
     }
 }
+
+// gradient of the boundary pack: padded NHWC (fp32 or bf16) -> NCHW fp32, folding the halo back
+__global__ void unpack_fold_kernel(const void* __restrict__ src, int src_fp32, int N, int C, int H, int W, int Cp,
+                                   int pad, int pad_mode, float* __restrict__ dst);
 
 __global__ void unpack_kernel(const float* __restrict__ src, int N, int C, int H, int W, int Cp,
                               float* __restrict__ dst) {
@@ -313,6 +320,7 @@ __global__ void __launch_bounds__(256) in_bwd_prep_kernel(const __grid_constant_
     }
     if (a.bstats == nullptr) return;
     // block reduction over the pixel rows that share a channel vector, then one atomic per channel
+#pragma unroll
     for (int q = 0; q < 8; ++q) {
         __syncthreads();
         s_red[threadIdx.x * 2] = active ? acc1[q] : 0.f;
@@ -365,6 +373,46 @@ __global__ void __launch_bounds__(256) in_bwd_apply_kernel(const __grid_constant
         }
         store8_bf16(p.draw, p.draw_lo, off, g);
     }
+}
+
+__global__ void unpack_fold_kernel(const void* __restrict__ src, int src_fp32, int N, int C, int H, int W, int Cp,
+                                   int pad, int pad_mode, float* __restrict__ dst) {
+    const int Hp = H + 2 * pad, Wp = W + 2 * pad;
+    const long long total = (long long)N * H * W;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int w = idx % W;
+        const int h = (idx / W) % H;
+        const int n = idx / ((long long)W * H);
+        int hq[3], wq[3];
+        const int nh = fold_positions(h, H, pad, pad_mode, hq);
+        const int nw = fold_positions(w, W, pad, pad_mode, wq);
+        for (int c0 = 0; c0 < C; c0 += 8) {
+            float g[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) g[q] = 0.f;
+            for (int x = 0; x < nh; ++x)
+                for (int y = 0; y < nw; ++y) {
+                    float t[8];
+                    load8(src, src_fp32 != 0, (((long long)n * Hp + hq[x]) * Wp + wq[y]) * Cp + c0, t);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) g[q] += t[q];
+                }
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                if (c0 + q < C) dst[(((long long)n * C + c0 + q) * H + h) * W + w] = g[q];
+        }
+    }
+}
+
+// bias gradient of a conv without normalisation: grad[c] += scale * sum_n bstats[n][c][0]
+__global__ void bias_grad_kernel(const float* __restrict__ bstats, int N, int C, int Cp, float* __restrict__ grad,
+                                 float scale) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float s = 0.f;
+    for (int n = 0; n < N; ++n) s += bstats[((long long)n * Cp + c) * 2];
+    grad[c] += scale * s;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -443,12 +491,11 @@ using namespace sscg;
     } while (0)
 
 extern "C" int sscg_pack_nchw(const float* src, int32_t N, int32_t C, int32_t H, int32_t W, void* dst, void* dst_lo,
-                              int32_t Cp, int32_t pad, int32_t pad_mode, void* stream) {
+                              int32_t dst_fp32, int32_t Cp, int32_t pad, int32_t pad_mode, void* stream) {
     if (Cp % 8 || Cp < C) return set_error("pack_nchw: Cp=%d must be a multiple of 8 and >= C=%d", Cp, C);
     const long long total = (long long)N * (H + 2 * pad) * (W + 2 * pad);
     pack_kernel<false><<<ew_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        src, nullptr, N, C, H, W, reinterpret_cast<__nv_bfloat16*>(dst), reinterpret_cast<__nv_bfloat16*>(dst_lo), Cp, pad,
-        pad_mode);
+        src, nullptr, N, C, H, W, dst, dst_lo, Cp, pad, pad_mode, dst_fp32);
     SSCG_CHECK_LAUNCH("pack_nchw");
     return 0;
 }
@@ -458,8 +505,7 @@ extern "C" int sscg_onehot_pack(const int64_t* labels, int32_t N, int32_t C, int
     if (Cp % 8 || Cp < C) return set_error("onehot_pack: Cp=%d must be a multiple of 8 and >= C=%d", Cp, C);
     const long long total = (long long)N * (H + 2 * pad) * (W + 2 * pad);
     pack_kernel<true><<<ew_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        nullptr, reinterpret_cast<const long long*>(labels), N, C, H, W, reinterpret_cast<__nv_bfloat16*>(dst),
-        reinterpret_cast<__nv_bfloat16*>(dst_lo), Cp, pad, pad_mode);
+        nullptr, reinterpret_cast<const long long*>(labels), N, C, H, W, dst, dst_lo, Cp, pad, pad_mode, 0);
     SSCG_CHECK_LAUNCH("onehot_pack");
     return 0;
 }
@@ -469,6 +515,23 @@ extern "C" int sscg_unpack_nhwc(const float* src, int32_t N, int32_t C, int32_t 
     const long long total = (long long)N * H * W;
     unpack_kernel<<<ew_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, N, C, H, W, Cp, dst);
     SSCG_CHECK_LAUNCH("unpack_nhwc");
+    return 0;
+}
+
+extern "C" int sscg_unpack_fold(const void* src, int32_t src_fp32, int32_t N, int32_t C, int32_t H, int32_t W,
+                                int32_t Cp, int32_t pad, int32_t pad_mode, float* dst, void* stream) {
+    if (Cp % 8) return set_error("unpack_fold: Cp=%d must be a multiple of 8", Cp);
+    const long long total = (long long)N * H * W;
+    unpack_fold_kernel<<<ew_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, src_fp32, N, C, H, W, Cp,
+                                                                                         pad, pad_mode, dst);
+    SSCG_CHECK_LAUNCH("unpack_fold");
+    return 0;
+}
+
+extern "C" int sscg_bias_grad(const float* bstats, int32_t N, int32_t C, int32_t Cp, float* grad, float scale,
+                              void* stream) {
+    bias_grad_kernel<<<(C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(bstats, N, C, Cp, grad, scale);
+    SSCG_CHECK_LAUNCH("bias_grad");
     return 0;
 }
 

@@ -1,0 +1,456 @@
+"""Execution engine: turns a ResNet-block generator or an n-layer PatchGAN (module trees with the
+reference's layout, reference arch/generators.py:65-95, arch/discriminators.py:42-63) into a list
+of fused *stages* and runs their forward / backward through the C ABI (libsscg_b200.so).
+
+A stage = one convolution-like GEMM + what follows it up to the next convolution's input buffer:
+
+    act[i] --conv_igemm--> raw[i] (+ InstanceNorm sums in the epilogue)
+           --in_apply----> act[i+1]   (normalise, ReLU/LeakyReLU, dropout, residual add, halo)
+
+Stages without InstanceNorm (PatchGAN stem/tail, generator head) apply bias + activation in the
+GEMM epilogue and write act[i+1] (or the fp32 output) directly.
+
+Backward per stage:  in_bwd_prep (+ in_bwd_apply)  ->  dRaw;  conv_wgrad -> weight-gradient slab;
+conv_igemm with the dgrad tap table -> gradient w.r.t. act[i].
+
+Precision modes: "bf16" (fast; bf16 operands and storage, fp32 accumulate/statistics) and
+"bf16x3" (parity; operands carried as hi+lo bf16 planes, raw outputs and gradients in fp32).
+"""
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional
+
+import torch
+
+from . import _lib as L
+from . import geometry as G
+from . import kernels as K
+
+
+@dataclass
+class StageSpec:
+    kind: str                 # 'conv' | 'window' | 'convT'
+    k: int
+    stride: int
+    pad: int
+    in_halo: int              # explicit halo carried by the input buffer (0 = implicit zero fill)
+    in_reflect: bool          # halo content of the input buffer
+    Cin: int
+    Cout: int
+    norm: bool
+    act: int
+    weight: torch.nn.Parameter
+    bias: Optional[torch.nn.Parameter]
+    dropout: bool = False
+    residual_from: Optional[int] = None   # index of the act buffer added after normalisation
+    final: bool = False                   # writes the fp32 NHWC network output
+    name: str = ""
+
+
+def _conv_geom(spec: StageSpec, Hin, Win):
+    if spec.kind == "convT":
+        return G.convT_out(Hin, spec.k, spec.stride, spec.pad, 1), G.convT_out(Win, spec.k, spec.stride, spec.pad, 1)
+    return G.conv_out(Hin, spec.k, spec.stride, spec.pad), G.conv_out(Win, spec.k, spec.stride, spec.pad)
+
+
+class StageWeights:
+    """bf16 GEMM operand slabs + fp32 wgrad accumulator of one stage (shape independent)."""
+
+    def __init__(self, spec: StageSpec, split: bool, need_dgrad: bool, device, first: bool = False):
+        s = spec
+        self.spec = s
+        self.split = split
+        k = s.k
+        self.transposed = s.kind == "convT"
+        # channel pitch of the stage input: the packed network input is padded to 8 channels, internal
+        # activations carry the producing GEMM's N padding
+        self.Cp_in = G.pad_in_channels(s.Cin) if first else G.pad_out_channels(s.Cin)
+        if s.kind == "window":
+            self.Kc = G.round_up(k * self.Cp_in, 64)
+            self.ntaps_fwd = k
+            fmode = 1
+        else:
+            self.Kc = G.round_up(self.Cp_in, 64)
+            self.ntaps_fwd = k * k
+            fmode = 0
+        self.Co_pad = G.pad_out_channels(s.Cout)          # forward N / channel pitch of raw
+        self.Co_pitch = self.Co_pad
+        bf = torch.bfloat16
+        self.w_fwd = torch.zeros(self.ntaps_fwd * self.Co_pad * self.Kc, dtype=bf, device=device)
+        self.w_fwd_lo = torch.zeros_like(self.w_fwd) if split else None
+        self.prep_fwd = K.wprep_args(s.weight, self.transposed, s.Cout, s.Cin, k, k, fmode, self.Cp_in, self.Co_pad,
+                                     self.Kc, self.w_fwd, self.w_fwd_lo)
+        # dgrad: rows = input channels (padded to a legal N tile), K = output-channel pitch
+        self.need_dgrad = need_dgrad
+        self.Ci_pad = G.pad_out_channels(self.Cp_in)
+        self.Kc_d = G.round_up(self.Co_pitch, 64)
+        if need_dgrad:
+            self.w_dg = torch.zeros(k * k * self.Ci_pad * self.Kc_d, dtype=bf, device=device)
+            self.w_dg_lo = torch.zeros_like(self.w_dg) if split else None
+            self.prep_dg = K.wprep_args(s.weight, self.transposed, s.Cout, s.Cin, k, k, 2, 0, self.Ci_pad, self.Kc_d,
+                                        self.w_dg, self.w_dg_lo)
+        # wgrad accumulator (fp32) and its unpack descriptor
+        if self.transposed:
+            # roles swapped: rows = Cin (M), K axis = Cout
+            self.wg_rows = G.round_up(s.Cin, 64)
+            self.wg_Kc = G.round_up(self.Co_pitch, 64)
+            self.wg_taps = k * k
+            wmode = 2
+        else:
+            self.wg_rows = G.round_up(s.Cout, 64)
+            self.wg_Kc = self.Kc
+            self.wg_taps = self.ntaps_fwd
+            wmode = fmode
+        self.dw = torch.zeros(self.wg_taps * self.wg_rows * self.wg_Kc, dtype=torch.float32, device=device)
+        self.unpack_wg = K.wprep_args(None, self.transposed, s.Cout, s.Cin, k, k, wmode, self.Cp_in, self.wg_rows,
+                                      self.wg_Kc, None)
+        self.bias_pad = None
+        if s.bias is not None and not s.norm:
+            self.bias_pad = torch.zeros(self.Co_pad, dtype=torch.float32, device=device)
+
+    def prepare(self):
+        # parameters may have been re-allocated (e.g. .to()), so refresh the source pointer
+        self.prep_fwd.w = self.spec.weight.data_ptr()
+        K.run_wprep(self.prep_fwd)
+        if self.need_dgrad:
+            self.prep_dg.w = self.spec.weight.data_ptr()
+            K.run_wprep(self.prep_dg)
+        if self.bias_pad is not None:
+            self.bias_pad[: self.spec.Cout].copy_(self.spec.bias.detach())
+
+
+class Ctx:
+    """Per-call activation storage (saved for backward)."""
+
+    def __init__(self):
+        self.act: List[K.ActBuf] = []
+        self.raw: List[Optional[K.ActBuf]] = []
+        self.stats = None
+        self.stat_off: List[int] = []
+        self.out = None
+        self.drop_seed = 0
+        self.busy = False
+
+
+class NetPlan:
+    """Stage list + buffers of one network for a fixed input shape (N, H, W)."""
+
+    def __init__(self, specs: List[StageSpec], weights: List[StageWeights], N, H, W, precision, device,
+                 need_input_grad_capable=True):
+        self.specs, self.weights = specs, weights
+        self.N, self.H, self.W = N, H, W
+        self.split = 3 if precision == "bf16x3" else 1
+        self.device = device
+        self.geom = []
+        h, w = H, W
+        for s in specs:
+            ho, wo = _conv_geom(s, h, w)
+            self.geom.append((h, w, ho, wo))
+            h, w = ho, wo
+        self.Hout, self.Wout = h, w
+        self.Cout = specs[-1].Cout
+        self.ctx_pool: List[Ctx] = []
+        self._scratch_ready = False
+        self._args_cache = {}
+
+    def _direct(self, s: StageSpec) -> bool:
+        """Un-normalised stage whose GEMM epilogue writes its consumer's buffer directly (bias +
+        activation fused).  In bf16x3 mode intermediate stages go through raw(fp32) + in_apply so the
+        consumer gets hi/lo planes."""
+        return (not s.norm) and (s.final or self.split == 1)
+
+    # ------------------------------------------------------------------ buffers
+    def _new_ctx(self) -> Ctx:
+        c = Ctx()
+        N, sp = self.N, self.split == 3
+        nstat = 0
+        for i, (s, wt) in enumerate(zip(self.specs, self.weights)):
+            hin, win, ho, wo = self.geom[i]
+            c.act.append(K.ActBuf(N, hin, win, wt.Cp_in, s.in_halo, self.device, split=sp))
+            if s.norm:
+                c.raw.append(K.ActBuf(N, ho, wo, wt.Co_pitch, 0, self.device, fp32=sp))
+                c.stat_off.append(nstat)
+                nstat += N * wt.Co_pitch * 2
+            elif not self._direct(s):
+                c.raw.append(K.ActBuf(N, ho, wo, wt.Co_pitch, 0, self.device, fp32=True))
+                c.stat_off.append(-1)
+            else:
+                c.raw.append(None)
+                c.stat_off.append(-1)
+        c.stats = torch.zeros(max(nstat, 2), dtype=torch.float32, device=self.device)
+        last = self.weights[-1]
+        c.out = K.ActBuf(N, self.Hout, self.Wout, last.Co_pitch, 0, self.device, fp32=True)
+        return c
+
+    def acquire_ctx(self) -> Ctx:
+        for c in self.ctx_pool:
+            if not c.busy:
+                c.busy = True
+                return c
+        c = self._new_ctx()
+        c.busy = True
+        self.ctx_pool.append(c)
+        return c
+
+    def release_ctx(self, c: Ctx):
+        c.busy = False
+
+    def _ensure_scratch(self):
+        """Backward scratch shared by all contexts of this plan (backward passes are serial)."""
+        if self._scratch_ready:
+            return
+        N, sp = self.N, self.split == 3
+        dev = self.device
+        # gradient w.r.t. act[i] buffers (padded extents where the halo is explicit)
+        self.gact: List[Optional[K.ActBuf]] = []
+        for i, (s, wt) in enumerate(zip(self.specs, self.weights)):
+            hin, win, _, _ = self.geom[i]
+            cp = wt.Ci_pad if i == 0 else wt.Cp_in
+            fp32 = sp or i == 0
+            self.gact.append(K.ActBuf(N, hin, win, cp, s.in_halo, dev, fp32=fp32))
+        last = self.weights[-1]
+        self.gout = K.ActBuf(N, self.Hout, self.Wout, last.Co_pitch, 0, dev, fp32=sp)
+        mx = max(self.geom[i][2] * self.geom[i][3] * self.weights[i].Co_pitch for i in range(len(self.specs)))
+        self.dz = torch.zeros(N * mx + K.SLACK, dtype=torch.float32 if sp else torch.bfloat16, device=dev)
+        self.draw = torch.zeros(N * mx + K.SLACK, dtype=torch.bfloat16, device=dev)
+        self.draw_lo = torch.zeros_like(self.draw) if sp else None
+        self.tbuf = [None, None]   # residual-path total gradients (ping-pong), allocated lazily
+        nb = sum(N * wt.Co_pitch * 2 for wt in self.weights)
+        self.bstats = torch.zeros(nb, dtype=torch.float32, device=dev)
+        self.bstat_off = []
+        o = 0
+        for wt in self.weights:
+            self.bstat_off.append(o)
+            o += N * wt.Co_pitch * 2
+        self._scratch_ready = True
+
+    def _tbuf(self, which, like: K.ActBuf):
+        if self.tbuf[which] is None:
+            self.tbuf[which] = K.ActBuf(like.N, like.H, like.W, like.C, 0, self.device, fp32=self.split == 3)
+        return self.tbuf[which]
+
+    # ------------------------------------------------------------------ forward
+    def _fwd_table(self, s: StageSpec):
+        if s.kind == "window":
+            return G.taps_conv_fwd_window(s.k, s.stride, 0)
+        if s.kind == "convT":
+            return G.taps_convT_fwd(s.k, s.k, s.stride, s.pad)
+        return G.taps_conv_fwd(s.k, s.k, s.stride, 0 if s.in_halo else -s.pad)
+
+    def _x_view(self, s: StageSpec, wt: StageWeights, buf: K.ActBuf):
+        """(view, lo pointer) of the stage input as the forward GEMM reads it."""
+        if s.kind == "window":
+            return buf.window_view(wt.Kc), (buf.lo.data_ptr() if buf.lo is not None else None)
+        if s.kind == "convT" or not s.in_halo:
+            return buf.view(interior=True), buf.lo_ptr(interior=True)
+        return buf.view(interior=False), buf.lo_ptr(interior=False)
+
+    def forward(self, c: Ctx, x=None, labels=None, n_classes=None, training=True, drop_seed=0):
+        """x: NCHW fp32 (or labels int64 N x 1 x H x W to be one-hot encoded on the fly).
+        Leaves the fp32 NHWC result in c.out; returns c."""
+        sp = self.split
+        c.stats.zero_()
+        s0 = self.specs[0]
+        mode0 = L.PAD_REFLECT if s0.in_reflect else L.PAD_ZERO
+        if labels is not None:
+            K.onehot_pack(labels, n_classes, c.act[0], mode0)
+        else:
+            K.pack_nchw(x, c.act[0], mode0)
+        c.drop_seed = drop_seed if training else 0
+        nst = len(self.specs)
+        for i, (s, wt) in enumerate(zip(self.specs, self.weights)):
+            hin, win, ho, wo = self.geom[i]
+            key = ("f", id(c), i)
+            args = self._args_cache.get(key)
+            if args is None:
+                view, lo = self._x_view(s, wt, c.act[i])
+                table = self._fwd_table(s)
+                if not self._direct(s):
+                    dst = c.raw[i]
+                    ca = K.conv_args(view, lo, table, wt.Kc, wt.w_fwd, wt.w_fwd_lo, wt.ntaps_fwd * wt.Co_pad, wt.Co_pad,
+                                     dst.hi.data_ptr(), dst.fp32, (dst.sN, dst.sH, dst.sW), (0, 0), ho, wo,
+                                     bias=None if s.norm else wt.bias_pad,
+                                     stats=c.stats[c.stat_off[i]:] if s.norm else None, split=sp)
+                    nxt = c.act[i + 1]
+                    aa = L.ApplyArgs()
+                    aa.raw, aa.raw_fp32 = dst.hi.data_ptr(), 1 if dst.fp32 else 0
+                    aa.stats, aa.eps = (c.stats[c.stat_off[i]:].data_ptr() if s.norm else None), 1e-5
+                    aa.N, aa.H, aa.W, aa.C = self.N, ho, wo, wt.Co_pitch
+                    aa.act, aa.slope = s.act, 0.2
+                    if s.residual_from is not None:
+                        rb = c.act[s.residual_from]
+                        aa.res = rb.view(interior=True)
+                        aa.res_lo = rb.lo_ptr(interior=True)
+                    aa.dst, aa.dst_lo = nxt.hi.data_ptr(), (nxt.lo.data_ptr() if nxt.lo is not None else None)
+                    aa.pad = nxt.pad
+                    aa.pad_mode = L.PAD_REFLECT if self.specs[i + 1].in_reflect else L.PAD_ZERO
+                    args = (ca, aa)
+                else:
+                    dst = c.out if s.final else c.act[i + 1]
+                    assert dst.pad == 0
+                    ca = K.conv_args(view, lo, table, wt.Kc, wt.w_fwd, wt.w_fwd_lo, wt.ntaps_fwd * wt.Co_pad, wt.Co_pad,
+                                     dst.hi.data_ptr(), dst.fp32, (dst.sN, dst.sH, dst.sW), (0, 0), ho, wo,
+                                     bias=wt.bias_pad, act=s.act, split=sp)
+                    args = (ca, None)
+                self._args_cache[key] = args
+            ca, aa = args
+            K.run_conv(ca)
+            if aa is not None:
+                aa.drop_seed = (c.drop_seed * 1000003 + i + 1) if (s.dropout and c.drop_seed) else 0
+                K.run_apply(aa)
+            assert i < nst
+        return c
+
+    def output_nchw(self, c: Ctx):
+        y = torch.empty(self.N, self.Cout, self.Hout, self.Wout, dtype=torch.float32, device=self.device)
+        K.unpack_nhwc(c.out.hi, self.N, self.Cout, self.Hout, self.Wout, c.out.C, y)
+        return y
+
+    # ------------------------------------------------------------------ backward
+    def backward(self, c: Ctx, grad_out=None, need_dx=True, need_dw=True, accumulate_dw=False, gout_ready=False):
+        """grad_out: NCHW fp32 gradient of the network output (or gout_ready=True when self.gout was
+        filled by a fused loss kernel).  Weight-gradient slabs are accumulated in self.weights[i].dw
+        (zeroed first unless accumulate_dw).  Returns grad_in NCHW fp32 (or None)."""
+        self._ensure_scratch()
+        sp = self.split
+        N = self.N
+        if not gout_ready:
+            K.pack_nchw(grad_out.contiguous(), self.gout, L.PAD_ZERO)
+        self.bstats.zero_()
+        if need_dw and not accumulate_dw:
+            for wt in self.weights:
+                wt.dw.zero_()
+        nst = len(self.specs)
+        for i in range(nst - 1, -1, -1):
+            s, wt = self.specs[i], self.weights[i]
+            hin, win, ho, wo = self.geom[i]
+            key = ("b", id(c), i, need_dx, need_dw)
+            args = self._args_cache.get(key)
+            if args is None:
+                args = self._build_bwd_args(c, i, need_dx, need_dw)
+                self._args_cache[key] = args
+            ba, use_apply, wa, da = args
+            ba.drop_seed = (c.drop_seed * 1000003 + i + 1) if (s.dropout and c.drop_seed) else 0
+            K.run_bwd_prep(ba)
+            if use_apply:
+                K.run_bwd_apply(ba, self.draw, self.draw_lo)
+            if wa is not None:
+                K.run_wgrad(wa)
+            if da is not None:
+                K.run_conv(da)
+        gx = None
+        if need_dx:
+            s0 = self.specs[0]
+            gx = torch.empty(N, s0.Cin, self.H, self.W, dtype=torch.float32, device=self.device)
+            K.unpack_fold(self.gact[0], s0.Cin, gx, L.PAD_REFLECT if s0.in_reflect else L.PAD_ZERO)
+        return gx
+
+    def _draw_view(self, i, lo=False):
+        wt = self.weights[i]
+        _, _, ho, wo = self.geom[i]
+        t = self.draw_lo if lo else self.draw
+        cp = wt.Co_pitch
+        return L.make_view(t.data_ptr(), self.N, ho, wo, cp, ho * wo * cp, wo * cp, cp)
+
+    def _build_bwd_args(self, c: Ctx, i, need_dx, need_dw):
+        s, wt = self.specs[i], self.weights[i]
+        sp = self.split
+        N = self.N
+        hin, win, ho, wo = self.geom[i]
+        nst = len(self.specs)
+        cp = wt.Co_pitch
+        # ---- 1. elementwise backward -> dRaw in self.draw ------------------------------------
+        ba = L.BwdArgs()
+        ba.N, ba.H, ba.W, ba.C = N, ho, wo, cp
+        ba.eps, ba.slope = 1e-5, 0.2
+        ba.act = s.act
+        if i == nst - 1:
+            g = self.gout
+            ba.dyp, ba.dyp_fp32 = g.view(interior=False), 1 if g.fp32 else 0
+            ba.pad, ba.pad_mode = 0, L.PAD_NONE
+        else:
+            g = self.gact[i + 1]
+            nxt = self.specs[i + 1]
+            ba.dyp, ba.dyp_fp32 = g.view(interior=False), 1 if g.fp32 else 0
+            ba.pad = nxt.in_halo
+            ba.pad_mode = (L.PAD_REFLECT if nxt.in_reflect else L.PAD_ZERO) if nxt.in_halo else L.PAD_NONE
+        # residual-path gradients (generator): see _residual_plan
+        skip, gout_t = self.res_bwd.get(i, (None, None)) if hasattr(self, "res_bwd") else (None, None)
+        if skip is not None:
+            sb = self._resolve_t(skip, c.act[i + 1])
+            ba.skip, ba.skip_fp32 = sb.view(interior=False), 1 if sb.fp32 else 0
+        if gout_t is not None:
+            tb = self._resolve_t(gout_t, c.act[i + 1])
+            ba.g_out, ba.g_fp32 = tb.hi.data_ptr(), 1 if tb.fp32 else 0
+        ba.bstats = self.bstats[self.bstat_off[i]:].data_ptr()
+        if s.norm:
+            raw = c.raw[i]
+            ba.raw, ba.raw_fp32 = raw.hi.data_ptr(), 1 if raw.fp32 else 0
+            ba.stats = c.stats[c.stat_off[i]:].data_ptr()
+            ba.dz, ba.dz_fp32, ba.dz_lo = self.dz.data_ptr(), 1 if sp == 3 else 0, None
+            use_apply = True
+        else:
+            # activation applied in the GEMM epilogue: its output carries the sign (LeakyReLU) / value (tanh);
+            # in bf16x3 mode the pre-activation (bias included) is kept in raw[i] and has the same sign
+            src = c.out if s.final else (c.act[i + 1] if self._direct(s) else c.raw[i])
+            ba.raw, ba.raw_fp32 = src.hi.data_ptr(), 1 if src.fp32 else 0
+            ba.stats = None
+            ba.dz, ba.dz_fp32 = self.draw.data_ptr(), 0
+            ba.dz_lo = self.draw_lo.data_ptr() if self.draw_lo is not None else None
+            use_apply = False
+        # ---- 2. wgrad ------------------------------------------------------------------------
+        wa = None
+        if need_dw:
+            xview, xlo = self._x_view(s, wt, c.act[i])
+            dview = self._draw_view(i)
+            dlo = self.draw_lo.data_ptr() if self.draw_lo is not None else None
+            if s.kind == "convT":
+                table = G.taps_convT_dgrad(s.k, s.k, s.stride, s.pad)
+                wa = K.wgrad_args(xview, xlo, dview, dlo, table, wt.wg_Kc, wt.wg_rows, wt.dw, wt.wg_taps * wt.wg_rows,
+                                  split=sp)
+            else:
+                table = self._fwd_table(s)
+                wa = K.wgrad_args(dview, dlo, xview, xlo, table, wt.wg_Kc, wt.wg_rows, wt.dw, wt.wg_taps * wt.wg_rows,
+                                  split=sp)
+        # ---- 3. dgrad ------------------------------------------------------------------------
+        da = None
+        if (i > 0 or need_dx) and wt.need_dgrad:
+            gin = self.gact[i]
+            dview = self._draw_view(i)
+            dlo = self.draw_lo.data_ptr() if self.draw_lo is not None else None
+            if s.kind == "convT":
+                table = G.taps_convT_dgrad(s.k, s.k, s.stride, s.pad)
+                Ho_d, Wo_d = hin, win
+                yoff = (gin.pad, gin.pad)
+            else:
+                org = 0 if s.in_halo else -s.pad
+                table = G.taps_conv_dgrad(s.k, s.k, s.stride, org)
+                if s.in_halo:
+                    Ho_d, Wo_d, yoff = gin.Hp, gin.Wp, (0, 0)
+                else:
+                    Ho_d, Wo_d, yoff = hin, win, (0, 0)
+            da = K.conv_args(dview, dlo, table, wt.Kc_d, wt.w_dg, wt.w_dg_lo, s.k * s.k * wt.Ci_pad, wt.Ci_pad,
+                             gin.hi.data_ptr(), gin.fp32, (gin.sN, gin.sH, gin.sW), yoff, Ho_d, Wo_d, split=sp)
+        return ba, use_apply, wa, da
+
+    def _resolve_t(self, tag, like):
+        kind, idx = tag
+        if kind == "t":
+            return self._tbuf(idx, like)
+        return self.gact[idx]   # ("g", stage index): a dgrad output used directly as a total gradient
+
+    # ------------------------------------------------------------------ gradients -> parameters
+    def param_grads(self, scale=1.0, into=None):
+        """Unpack the wgrad slabs into parameter-shaped fp32 gradients.  Returns a list aligned with
+        [(weight, bias) for every stage]; biases cancelled by InstanceNorm get exact zeros."""
+        out = []
+        for i, (s, wt) in enumerate(zip(self.specs, self.weights)):
+            gw = torch.zeros_like(s.weight, dtype=torch.float32) if into is None else into[i][0]
+            K.run_wgrad_unpack(wt.unpack_wg, wt.dw, gw, scale)
+            gb = None
+            if s.bias is not None:
+                gb = torch.zeros_like(s.bias, dtype=torch.float32) if into is None else into[i][1]
+                if not s.norm:
+                    K.bias_grad(self.bstats[self.bstat_off[i]:], self.N, s.Cout, wt.Co_pitch, gb, scale)
+            out.append((gw, gb))
+        return out

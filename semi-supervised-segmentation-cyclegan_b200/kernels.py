@@ -181,8 +181,8 @@ def run_wgrad_unpack(a, slab, grad, scale=1.0):
 def pack_nchw(src, dst: ActBuf, pad_mode):
     N, Cc, H, W = src.shape
     assert src.dtype == torch.float32 and src.is_contiguous()
-    L.check(L.lib().sscg_pack_nchw(_ptr(src), N, Cc, H, W, _ptr(dst.hi), _ptr(dst.lo), dst.C, dst.pad, pad_mode,
-                                   _stream()), "sscg_pack_nchw")
+    L.check(L.lib().sscg_pack_nchw(_ptr(src), N, Cc, H, W, _ptr(dst.hi), _ptr(dst.lo), 1 if dst.fp32 else 0, dst.C,
+                                   dst.pad, pad_mode, _stream()), "sscg_pack_nchw")
 
 
 def onehot_pack(labels, Cc, dst: ActBuf, pad_mode):
@@ -194,6 +194,16 @@ def onehot_pack(labels, Cc, dst: ActBuf, pad_mode):
 
 def unpack_nhwc(src_f32, N, Cc, H, W, Cp, dst):
     L.check(L.lib().sscg_unpack_nhwc(_ptr(src_f32), N, Cc, H, W, Cp, _ptr(dst), _stream()), "sscg_unpack_nhwc")
+
+
+def unpack_fold(src: ActBuf, Cc, dst, pad_mode):
+    L.check(L.lib().sscg_unpack_fold(_ptr(src.hi), 1 if src.fp32 else 0, src.N, Cc, src.H, src.W, src.C, src.pad,
+                                     pad_mode, _ptr(dst), _stream()), "sscg_unpack_fold")
+
+
+def bias_grad(bstats, N, Cc, Cp, grad, scale=1.0):
+    L.check(L.lib().sscg_bias_grad(_ptr(bstats), N, Cc, Cp, _ptr(grad), C.c_float(scale), _stream()),
+            "sscg_bias_grad")
 
 
 def device_error():

@@ -1,0 +1,151 @@
+"""Autograd bridge between the nn.Module boundary (arch.*) and the stage engine.
+
+`NetRunner` is owned by one network module.  It builds the stage list once, keeps the bf16 weight
+slabs in sync with the fp32 parameters (re-derived whenever a parameter's version counter moves,
+i.e. after every optimizer step), caches one NetPlan per input shape and exposes the whole network
+as a single torch.autograd.Function so callers can keep composing losses with stock torch
+(reference model.py:398-468) and call .backward().
+"""
+import os
+from typing import Callable, List
+
+import torch
+
+from . import _lib as L
+from .engine import NetPlan, StageSpec, StageWeights
+
+_DEFAULT_PRECISION = os.environ.get("SSCG_PRECISION", "bf16")
+
+
+def set_default_precision(p: str):
+    """'bf16' (fast path) or 'bf16x3' (parity mode: hi/lo operand split, fp32 storage)."""
+    global _DEFAULT_PRECISION
+    if p not in ("bf16", "bf16x3"):
+        raise ValueError("precision must be 'bf16' or 'bf16x3'")
+    _DEFAULT_PRECISION = p
+
+
+def default_precision() -> str:
+    return _DEFAULT_PRECISION
+
+
+class NetRunner:
+    def __init__(self, build_specs: Callable[[], List[StageSpec]], residual_plan=None):
+        self._build_specs = build_specs
+        self._residual_plan = residual_plan
+        self.specs = None
+        self.weights = None
+        self.plans = {}
+        self.precision = None
+        self._wkey = None
+        self.device = None
+
+    def _setup(self, device, precision):
+        if self.specs is not None and self.precision == precision and self.device == device:
+            return
+        L.lib()   # fail loudly here if the extension is missing
+        self.specs = self._build_specs()
+        self.precision = precision
+        self.device = device
+        split = precision == "bf16x3"
+        self.weights = [StageWeights(s, split, True, device, first=(i == 0)) for i, s in enumerate(self.specs)]
+        self.plans = {}
+        self._wkey = None
+
+    def params(self):
+        ps = []
+        for s in self.specs:
+            ps.append(s.weight)
+            if s.bias is not None:
+                ps.append(s.bias)
+        return ps
+
+    def ensure_weights(self):
+        key = tuple((p.data_ptr(), p._version) for p in self.params())
+        if key != self._wkey:
+            with torch.no_grad():
+                for w in self.weights:
+                    w.prepare()
+            self._wkey = key
+
+    def plan(self, N, H, W) -> NetPlan:
+        k = (N, H, W)
+        p = self.plans.get(k)
+        if p is None:
+            p = NetPlan(self.specs, self.weights, N, H, W, self.precision, self.device)
+            if self._residual_plan is not None:
+                p.res_bwd = self._residual_plan(self.specs)
+            self.plans[k] = p
+        return p
+
+    def __call__(self, x, training, use_dropout, precision=None):
+        if not x.is_cuda:
+            raise RuntimeError("fused path needs CUDA tensors")
+        self._setup(x.device, precision or _DEFAULT_PRECISION)
+        params = self.params()
+        return _FusedNet.apply(self, training and use_dropout, x, *params)
+
+
+class _CtxLease:
+    """Returns the activation context to its plan when the autograd graph that holds it is freed
+    (also when backward is never run, e.g. model.py:409 `recon_lab_img`, which feeds no loss)."""
+
+    def __init__(self, plan, c):
+        self.plan, self.c = plan, c
+
+    def release(self):
+        if self.c is not None:
+            self.plan.release_ctx(self.c)
+            self.c = None
+
+    def __del__(self):
+        self.release()
+
+
+class _FusedNet(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, runner: NetRunner, dropout_on, x, *params):
+        x = x.detach()
+        if x.dtype != torch.float32:
+            x = x.float()
+        x = x.contiguous()
+        N, _, H, W = x.shape
+        runner.ensure_weights()
+        plan = runner.plan(N, H, W)
+        c = plan.acquire_ctx()
+        seed = 0
+        if dropout_on:
+            seed = int(torch.randint(1, 2 ** 31 - 1, (1,)).item())   # CPU generator: follows torch.manual_seed
+        plan.forward(c, x, training=dropout_on, drop_seed=seed)
+        y = plan.output_nchw(c)
+        need_grad = torch.is_grad_enabled() and any(ctx.needs_input_grad[2:])
+        if need_grad:
+            ctx.runner, ctx.plan, ctx.lease = runner, plan, _CtxLease(plan, c)
+        else:
+            plan.release_ctx(c)
+            ctx.plan = None
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        plan, c, runner = ctx.plan, ctx.lease.c, ctx.runner
+        if c is None:
+            raise RuntimeError("fused network: backward called twice on the same graph (activations were released)")
+        need_dx = ctx.needs_input_grad[2]
+        need_dw = any(ctx.needs_input_grad[3:])
+        gx = plan.backward(c, gy.float(), need_dx=need_dx, need_dw=need_dw)
+        grads = []
+        if need_dw:
+            pg = plan.param_grads()
+            flags = list(ctx.needs_input_grad[3:])
+            j = 0
+            for (gw, gb), s in zip(pg, plan.specs):
+                grads.append(gw if flags[j] else None)
+                j += 1
+                if s.bias is not None:
+                    grads.append(gb if flags[j] else None)
+                    j += 1
+        else:
+            grads = [None] * (len(ctx.needs_input_grad) - 3)
+        ctx.lease.release()
+        return (None, None, gx, *grads)
