@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""bench.py — training-step throughput of the semi-supervised CycleGAN hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--variant classic|head]
+
+One "step" = one full optimisation step of model.py:370-552 (generator phase + discriminator phase,
+both optimizer updates) on one synthetic batch per rank.  Workload at every N: BASELINE.json
+configs[1] — synthetic VOC 3x256x256 / 21 classes, batch 16 labeled + 16 unlabeled images per GPU,
+bf16 compute.  metric = labeled images per second summed over ranks (weak scaling).
+
+Prints ONE JSON line (rank 0).  `value` is device-timed with inputs resident in HBM; `e2e` is the
+same metric through the public host API (pinned host buffers -> H2D -> step -> D2H of the 9 losses).
+`--impl reference` times the reference's algorithm on the host CPU (the oracle port, all host
+threads) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "train_step_images_per_sec_256x256_bf16"
+UNIT = "img/s"
+H = W = 256
+NCLS = 21
+BATCH = 16
+
+
+# ------------------------------------------------------------------------------------------------
+# algorithmic FLOPs (SURVEY.md §8d / BASELINE.md §3): 1 MAC = 2 FLOP, transposed conv at 9 taps per
+# input pixel, backward of a conv = dgrad (+ wgrad when the net is trained)
+# ------------------------------------------------------------------------------------------------
+def f_gen(h, w, ci, co, ngf=64):
+    hw = h * w
+    return 2 * (hw * 49 * ngf * ci + (hw // 4) * 9 * ngf * 2 * ngf + (hw // 16) * 9 * 2 * ngf * 4 * ngf
+                + 18 * (hw // 16) * 9 * (4 * ngf) ** 2 + (hw // 16) * 9 * 4 * ngf * 2 * ngf
+                + (hw // 4) * 9 * 2 * ngf * ngf + hw * 49 * ngf * co)
+
+
+def f_dis(h, w, ci, ndf=64):
+    return 2 * ((h * w // 4) * 16 * ci * ndf + (h * w // 16) * 16 * ndf * 2 * ndf + (h * w // 64) * 16 * 2 * ndf * 4 * ndf
+                + (h // 8 - 1) * (w // 8 - 1) * 16 * 4 * ndf * 8 * ndf + (h // 8 - 2) * (w // 8 - 2) * 16 * 8 * ndf)
+
+
+def step_flops_per_sample(variant, h=H, w=W, c=NCLS, cimg=3):
+    """Per labeled sample per step.  Routes follow SURVEY.md §3.2: Gsi 3 fwd + 3 bwd, Gis 3 fwd + 2 bwd
+    (first-layer dgrad skipped where the input needs no gradient is ignored here: < 1 %)."""
+    gis, gsi = f_gen(h, w, c, cimg), f_gen(h, w, cimg, c)
+    di, ds = f_dis(h, w, cimg), f_dis(h, w, c)
+    fwd = 3 * gis + 3 * gsi
+    bwd = 2 * (2 * gis) + 3 * (2 * gsi)                    # dgrad + wgrad
+    # G phase discriminators (frozen): Di fwd + dgrad, Ds fwd only
+    fwd += di + ds
+    bwd += di
+    # D phase: 2 Di + 2 Ds forward, dgrad + wgrad each
+    fwd += 2 * di + 2 * ds
+    bwd += 2 * (2 * di) + 2 * (2 * ds)
+    if variant == "head":
+        fwd += 2 * gsi + 2 * gis + di                      # old_Gsi x2, old_Gis x2, old_Di(recon_img) in G phase
+        bwd += di                                          # dgrad through old_Di
+        fwd += 2 * di                                      # D phase: old_Di x2
+        bwd += 2 * (2 * di)
+        fwd -= 0
+    return fwd, bwd
+
+
+def res_conv_flops(n, h=H, w=W, ngf=64):
+    return 2 * n * (h // 4) * (w // 4) * 9 * (4 * ngf) * (4 * ngf)
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "200"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        return out
+
+
+def make_batches(n_batches, batch, device, seed, pin=False):
+    g = torch.Generator().manual_seed(seed)
+    out = []
+    for _ in range(n_batches):
+        l_img = torch.rand(batch, 3, H, W, generator=g) * 2 - 1
+        unl_img = torch.rand(batch, 3, H, W, generator=g) * 2 - 1
+        coarse = torch.randint(0, NCLS, (batch, 1, H // 16, W // 16), generator=g)      # blocky masks
+        l_gt = coarse.repeat_interleave(16, 2).repeat_interleave(16, 3).contiguous()
+        if pin:
+            out.append((l_img.pin_memory(), l_gt.pin_memory(), unl_img.pin_memory()))
+        else:
+            out.append((l_img.to(device), l_gt.to(device), unl_img.to(device)))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_step_factory(n, variant, threads=None):
+    """The reference's algorithm on the host CPU: oracle port (oracle/ref_step.py) + torch Adam
+    (model.py:286-287).  Returns (step callable, threads used)."""
+    from oracle import ref_step as RS
+    import sscg_b200  # noqa: F401
+    from sscg_b200.arch import define_Dis, define_Gen
+    if threads:
+        torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        nets = {"Gis": define_Gen(NCLS, 3, 64, "resnet_9blocks", "instance", False, []).state_dict(),
+                "Gsi": define_Gen(3, NCLS, 64, "resnet_9blocks_softmax", "instance", False, []).state_dict(),
+                "Di": define_Dis(3, 64, "n_layers", 3, "instance", []).state_dict(),
+                "Ds": define_Dis(NCLS, 64, "n_layers", 3, "instance", []).state_dict()}
+        if variant == "head":
+            nets["old_Gis"] = define_Gen(NCLS, 3, 64, "resnet_9blocks", "instance", False, []).state_dict()
+            nets["old_Gsi"] = define_Gen(3, NCLS, 64, "resnet_9blocks_softmax", "instance", False, []).state_dict()
+            nets["old_Di"] = define_Dis(3, 64, "n_layers", 3, "instance", []).state_dict()
+    nets = {k: {kk: vv.detach().clone() for kk, vv in sd.items()} for k, sd in nets.items()}
+    g_params = [p.requires_grad_(True) for k in ("Gis", "Gsi") for p in nets[k].values()]
+    d_params = [p.requires_grad_(True) for k in ("Di", "Ds") for p in nets[k].values()]
+    g_opt = torch.optim.Adam(g_params, lr=2e-4, betas=(0.5, 0.999))
+    d_opt = torch.optim.Adam(d_params, lr=2e-4, betas=(0.5, 0.999))
+    batches = make_batches(2, n, "cpu", 7)
+    state = {"i": 0}
+
+    def step():
+        l_img, l_gt, unl_img = batches[state["i"] % len(batches)]
+        state["i"] += 1
+        losses, grads, _ = RS.full_step(nets, l_img, l_gt, unl_img, NCLS, variant=variant, dead_forwards=True)
+        for k in ("Gis", "Gsi"):
+            for name, p in nets[k].items():
+                p.grad = grads[k][name]
+        g_opt.step()
+        for k in ("Di", "Ds"):
+            for name, p in nets[k].items():
+                p.grad = grads[k][name]
+        d_opt.step()
+        return losses
+
+    return step, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = args.ref_batch
+    step, threads = cpu_reference_step_factory(n, args.variant)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    value = n * args.steps / dt
+    sample = "%d-image (of %d) 256x256 batch per step, %s variant, fp32, oracle port + torch Adam" % (n, BATCH, args.variant)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "configs[1]: full semisupervised_cycleGAN step, synthetic VOC 3x256x256 / 21-class",
+                       "variant": args.variant, "per_step_sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    import sscg_b200  # noqa: F401
+    from sscg_b200 import kernels as K
+    from sscg_b200.step import SemiSupCycleGAN
+
+    import contextlib
+    import io
+    torch.manual_seed(0)          # identical initial weights on every rank
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = SemiSupCycleGAN(n_classes=NCLS, variant=args.variant, use_dropout=not args.no_dropout, device=dev,
+                                precision=args.precision)
+    if world > 1:
+        for p in list(model.g_grads.params) + list(model.d_grads.params):
+            dist.broadcast(p.data, 0)
+    dev_batches = make_batches(3, args.batch, dev, 100 + rank)
+    host_batches = make_batches(3, args.batch, dev, 100 + rank, pin=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        model.train_step(*dev_batches[i % 3])
+    barrier()
+    # ---- timed region: device-resident inputs -----------------------------------------------
+    sampler = ClockSampler(local) if rank == 0 else None
+    l0 = K.launch_count()
+    K.prof_begin()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        model.train_step(*dev_batches[i % 3])
+    e1.record()
+    barrier()
+    prof, prof_complete = K.prof_end()
+    launches = K.launch_count() - l0
+    clocks = sampler.stop() if sampler else None
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    # ---- end-to-end region: pinned host buffers, H2D + D2H inside ---------------------------
+    for i in range(2):
+        model.train_step_host(*host_batches[i % 3])
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        last = model.train_step_host(*host_batches[i % 3])
+    torch.cuda.synchronize()
+    t_e2e = torch.tensor([time.perf_counter() - t0], device=dev)
+    if world > 1:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    t_e2e = float(t_e2e.item())
+    dev_err = K.device_error()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    # ---- derived numbers ------------------------------------------------------------------------
+    peaks, peak_src = load_peaks()
+    ms_step = ms_total / args.steps
+    value = world * args.batch / (ms_step / 1e3)
+    fwd, bwd = step_flops_per_sample(args.variant)
+    tf_step = (fwd + bwd) * args.batch / 1e12
+    res_ms, res_n = prof.get("res_conv_fwd", (0.0, 0))
+    roof = None
+    if res_n:
+        achieved = res_conv_flops(args.batch) / 1e12 / (res_ms / res_n / 1e3)
+        peak = peaks["bf16_tflops_sustained"]
+        roof = {"bound": "tensor", "kernel": "conv_igemm<BN=256> 3x3 256->256 @64x64 (residual-block conv, forward)",
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": peak_src + " (sustained cuBLAS bf16: kernel timed inside a long step)",
+                "avg_launch_ms": res_ms / res_n, "launches_timed": res_n,
+                "algorithmic_flops_per_launch": res_conv_flops(args.batch)}
+    h2d = sum(t.numel() * t.element_size() for t in host_batches[0])
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if args.precision == "bf16" else "bf16x3", "data": "synthetic",
+            "config": {"workload": "configs[1]: full semisupervised_cycleGAN step, synthetic VOC 3x256x256 / 21-class, "
+                                   "bs=16 labeled + 16 unlabeled per GPU, Gis/Gsi = resnet_9blocks[_softmax], "
+                                   "Di/Ds = n_layers(3), dropout %s" % ("off" if args.no_dropout else "on"),
+                       "variant": args.variant, "batch_per_gpu": args.batch, "global_batch": world * args.batch,
+                       "parallelism": "dp%d" % world, "precision": args.precision,
+                       "l2": "working set per step (several GB of activations) exceeds the 126 MB L2; no explicit flush",
+                       "algorithmic_tflop_per_step_per_gpu": tf_step,
+                       "step_tflops_achieved": tf_step / (ms_step / 1e3),
+                       "step_frac_of_sustained_peak": tf_step / (ms_step / 1e3) / peaks["bf16_tflops_sustained"]},
+            "roofline": roof,
+            "kernel_time_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()},
+            "kernel_launches_per_step": {k: v[1] / args.steps for k, v in prof.items()},
+            "kernel_profile_complete": prof_complete,
+            "e2e": {"value": world * args.batch * args.steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": 9 * 4, "ms_per_step": t_e2e / args.steps * 1e3},
+            "gpu_launches": launches, "clocks": clocks, "device_error": dev_err,
+            "losses_last_step": last}
+    if world == 1 and not args.no_cpu_baseline:
+        step, threads = cpu_reference_step_factory(args.ref_batch, args.variant)
+        t0 = time.perf_counter()
+        step()
+        dt = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": args.ref_batch / dt, "unit": UNIT, "cores": threads, "kind": "port",
+                                "sample": "1 step on a %d-image (of %d) 256x256 batch, %s variant, fp32, oracle port + "
+                                          "torch Adam, %.1f s" % (args.ref_batch, BATCH, args.variant, dt)}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--variant", default="classic", choices=["classic", "head"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16x3"])
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--ref-batch", type=int, default=1, help="images per CPU-reference step (bounded sample)")
+    ap.add_argument("--no-dropout", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -87,6 +87,7 @@ typedef struct SscgConvArgs {
     float* stats;          /* [N][Co_pad][2] fp32 (sum, sum of squares), accumulated atomically; or NULL */
     int32_t TH, TW;        /* output tile, TH*TW == 128 */
     int32_t BN;            /* N tile: 16, 32, 64, 128 or 256 */
+    int32_t tag;           /* profiling class (0..15), see sscg_prof_begin */
 } SscgConvArgs;
 
 int sscg_conv_igemm(const SscgConvArgs* a, void* stream);
@@ -112,6 +113,7 @@ typedef struct SscgWgradArgs {
     int32_t TH, TW;        /* pixel block, TH*TW == 64 */
     int32_t BN;            /* K-column tile of dWt: 64, 128 or 256 (divides Kc) */
     int32_t ksplit;        /* number of CTAs sharing one (tap, co-tile, k-tile) */
+    int32_t tag;           /* profiling class (0..15) */
 } SscgWgradArgs;
 
 int sscg_conv_wgrad(const SscgWgradArgs* a, void* stream);
@@ -211,6 +213,15 @@ int sscg_fill_zero(void* ptr, int64_t bytes, void* stream);
 const char* sscg_last_error(void);
 int sscg_device_error(void);   /* reads (and clears) the device-side protocol error flag; 0 = none */
 int sscg_version(void);
+
+/* Measurement hooks (bench.py): every launcher counts its launch; while profiling is on, launches
+ * are bracketed by CUDA events on their own stream and accumulated per `tag`
+ * (conv/wgrad: the tag in the argument block; elementwise kernels: 7 = apply, 8 = backward
+ * prep/apply, 9 = pack/unpack/weight prep).  sscg_prof_end synchronises the device and returns the
+ * summed milliseconds and launch counts per tag (arrays of 16). */
+uint64_t sscg_launch_count(void);
+int sscg_prof_begin(void);
+int sscg_prof_end(float* sum_ms, int32_t* count);
 
 #ifdef __cplusplus
 }

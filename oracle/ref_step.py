@@ -47,7 +47,8 @@ def _req(sd, flag):
     return {k: v.detach().clone().requires_grad_(flag) for k, v in sd.items()}
 
 
-def generator_phase(nets, l_img, l_gt, unl_img, C, variant="classic", w=StepWeights(), emulate_bf16=False):
+def generator_phase(nets, l_img, l_gt, unl_img, C, variant="classic", w=StepWeights(), emulate_bf16=False,
+                    dead_forwards=False):
     """model.py:379-474 up to (not including) g_optimizer.step().
     nets: dict of state_dicts {"Gis","Gsi","Di","Ds"[,"old_Gis","old_Gsi","old_Di"]}.
     Returns (losses dict, grads dict {"Gis": {...}, "Gsi": {...}}, tensors needed by the D phase)."""
@@ -61,7 +62,11 @@ def generator_phase(nets, l_img, l_gt, unl_img, C, variant="classic", w=StepWeig
     lab_gt_p = F.softmax(lab_gt, dim=1)                                   # :401
     fake_gt_p = F.softmax(fake_gt, dim=1)                                 # :402
     recon_img = _gen(Gis, fake_gt_p, True, e)                             # :408
-    # recon_lab_img = Gis(lab_gt_p) (model.py:409) feeds no loss: omitted from the graph, see SURVEY §3.2 step 5
+    # recon_lab_img = Gis(lab_gt_p) (model.py:409) feeds no loss: it cannot change any
+    # result; `dead_forwards=True` still executes it so that CPU-baseline timings do the reference's work
+    if dead_forwards:
+        with torch.no_grad():
+            _gen(Gis, lab_gt_p.detach(), True, e)
     recon_gt = _gen(Gsi, fake_img, False, e)                              # :410
     fake_img_dis = _dis(Di, fake_img, e)                                  # :431
     fake_gt_oh = RA.argmax_one_hot(fake_gt_p, C)                          # :435-437
@@ -76,6 +81,9 @@ def generator_phase(nets, l_img, l_gt, unl_img, C, variant="classic", w=StepWeig
         old_Di = _req(nets["old_Di"], False)
         resnet_fake_gt = F.softmax(_gen(old_Gsi, unl_img, False, e), dim=1)       # :418,421
         resnet_recon_img = _gen(old_Gis, resnet_fake_gt, True, e)                 # :422
+        if dead_forwards:                                                         # :419,423 (unused results)
+            with torch.no_grad():
+                _gen(old_Gis, F.softmax(_gen(old_Gsi, l_img, False, e), dim=1), True, e)
         img_cycle_loss = _mse_to(_dis(old_Di, recon_img, e), 1.0)                 # :432,452
         unsup = w.adversarial_weight * (img_gen_loss + gt_gen_loss) + img_cycle_loss + gt_cycle_loss * w.lamda_gt  # :466
         extra["resnet_recon_img"] = resnet_recon_img.detach()
@@ -126,12 +134,13 @@ def discriminator_phase(nets, l_gt, unl_img, fake_img, fake_gt, recon_img, C, va
     return losses, grads
 
 
-def full_step(nets, l_img, l_gt, unl_img, C, variant="classic", w=StepWeights(), emulate_bf16=False):
+def full_step(nets, l_img, l_gt, unl_img, C, variant="classic", w=StepWeights(), emulate_bf16=False,
+              dead_forwards=False):
     """One step with an empty history pool (pool passes the current batch through, utils.py:286-289).
     NOTE: the reference updates the generators (g_optimizer.step(), model.py:474) before the D phase,
     but the D phase only consumes tensors produced before that update, so gradients of both phases
     are functions of the pre-step weights."""
-    gl, gg, t = generator_phase(nets, l_img, l_gt, unl_img, C, variant, w, emulate_bf16)
+    gl, gg, t = generator_phase(nets, l_img, l_gt, unl_img, C, variant, w, emulate_bf16, dead_forwards)
     dl, dg = discriminator_phase(nets, l_gt, unl_img, t["fake_img"], t["fake_gt"], t["recon_img"], C, variant, w,
                                  t.get("resnet_recon_img"), emulate_bf16)
     losses = dict(gl)

@@ -40,7 +40,7 @@ class ConvArgs(C.Structure):
         ("y_oh", C.c_int32), ("y_ow", C.c_int32), ("Ho", C.c_int32), ("Wo", C.c_int32),
         ("bias", C.c_void_p), ("act", C.c_int32), ("slope", C.c_float),
         ("stats", C.c_void_p),
-        ("TH", C.c_int32), ("TW", C.c_int32), ("BN", C.c_int32),
+        ("TH", C.c_int32), ("TW", C.c_int32), ("BN", C.c_int32), ("tag", C.c_int32),
     ]
 
 
@@ -51,7 +51,7 @@ class WgradArgs(C.Structure):
         ("n_taps", C.c_int32), ("taps", Tap * SSCG_MAX_TAPS),
         ("Co_pad", C.c_int32), ("split", C.c_int32),
         ("dw", C.c_void_p), ("w_rows", C.c_int32),
-        ("TH", C.c_int32), ("TW", C.c_int32), ("BN", C.c_int32), ("ksplit", C.c_int32),
+        ("TH", C.c_int32), ("TW", C.c_int32), ("BN", C.c_int32), ("ksplit", C.c_int32), ("tag", C.c_int32),
     ]
 
 
@@ -113,6 +113,8 @@ _SIGNATURES = {
     "sscg_fill_zero": [C.c_void_p, C.c_int64, C.c_void_p],
     "sscg_device_error": [],
     "sscg_version": [],
+    "sscg_prof_begin": [],
+    "sscg_prof_end": [C.POINTER(C.c_float), C.POINTER(C.c_int32)],
 }
 
 _lib = None
@@ -120,7 +122,7 @@ _lib = None
 
 def exported_symbols():
     """Names every entry point include/sscg_b200.h declares (used by the CPU-side ABI test)."""
-    return list(_SIGNATURES.keys()) + ["sscg_last_error"]
+    return list(_SIGNATURES.keys()) + ["sscg_last_error", "sscg_launch_count"]
 
 
 def lib():
@@ -140,6 +142,8 @@ def lib():
         fn.restype = C.c_int
     l.sscg_last_error.restype = C.c_char_p
     l.sscg_last_error.argtypes = []
+    l.sscg_launch_count.restype = C.c_uint64
+    l.sscg_launch_count.argtypes = []
     _lib = l
     return l
 

@@ -67,7 +67,60 @@ int encode_2d(CUtensorMap* tm, const void* ptr, int cols, int rows, int box_cols
     return 0;
 }
 
+// ---- launch accounting / per-tag event timing ---------------------------------------------------
+static unsigned long long g_launches = 0;
+constexpr int kProfMax = 8192;
+static struct {
+    bool on = false;
+    bool created = false;
+    int n = 0;
+    cudaEvent_t ev[2 * kProfMax];
+    int tag[kProfMax];
+} g_prof;
+
+LaunchScope::LaunchScope(int tag, cudaStream_t s) : slot(-1), stream(s) {
+    ++g_launches;
+    if (g_prof.on && g_prof.n < kProfMax) {
+        slot = g_prof.n++;
+        g_prof.tag[slot] = tag & 15;
+        cudaEventRecord(g_prof.ev[2 * slot], stream);
+    }
+}
+LaunchScope::~LaunchScope() {
+    if (slot >= 0) cudaEventRecord(g_prof.ev[2 * slot + 1], stream);
+}
+
 }  // namespace sscg
+
+extern "C" uint64_t sscg_launch_count(void) { return sscg::g_launches; }
+
+extern "C" int sscg_prof_begin(void) {
+    using namespace sscg;
+    if (!g_prof.created) {
+        for (int i = 0; i < 2 * kProfMax; ++i)
+            if (cudaEventCreate(&g_prof.ev[i]) != cudaSuccess) return set_error("prof_begin: cudaEventCreate failed");
+        g_prof.created = true;
+    }
+    g_prof.n = 0;
+    g_prof.on = true;
+    return 0;
+}
+
+extern "C" int sscg_prof_end(float* sum_ms, int32_t* count) {
+    using namespace sscg;
+    g_prof.on = false;
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) return set_error("prof_end: %s", cudaGetErrorString(e));
+    for (int t = 0; t < 16; ++t) { sum_ms[t] = 0.f; count[t] = 0; }
+    for (int i = 0; i < g_prof.n; ++i) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, g_prof.ev[2 * i], g_prof.ev[2 * i + 1]) == cudaSuccess) {
+            sum_ms[g_prof.tag[i]] += ms;
+            count[g_prof.tag[i]] += 1;
+        }
+    }
+    return g_prof.n >= kProfMax ? 2 : 0;   // 2: event pool exhausted (partial coverage)
+}
 
 extern "C" const char* sscg_last_error(void) { return sscg::g_err; }
 extern "C" int sscg_version(void) { return 100; }

@@ -292,7 +292,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 // ------------------------------------------------------------------------------------------------
 template <int BN, int SPLIT>
 static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmAlo, const CUtensorMap& tmB,
-                        const CUtensorMap& tmBlo, const ConvDev& d, dim3 grid, cudaStream_t stream) {
+                        const CUtensorMap& tmBlo, const ConvDev& d, dim3 grid, cudaStream_t stream, int tag) {
     using Cfg = IgemmCfg<BN, SPLIT>;
     static bool configured = false;
     if (!configured) {
@@ -302,7 +302,10 @@ static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmAlo, const 
                                                cudaGetErrorString(e));
         configured = true;
     }
-    conv_igemm_kernel<BN, SPLIT><<<grid, 192, Cfg::kSmemBytes, stream>>>(tmA, tmAlo, tmB, tmBlo, d);
+    {
+        LaunchScope ls(tag, stream);
+        conv_igemm_kernel<BN, SPLIT><<<grid, 192, Cfg::kSmemBytes, stream>>>(tmA, tmAlo, tmB, tmBlo, d);
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_error("conv_igemm<%d,%d> launch: %s", BN, SPLIT, cudaGetErrorString(e));
     return 0;
@@ -357,8 +360,8 @@ extern "C" int sscg_conv_igemm(const SscgConvArgs* a, void* stream_) {
     dim3 grid((unsigned)(d.tiles_h * d.tiles_w * d.N), (unsigned)(a->Co_pad / a->BN), (unsigned)a->n_phases);
 #define SSCG_DISPATCH(BN_)                                                                       \
     case BN_:                                                                                     \
-        return a->split == 3 ? launch_igemm<BN_, 3>(tmA, tmAlo, tmB, tmBlo, d, grid, stream)      \
-                             : launch_igemm<BN_, 1>(tmA, tmAlo, tmB, tmBlo, d, grid, stream);
+        return a->split == 3 ? launch_igemm<BN_, 3>(tmA, tmAlo, tmB, tmBlo, d, grid, stream, a->tag)      \
+                             : launch_igemm<BN_, 1>(tmA, tmAlo, tmB, tmBlo, d, grid, stream, a->tag);
     switch (a->BN) {
         SSCG_DISPATCH(16)
         SSCG_DISPATCH(32)

@@ -193,7 +193,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
 
 template <int BN, int SPLIT>
 static int launch_wgrad(const CUtensorMap& tmDy, const CUtensorMap& tmDyLo, const CUtensorMap& tmX,
-                        const CUtensorMap& tmXLo, const WgradDev& d, dim3 grid, cudaStream_t stream) {
+                        const CUtensorMap& tmXLo, const WgradDev& d, dim3 grid, cudaStream_t stream, int tag) {
     using Cfg = WgradCfg<BN, SPLIT>;
     static bool configured = false;
     if (!configured) {
@@ -202,7 +202,10 @@ static int launch_wgrad(const CUtensorMap& tmDy, const CUtensorMap& tmDyLo, cons
         if (e != cudaSuccess) return set_error("conv_wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         configured = true;
     }
-    conv_wgrad_kernel<BN, SPLIT><<<grid, 192, Cfg::kSmemBytes, stream>>>(tmDy, tmDyLo, tmX, tmXLo, d);
+    {
+        LaunchScope ls(tag, stream);
+        conv_wgrad_kernel<BN, SPLIT><<<grid, 192, Cfg::kSmemBytes, stream>>>(tmDy, tmDyLo, tmX, tmXLo, d);
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_error("conv_wgrad<%d,%d> launch: %s", BN, SPLIT, cudaGetErrorString(e));
     return 0;
@@ -247,8 +250,8 @@ extern "C" int sscg_conv_wgrad(const SscgWgradArgs* a, void* stream_) {
     dim3 grid((unsigned)a->ksplit, (unsigned)(m_tiles * d.n_ktiles), (unsigned)a->n_taps);
 #define SSCG_WG(BN_)                                                                          \
     case BN_:                                                                                  \
-        return a->split == 3 ? launch_wgrad<BN_, 3>(tmDy, tmDyLo, tmX, tmXLo, d, grid, stream) \
-                             : launch_wgrad<BN_, 1>(tmDy, tmDyLo, tmX, tmXLo, d, grid, stream);
+        return a->split == 3 ? launch_wgrad<BN_, 3>(tmDy, tmDyLo, tmX, tmXLo, d, grid, stream, a->tag) \
+                             : launch_wgrad<BN_, 1>(tmDy, tmDyLo, tmX, tmXLo, d, grid, stream, a->tag);
     switch (a->BN) {
         SSCG_WG(64)
         SSCG_WG(128)

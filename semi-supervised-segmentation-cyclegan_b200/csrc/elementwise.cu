@@ -494,8 +494,11 @@ extern "C" int sscg_pack_nchw(const float* src, int32_t N, int32_t C, int32_t H,
                               int32_t dst_fp32, int32_t Cp, int32_t pad, int32_t pad_mode, void* stream) {
     if (Cp % 8 || Cp < C) return set_error("pack_nchw: Cp=%d must be a multiple of 8 and >= C=%d", Cp, C);
     const long long total = (long long)N * (H + 2 * pad) * (W + 2 * pad);
-    pack_kernel<false><<<ew_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        src, nullptr, N, C, H, W, dst, dst_lo, Cp, pad, pad_mode, dst_fp32);
+    {
+        LaunchScope ls_(9, static_cast<cudaStream_t>(stream));
+        pack_kernel<false><<<ew_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+            src, nullptr, N, C, H, W, dst, dst_lo, Cp, pad, pad_mode, dst_fp32);
+    }
     SSCG_CHECK_LAUNCH("pack_nchw");
     return 0;
 }
@@ -504,8 +507,11 @@ extern "C" int sscg_onehot_pack(const int64_t* labels, int32_t N, int32_t C, int
                                 void* dst_lo, int32_t Cp, int32_t pad, int32_t pad_mode, void* stream) {
     if (Cp % 8 || Cp < C) return set_error("onehot_pack: Cp=%d must be a multiple of 8 and >= C=%d", Cp, C);
     const long long total = (long long)N * (H + 2 * pad) * (W + 2 * pad);
-    pack_kernel<true><<<ew_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        nullptr, reinterpret_cast<const long long*>(labels), N, C, H, W, dst, dst_lo, Cp, pad, pad_mode, 0);
+    {
+        LaunchScope ls_(9, static_cast<cudaStream_t>(stream));
+        pack_kernel<true><<<ew_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+            nullptr, reinterpret_cast<const long long*>(labels), N, C, H, W, dst, dst_lo, Cp, pad, pad_mode, 0);
+    }
     SSCG_CHECK_LAUNCH("onehot_pack");
     return 0;
 }
@@ -513,7 +519,10 @@ extern "C" int sscg_onehot_pack(const int64_t* labels, int32_t N, int32_t C, int
 extern "C" int sscg_unpack_nhwc(const float* src, int32_t N, int32_t C, int32_t H, int32_t W, int32_t Cp, float* dst,
                                 void* stream) {
     const long long total = (long long)N * H * W;
-    unpack_kernel<<<ew_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, N, C, H, W, Cp, dst);
+    {
+        LaunchScope ls_(9, static_cast<cudaStream_t>(stream));
+        unpack_kernel<<<ew_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, N, C, H, W, Cp, dst);
+    }
     SSCG_CHECK_LAUNCH("unpack_nhwc");
     return 0;
 }
@@ -522,15 +531,21 @@ extern "C" int sscg_unpack_fold(const void* src, int32_t src_fp32, int32_t N, in
                                 int32_t Cp, int32_t pad, int32_t pad_mode, float* dst, void* stream) {
     if (Cp % 8) return set_error("unpack_fold: Cp=%d must be a multiple of 8", Cp);
     const long long total = (long long)N * H * W;
-    unpack_fold_kernel<<<ew_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, src_fp32, N, C, H, W, Cp,
-                                                                                         pad, pad_mode, dst);
+    {
+        LaunchScope ls_(9, static_cast<cudaStream_t>(stream));
+        unpack_fold_kernel<<<ew_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, src_fp32, N, C, H, W, Cp,
+                                                                                             pad, pad_mode, dst);
+    }
     SSCG_CHECK_LAUNCH("unpack_fold");
     return 0;
 }
 
 extern "C" int sscg_bias_grad(const float* bstats, int32_t N, int32_t C, int32_t Cp, float* grad, float scale,
                               void* stream) {
-    bias_grad_kernel<<<(C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(bstats, N, C, Cp, grad, scale);
+    {
+        LaunchScope ls_(9, static_cast<cudaStream_t>(stream));
+        bias_grad_kernel<<<(C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(bstats, N, C, Cp, grad, scale);
+    }
     SSCG_CHECK_LAUNCH("bias_grad");
     return 0;
 }
@@ -541,7 +556,10 @@ extern "C" int sscg_in_apply(const SscgApplyArgs* a, void* stream) {
     d.a = *a;
     int gridx;
     vec_layout(a->C, (long long)(a->H + 2 * a->pad) * (a->W + 2 * a->pad), d.CH, d.rows, d.iters, gridx);
-    in_apply_kernel<<<dim3(gridx, a->N), 256, 0, static_cast<cudaStream_t>(stream)>>>(d);
+    {
+        LaunchScope ls_(7, static_cast<cudaStream_t>(stream));
+        in_apply_kernel<<<dim3(gridx, a->N), 256, 0, static_cast<cudaStream_t>(stream)>>>(d);
+    }
     SSCG_CHECK_LAUNCH("in_apply");
     return 0;
 }
@@ -552,7 +570,10 @@ extern "C" int sscg_in_bwd_prep(const SscgBwdArgs* a, void* stream) {
     d.a = *a; d.draw = nullptr; d.draw_lo = nullptr;
     int gridx;
     vec_layout(a->C, (long long)a->H * a->W, d.CH, d.rows, d.iters, gridx);
-    in_bwd_prep_kernel<<<dim3(gridx, a->N), 256, 0, static_cast<cudaStream_t>(stream)>>>(d);
+    {
+        LaunchScope ls_(8, static_cast<cudaStream_t>(stream));
+        in_bwd_prep_kernel<<<dim3(gridx, a->N), 256, 0, static_cast<cudaStream_t>(stream)>>>(d);
+    }
     SSCG_CHECK_LAUNCH("in_bwd_prep");
     return 0;
 }
@@ -564,21 +585,30 @@ extern "C" int sscg_in_bwd_apply(const SscgBwdArgs* a, void* draw, void* draw_lo
     d.a = *a; d.draw = draw; d.draw_lo = draw_lo;
     int gridx;
     vec_layout(a->C, (long long)a->H * a->W, d.CH, d.rows, d.iters, gridx);
-    in_bwd_apply_kernel<<<dim3(gridx, a->N), 256, 0, static_cast<cudaStream_t>(stream)>>>(d);
+    {
+        LaunchScope ls_(8, static_cast<cudaStream_t>(stream));
+        in_bwd_apply_kernel<<<dim3(gridx, a->N), 256, 0, static_cast<cudaStream_t>(stream)>>>(d);
+    }
     SSCG_CHECK_LAUNCH("in_bwd_apply");
     return 0;
 }
 
 extern "C" int sscg_wprep(const SscgWprepArgs* a, void* stream) {
     const long long total = (long long)(a->mode == 1 ? a->KH : a->KH * a->KW) * a->rows_pad * a->Kc;
-    wprep_kernel<<<ew_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(*a);
+    {
+        LaunchScope ls_(9, static_cast<cudaStream_t>(stream));
+        wprep_kernel<<<ew_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(*a);
+    }
     SSCG_CHECK_LAUNCH("wprep");
     return 0;
 }
 
 extern "C" int sscg_wgrad_unpack(const SscgWprepArgs* a, const float* slab, float* grad, float scale, void* stream) {
     const long long total = (long long)(a->mode == 1 ? a->KH : a->KH * a->KW) * a->rows_pad * a->Kc;
-    wgrad_unpack_kernel<<<ew_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(*a, slab, grad, scale);
+    {
+        LaunchScope ls_(9, static_cast<cudaStream_t>(stream));
+        wgrad_unpack_kernel<<<ew_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(*a, slab, grad, scale);
+    }
     SSCG_CHECK_LAUNCH("wgrad_unpack");
     return 0;
 }

@@ -17,6 +17,14 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 PFN_encodeTiled get_encode_tiled();
 
+// Launch accounting + optional CUDA-event bracketing per profiling tag (see sscg_prof_begin).
+struct LaunchScope {
+    int slot;
+    cudaStream_t stream;
+    LaunchScope(int tag, cudaStream_t s);
+    ~LaunchScope();
+};
+
 // 4-D map over an NHWC bf16 view: dims (C, W, H, N), 128B swizzle, zero fill outside the view.
 int encode_view_4d(CUtensorMap* tm, const SscgView& v, const void* ptr, const uint32_t box[4], const uint32_t es[4]);
 // 2-D map over a row-major bf16 matrix [rows][cols]

@@ -270,7 +270,8 @@ class NetPlan:
                     ca = K.conv_args(view, lo, table, wt.Kc, wt.w_fwd, wt.w_fwd_lo, wt.ntaps_fwd * wt.Co_pad, wt.Co_pad,
                                      dst.hi.data_ptr(), dst.fp32, (dst.sN, dst.sH, dst.sW), (0, 0), ho, wo,
                                      bias=None if s.norm else wt.bias_pad,
-                                     stats=c.stats[c.stat_off[i]:] if s.norm else None, split=sp)
+                                     stats=c.stats[c.stat_off[i]:] if s.norm else None, split=sp,
+                                     tag=1 if s.name.startswith("res") else 4)
                     nxt = c.act[i + 1]
                     aa = L.ApplyArgs()
                     aa.raw, aa.raw_fp32 = dst.hi.data_ptr(), 1 if dst.fp32 else 0
@@ -290,7 +291,7 @@ class NetPlan:
                     assert dst.pad == 0
                     ca = K.conv_args(view, lo, table, wt.Kc, wt.w_fwd, wt.w_fwd_lo, wt.ntaps_fwd * wt.Co_pad, wt.Co_pad,
                                      dst.hi.data_ptr(), dst.fp32, (dst.sN, dst.sH, dst.sW), (0, 0), ho, wo,
-                                     bias=wt.bias_pad, act=s.act, split=sp)
+                                     bias=wt.bias_pad, act=s.act, split=sp, tag=4)
                     args = (ca, None)
                 self._args_cache[key] = args
             ca, aa = args
@@ -307,7 +308,8 @@ class NetPlan:
         return y
 
     # ------------------------------------------------------------------ backward
-    def backward(self, c: Ctx, grad_out=None, need_dx=True, need_dw=True, accumulate_dw=False, gout_ready=False):
+    def backward(self, c: Ctx, grad_out=None, need_dx=True, need_dw=True, accumulate_dw=False, gout_ready=False,
+                 debug_hook=None):
         """grad_out: NCHW fp32 gradient of the network output (or gout_ready=True when self.gout was
         filled by a fused loss kernel).  Weight-gradient slabs are accumulated in self.weights[i].dw
         (zeroed first unless accumulate_dw).  Returns grad_in NCHW fp32 (or None)."""
@@ -338,6 +340,8 @@ class NetPlan:
                 K.run_wgrad(wa)
             if da is not None:
                 K.run_conv(da)
+            if debug_hook is not None:
+                debug_hook(i, self)
         gx = None
         if need_dx:
             s0 = self.specs[0]
@@ -407,11 +411,11 @@ class NetPlan:
             if s.kind == "convT":
                 table = G.taps_convT_dgrad(s.k, s.k, s.stride, s.pad)
                 wa = K.wgrad_args(xview, xlo, dview, dlo, table, wt.wg_Kc, wt.wg_rows, wt.dw, wt.wg_taps * wt.wg_rows,
-                                  split=sp)
+                                  split=sp, tag=6)
             else:
                 table = self._fwd_table(s)
                 wa = K.wgrad_args(dview, dlo, xview, xlo, table, wt.wg_Kc, wt.wg_rows, wt.dw, wt.wg_taps * wt.wg_rows,
-                                  split=sp)
+                                  split=sp, tag=3 if s.name.startswith("res") else 6)
         # ---- 3. dgrad ------------------------------------------------------------------------
         da = None
         if (i > 0 or need_dx) and wt.need_dgrad:
@@ -430,7 +434,8 @@ class NetPlan:
                 else:
                     Ho_d, Wo_d, yoff = hin, win, (0, 0)
             da = K.conv_args(dview, dlo, table, wt.Kc_d, wt.w_dg, wt.w_dg_lo, s.k * s.k * wt.Ci_pad, wt.Ci_pad,
-                             gin.hi.data_ptr(), gin.fp32, (gin.sN, gin.sH, gin.sW), yoff, Ho_d, Wo_d, split=sp)
+                             gin.hi.data_ptr(), gin.fp32, (gin.sN, gin.sH, gin.sW), yoff, Ho_d, Wo_d, split=sp,
+                             tag=2 if s.name.startswith("res") else 5)
         return ba, use_apply, wa, da
 
     def _resolve_t(self, tag, like):

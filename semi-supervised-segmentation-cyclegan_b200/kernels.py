@@ -90,7 +90,7 @@ def fill_taps(dst_taps, table: TapTable):
 
 
 def conv_args(xview, x_lo, table: TapTable, Kc, w, w_lo, w_rows, Co_pad, y_ptr, y_fp32, y_strides, y_off, Ho, Wo,
-              bias=None, act=L.ACT_NONE, slope=0.2, stats=None, BN=None, tile=None, split=1):
+              bias=None, act=L.ACT_NONE, slope=0.2, stats=None, BN=None, tile=None, split=1, tag=4):
     a = L.ConvArgs()
     a.x = xview
     a.x_lo = x_lo
@@ -113,11 +113,12 @@ def conv_args(xview, x_lo, table: TapTable, Kc, w, w_lo, w_rows, Co_pad, y_ptr, 
         tile = pick_tile(w_phase, 128)
     a.TH, a.TW = tile
     a.BN = BN if BN is not None else (Co_pad if Co_pad <= 256 else 256)
+    a.tag = tag
     return a
 
 
 def wgrad_args(dyview, dy_lo, xview, x_lo, table: TapTable, Kc, Co_pad, dw, w_rows, BN=None, tile=None, ksplit=None,
-               split=1):
+               split=1, tag=6):
     assert table.n_phases == 1
     a = L.WgradArgs()
     a.dy, a.dy_lo, a.x, a.x_lo = dyview, dy_lo, xview, x_lo
@@ -137,6 +138,7 @@ def wgrad_args(dyview, dy_lo, xview, x_lo, table: TapTable, Kc, Co_pad, dw, w_ro
         ctas = len(table.taps) * ((Co_pad + 127) // 128) * (Kc // BN)
         ksplit = max(1, min(blocks, (148 * 2 + ctas - 1) // ctas))
     a.ksplit = ksplit
+    a.tag = tag
     return a
 
 
@@ -204,6 +206,28 @@ def unpack_fold(src: ActBuf, Cc, dst, pad_mode):
 def bias_grad(bstats, N, Cc, Cp, grad, scale=1.0):
     L.check(L.lib().sscg_bias_grad(_ptr(bstats), N, Cc, Cp, _ptr(grad), C.c_float(scale), _stream()),
             "sscg_bias_grad")
+
+
+TAG_NAMES = {1: "res_conv_fwd", 2: "res_conv_dgrad", 3: "res_conv_wgrad", 4: "other_conv_fwd", 5: "other_conv_dgrad",
+             6: "other_conv_wgrad", 7: "in_apply", 8: "in_bwd", 9: "pack_unpack_wprep"}
+
+
+def launch_count():
+    return int(L.lib().sscg_launch_count())
+
+
+def prof_begin():
+    L.check(L.lib().sscg_prof_begin(), "sscg_prof_begin")
+
+
+def prof_end():
+    """-> ({tag name: (sum_ms, launches)}, complete flag)"""
+    ms = (C.c_float * 16)()
+    cnt = (C.c_int32 * 16)()
+    rc = L.lib().sscg_prof_end(ms, cnt)
+    if rc not in (0, 2):
+        L.check(rc, "sscg_prof_end")
+    return {TAG_NAMES.get(t, "tag%d" % t): (float(ms[t]), int(cnt[t])) for t in range(16) if cnt[t]}, rc == 0
 
 
 def device_error():

@@ -118,7 +118,8 @@ class _FusedNet(torch.autograd.Function):
             seed = int(torch.randint(1, 2 ** 31 - 1, (1,)).item())   # CPU generator: follows torch.manual_seed
         plan.forward(c, x, training=dropout_on, drop_seed=seed)
         y = plan.output_nchw(c)
-        need_grad = torch.is_grad_enabled() and any(ctx.needs_input_grad[2:])
+        # (grad mode is always off inside Function.forward; needs_input_grad already reflects no_grad())
+        need_grad = any(ctx.needs_input_grad[2:])
         if need_grad:
             ctx.runner, ctx.plan, ctx.lease = runner, plan, _CtxLease(plan, c)
         else:

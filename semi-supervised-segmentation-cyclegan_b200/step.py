@@ -1,0 +1,231 @@
+"""The semi-supervised CycleGAN training step (reference model.py:370-552) on top of the drop-in
+modules — the caller of the hot path.
+
+`SemiSupCycleGAN.train_step` follows the reference's step line by line (citations inline) with the
+north-star network choice (Gis = resnet_9blocks, Gsi = resnet_9blocks_softmax, Di = Ds = n_layers(3),
+SURVEY.md §3.2) and two variants:
+  * 'head'    — literal HEAD semantics with the frozen auxiliary nets old_Gis / old_Gsi / old_Di;
+  * 'classic' — 2 generators + 2 discriminators and the L1 image-cycle loss (model.py:453).
+Differences from the reference, all outside the arithmetic of the step:
+  * the history pool keeps whole batches ON THE DEVICE (utils.py:278-299 keeps numpy copies and
+    round-trips 113 MB over PCIe per step, model.py:490-495); the swap decisions consume
+    numpy's RNG exactly like the reference;
+  * data parallelism: one process per GPU, gradients of each optimizer live in one flat fp32
+    bucket that is all-reduced (AVG) over NCCL after gen_loss.backward() / discriminator_loss.backward();
+  * `interp` (model.py:268) is the identity for the ResNet generators (same output size) and is elided
+    after checking the shapes.
+"""
+import copy
+import itertools
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .arch import define_Dis, define_Gen, set_grad
+
+
+@dataclass
+class StepWeights:
+    lamda_img: float = 0.5              # main.py:21 (classic variant only; unused at HEAD)
+    lamda_gt: float = 0.1               # main.py:22
+    lab_CE_weight: float = 1.0          # main.py:25
+    lab_MSE_weight: float = 1.0         # main.py:26
+    adversarial_weight: float = 1.0     # main.py:29
+    discriminator_weight: float = 1.0   # main.py:30
+
+
+def make_one_hot(labels, C):
+    # reference utils.py:314-350 — scatter_ of ones along the channel axis
+    one_hot = torch.zeros(labels.size(0), C, labels.size(2), labels.size(3), dtype=torch.float32, device=labels.device)
+    return one_hot.scatter_(1, labels.long(), 1)
+
+
+class DevicePool:
+    """Device-resident Sample_from_Pool (reference utils.py:278-299): stores whole batches; once 50
+    are held, returns a stored batch with probability 0.5 (and replaces it with the new one)."""
+
+    def __init__(self, max_elements=50):
+        self.max_elements = max_elements
+        self.cur_elements = 0
+        self.items = []
+
+    def __call__(self, in_items):
+        return_items = []
+        for in_item in in_items:
+            if self.cur_elements < self.max_elements:
+                self.items.append(in_item)
+                self.cur_elements = self.cur_elements + 1
+                return_items.append(in_item)
+            else:
+                if np.random.ranf() > 0.5:
+                    idx = np.random.randint(0, self.max_elements)
+                    tmp = self.items[idx]
+                    self.items[idx] = in_item
+                    return_items.append(tmp)
+                else:
+                    return_items.append(in_item)
+        return return_items
+
+
+class FlatGrads:
+    """All gradients of one optimizer in a single fp32 bucket (p.grad are views into it)."""
+
+    def __init__(self, params):
+        self.params = [p for p in params]
+        n = sum(p.numel() for p in self.params)
+        dev = self.params[0].device
+        self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
+        off = 0
+        for p in self.params:
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+
+    def zero(self):
+        self.flat.zero_()
+
+    def allreduce_mean(self, group=None):
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+            self.flat.div_(dist.get_world_size(group))
+
+
+class SemiSupCycleGAN:
+    def __init__(self, n_classes=21, img_channels=3, ngf=64, ndf=64, variant="classic", use_dropout=True, lr=2e-4,
+                 device="cuda", precision=None, weights=None, keep_dead_forward=True, fused_adam=True):
+        assert variant in ("classic", "head")
+        self.C, self.variant = n_classes, variant
+        self.w = weights or StepWeights()
+        self.keep_dead_forward = keep_dead_forward
+        gpu_ids = [torch.device(device).index or 0] if torch.device(device).type == "cuda" else []
+        # same construction order as the reference (model.py:215-230)
+        self.Gis = define_Gen(n_classes, img_channels, ngf, "resnet_9blocks", norm="instance", use_dropout=use_dropout,
+                              gpu_ids=gpu_ids)
+        self.Gsi = define_Gen(img_channels, n_classes, ngf, "resnet_9blocks_softmax", norm="instance",
+                              use_dropout=use_dropout, gpu_ids=gpu_ids)
+        self.Di = define_Dis(img_channels, ndf, "n_layers", n_layers_D=3, norm="instance", gpu_ids=gpu_ids)
+        self.Ds = define_Dis(n_classes, ndf, "n_layers", n_layers_D=3, norm="instance", gpu_ids=gpu_ids)
+        self.nets = {"Gis": self.Gis, "Gsi": self.Gsi, "Di": self.Di, "Ds": self.Ds}
+        if variant == "head":
+            self.old_Gis = define_Gen(n_classes, img_channels, ngf, "resnet_9blocks", norm="instance",
+                                      use_dropout=use_dropout, gpu_ids=gpu_ids)
+            self.old_Gsi = define_Gen(img_channels, n_classes, ngf, "resnet_9blocks_softmax", norm="instance",
+                                      use_dropout=use_dropout, gpu_ids=gpu_ids)
+            self.old_Di = define_Dis(img_channels, ndf, "n_layers", n_layers_D=3, norm="instance", gpu_ids=gpu_ids)
+            self.nets.update({"old_Gis": self.old_Gis, "old_Gsi": self.old_Gsi, "old_Di": self.old_Di})
+        for n in self.nets.values():
+            n.precision = precision
+        self.MSE, self.L1, self.CE = nn.MSELoss(), nn.L1Loss(), nn.CrossEntropyLoss()     # model.py:270-272
+        self.softmax = nn.Softmax2d()                                                     # model.py:273
+        g_params = list(itertools.chain(self.Gis.parameters(), self.Gsi.parameters()))
+        d_params = list(itertools.chain(self.Di.parameters(), self.Ds.parameters()))
+        kw = {"fused": True} if (fused_adam and torch.device(device).type == "cuda") else {}
+        self.g_optimizer = torch.optim.Adam(g_params, lr=lr, betas=(0.5, 0.999), **kw)       # model.py:286
+        self.d_optimizer = torch.optim.Adam(d_params, lr=lr, betas=(0.5, 0.999), **kw)       # model.py:287
+        self.g_grads, self.d_grads = FlatGrads(g_params), FlatGrads(d_params)
+        self.pool_recon, self.pool_fake_img, self.pool_fake_gt = DevicePool(), DevicePool(), DevicePool()  # :350-352
+        self.Gsi.train()
+        self.Gis.train()                                                                 # model.py:363-364
+
+    def load_state(self, sds):
+        for k, sd in sds.items():
+            self.nets[k].load_state_dict(sd)
+
+    def _ones(self, t):
+        return torch.ones_like(t)
+
+    def train_step(self, l_img, l_gt, unl_img):
+        """One optimisation step on device tensors: l_img, unl_img N x Cimg x H x W fp32 in [-1, 1],
+        l_gt N x 1 x H x W int64.  Returns the 9 logged scalars (model.py:548-550) as 0-d device tensors."""
+        C, w = self.C, self.w
+        head = self.variant == "head"
+        frozen_d = [self.Di, self.Ds] + ([self.old_Di] if head else [])
+        # ---- generator phase (model.py:379-474) --------------------------------------------
+        set_grad(frozen_d, False)                                                        # :379
+        if head:
+            set_grad([self.old_Gsi, self.old_Gis], False)                                # :380
+        self.g_grads.zero()                                                              # :381
+        fake_img = self.Gis(make_one_hot(l_gt, C).float())                               # :385
+        fake_gt = self.Gsi(unl_img.float())                                              # :386
+        lab_gt = self.Gsi(l_img)                                                         # :387
+        assert fake_img.shape[2:] == l_img.shape[2:] and fake_gt.shape[2:] == l_img.shape[2:]   # interp == identity
+        lab_loss_CE = self.CE(lab_gt, l_gt.squeeze(1))                                   # :398
+        lab_gt = self.softmax(lab_gt)                                                    # :401
+        fake_gt = self.softmax(fake_gt)                                                  # :402
+        recon_img = self.Gis(fake_gt.float())                                            # :408
+        if self.keep_dead_forward:
+            with torch.no_grad():
+                self.Gis(lab_gt.float())      # recon_lab_img (:409) feeds no loss: forward only
+        recon_gt = self.Gsi(fake_img.float())                                            # :410
+        if head:
+            with torch.no_grad():             # frozen aux nets, inputs without grad (:418-423)
+                resnet_fake_gt = self.softmax(self.old_Gsi(unl_img.float()))
+                resnet_lab_gt = self.softmax(self.old_Gsi(l_img))
+                resnet_recon_img = self.old_Gis(resnet_fake_gt.float())
+                self.old_Gis(resnet_lab_gt.float())                                      # resnet_recon_lab_img: unused
+        fake_img_dis = self.Di(fake_img)                                                 # :431
+        fake_gt_disc = make_one_hot(fake_gt.data.max(1)[1].unsqueeze(1), C)              # :435-437
+        fake_gt_dis = self.Ds(fake_gt_disc.float())                                      # :438
+        img_gen_loss = self.MSE(fake_img_dis, self._ones(fake_img_dis))                  # :445
+        gt_gen_loss = self.MSE(fake_gt_dis, self._ones(fake_gt_dis))                     # :446
+        gt_cycle_loss = self.CE(recon_gt, l_gt.squeeze(1))                               # :455
+        lab_loss_MSE = self.L1(fake_img, l_img)                                          # :461
+        fullsupervisedloss = w.lab_CE_weight * lab_loss_CE + w.lab_MSE_weight * lab_loss_MSE      # :464
+        if head:
+            resnet_fake_img_dis = self.old_Di(recon_img)                                 # :432
+            img_cycle_loss = self.MSE(resnet_fake_img_dis, self._ones(resnet_fake_img_dis))       # :452
+            unsupervisedloss = (w.adversarial_weight * (img_gen_loss + gt_gen_loss) + img_cycle_loss
+                                + gt_cycle_loss * w.lamda_gt)                            # :466
+        else:
+            img_cycle_loss = self.L1(recon_img, unl_img)                                 # :453
+            unsupervisedloss = (w.adversarial_weight * (img_gen_loss + gt_gen_loss) + img_cycle_loss * w.lamda_img
+                                + gt_cycle_loss * w.lamda_gt)
+        gen_loss = fullsupervisedloss + unsupervisedloss                                 # :468
+        gen_loss.backward()                                                              # :472
+        self.g_grads.allreduce_mean()
+        self.g_optimizer.step()                                                          # :474
+        # ---- discriminator phase (model.py:481-542) ----------------------------------------
+        set_grad(frozen_d, True)                                                         # :481
+        self.d_grads.zero()                                                              # :482
+        recon_img = self.pool_recon([recon_img.detach()])[0]                             # :490
+        fake_img = self.pool_fake_img([fake_img.detach()])[0]                            # :491
+        fake_gt = self.pool_fake_gt([fake_gt.detach()])[0]                               # :493
+        unl_img_dis = self.Di(unl_img)                                                   # :499
+        fake_img_dis = self.Di(fake_img)                                                 # :500
+        real_gt_dis = self.Ds(make_one_hot(l_gt, C).float())                             # :506-507
+        fake_gt_disc = make_one_hot(fake_gt.data.max(1)[1].unsqueeze(1), C)              # :509-511
+        fake_gt_dis = self.Ds(fake_gt_disc.float())                                      # :512
+        img_dis_loss = (self.MSE(unl_img_dis, torch.ones_like(unl_img_dis))
+                        + self.MSE(fake_img_dis, torch.zeros_like(fake_img_dis))) * 0.5  # :521-522,531
+        gt_dis_loss = (self.MSE(real_gt_dis, torch.ones_like(real_gt_dis))
+                       + self.MSE(fake_gt_dis, torch.zeros_like(fake_gt_dis))) * 0.5     # :523-524,532
+        if head:
+            resnet_recon_img_dis = self.old_Di(resnet_recon_img)                         # :501
+            resnet_fake_img_dis = self.old_Di(recon_img)                                 # :502
+            cycle_img_dis_loss = (self.MSE(resnet_recon_img_dis, torch.ones_like(resnet_recon_img_dis))
+                                  + self.MSE(resnet_fake_img_dis, torch.zeros_like(resnet_fake_img_dis)))  # :527-534
+            discriminator_loss = w.discriminator_weight * (img_dis_loss + gt_dis_loss) + cycle_img_dis_loss  # :538
+        else:
+            cycle_img_dis_loss = torch.zeros((), device=l_img.device)
+            discriminator_loss = w.discriminator_weight * (img_dis_loss + gt_dis_loss)
+        discriminator_loss.backward()                                                    # :539
+        self.d_grads.allreduce_mean()
+        self.d_optimizer.step()                                                          # :542
+        return {"img_dis_loss": img_dis_loss.detach(), "gt_dis_loss": gt_dis_loss.detach(),
+                "cycle_img_dis_loss": cycle_img_dis_loss.detach(), "img_gen_loss": img_gen_loss.detach(),
+                "gt_gen_loss": gt_gen_loss.detach(), "img_cycle_loss": img_cycle_loss.detach(),
+                "gt_cycle_loss": gt_cycle_loss.detach(), "lab_loss_CE": lab_loss_CE.detach(),
+                "lab_loss_MSE": lab_loss_MSE.detach()}
+
+    def train_step_host(self, l_img_host, l_gt_host, unl_img_host):
+        """End-to-end entry: pinned host buffers in, the 9 scalars out on the host."""
+        dev = next(self.Gis.parameters()).device
+        l_img = l_img_host.to(dev, non_blocking=True)
+        l_gt = l_gt_host.to(dev, non_blocking=True)
+        unl_img = unl_img_host.to(dev, non_blocking=True)
+        out = self.train_step(l_img, l_gt, unl_img)
+        stacked = torch.stack([out[k] for k in sorted(out)])
+        host = stacked.cpu()
+        return {k: float(v) for k, v in zip(sorted(out), host)}

@@ -1,0 +1,84 @@
+"""-m gpu: the full training step (sscg_b200.step.SemiSupCycleGAN on cuda:0, fused kernels underneath)
+against (1) the 9 scalars the reference's literal train() loop logged at step 0 (golden, made by
+oracle/make_golden.py from the unmodified reference) and (2) the oracle's gradients.
+Tolerance: 1e-3 relative on the loss scalars in parity mode (bf16x3); gradients rel-L2 <= 1e-2
+(tiny nets; ReLU-kink flips are improbable but possible, see tests/test_modules_gpu.py)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_step as RS
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+KEYS = ("img_dis_loss", "gt_dis_loss", "cycle_img_dis_loss", "img_gen_loss", "gt_gen_loss", "img_cycle_loss",
+        "gt_cycle_loss", "lab_loss_CE", "lab_loss_MSE")
+
+
+def _t(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+def _sd(z, prefix):
+    return {k[len(prefix):]: _t(z[k]) for k in z.files if k.startswith(prefix)}
+
+
+def _build(variant, precision, z):
+    import sscg_b200  # noqa: F401
+    from sscg_b200.step import SemiSupCycleGAN
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    m = SemiSupCycleGAN(n_classes=21, ngf=4, ndf=4, variant=variant, use_dropout=False, device="cuda:0",
+                        precision=precision)
+    names = ["Gis", "Gsi", "Di", "Ds"] + (["old_Gis", "old_Gsi", "old_Di"] if variant == "head" else [])
+    m.load_state({nm: _sd(z, nm + ".") for nm in names})
+    return m, names
+
+
+def test_head_step_matches_reference_train_loop():
+    z = np.load(os.path.join(GOLD, "step_head.npz"))
+    m, names = _build("head", "bf16x3", z)
+    out = m.train_step(_t(z["l_img"]).cuda(), _t(z["l_gt"]).cuda(), _t(z["unl_img"]).cuda())
+    for k in KEYS:
+        ref = float(z["loss." + k])
+        assert abs(float(out[k]) - ref) <= 1e-3 * max(1.0, abs(ref)), (k, float(out[k]), ref)
+
+
+@pytest.mark.parametrize("variant", ["classic", "head"])
+def test_step_gradients_match_oracle(variant):
+    z = np.load(os.path.join(GOLD, "step_head.npz"))
+    m, names = _build(variant, "bf16x3", z)
+    nets = {nm: _sd(z, nm + ".") for nm in names}
+    l_img, l_gt, unl = _t(z["l_img"]), _t(z["l_gt"]), _t(z["unl_img"])
+    losses, grads, _ = RS.full_step(nets, l_img, l_gt, unl, 21, variant=variant)
+    out = m.train_step(l_img.cuda(), l_gt.cuda(), unl.cuda())
+    for k in KEYS:
+        assert abs(float(out[k]) - losses[k]) <= 1e-3 * max(1.0, abs(losses[k])), (k, float(out[k]), losses[k])
+    for nm in ("Gis", "Gsi", "Di", "Ds"):
+        for pname, p in m.nets[nm].named_parameters():
+            g = grads[nm][pname]
+            if pname.endswith(".bias") and float(g.abs().max()) < 1e-5:
+                continue     # cancelled by InstanceNorm: fp32 noise in the oracle, exact zero here
+            rel = float((p.grad.cpu() - g).norm() / max(float(g.norm()), 1e-30))
+            assert rel <= 1e-2, (nm, pname, rel)
+
+
+def test_bf16_step_runs_and_is_finite_with_dropout():
+    import sscg_b200  # noqa: F401
+    from sscg_b200.step import SemiSupCycleGAN
+    torch.manual_seed(0)
+    m = SemiSupCycleGAN(n_classes=21, variant="classic", use_dropout=True, device="cuda:0", precision="bf16")
+    l_img = (torch.rand(2, 3, 64, 64) * 2 - 1).cuda()
+    unl = (torch.rand(2, 3, 64, 64) * 2 - 1).cuda()
+    l_gt = torch.randint(0, 21, (2, 1, 64, 64)).cuda()
+    first = None
+    for _ in range(3):
+        out = m.train_step(l_img, l_gt, unl)
+        assert all(bool(torch.isfinite(v)) for v in out.values())
+        first = first or {k: float(v) for k, v in out.items()}
+    # three Adam steps on a fixed batch must reduce the supervised CE
+    assert float(out["lab_loss_CE"]) < first["lab_loss_CE"]
+    host = m.train_step_host(l_img.cpu().pin_memory(), l_gt.cpu().pin_memory(), unl.cpu().pin_memory())
+    assert set(host) == set(KEYS)
