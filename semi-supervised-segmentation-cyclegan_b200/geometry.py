@@ -43,10 +43,23 @@ def pad_in_channels(c: int) -> int:
     return round_up(c, 8)
 
 
-def pick_tile(w_out: int, pixels: int = 128) -> Tuple[int, int]:
-    """(TH, TW) with TH*TW == pixels, TW a power of two covering the row when it can."""
-    tw = min(pixels, next_pow2(max(w_out, 1)))
-    return pixels // tw, tw
+def pick_tile(w_out: int, pixels: int = 128, h_out: int = 0) -> Tuple[int, int]:
+    """(TH, TW) with TH*TW == pixels and TW a power of two.  Without h_out: the widest TW that the row
+    can use.  With h_out: the shape that covers h_out x w_out with the fewest tiles (ties -> wider TW,
+    longer contiguous rows per TMA box); this matters for extents such as 66 x 66 (dgrad w.r.t. a
+    reflect-padded buffer), where 1 x 128 tiles would leave half of every tile empty."""
+    if h_out <= 0:
+        tw = min(pixels, next_pow2(max(w_out, 1)))
+        return pixels // tw, tw
+    best = None
+    tw = pixels
+    while tw >= 4:
+        th = pixels // tw
+        tiles = ((h_out + th - 1) // th) * ((w_out + tw - 1) // tw)
+        if best is None or tiles < best[0]:
+            best = (tiles, th, tw)
+        tw //= 2
+    return best[1], best[2]
 
 
 def conv_out(n: int, k: int, s: int, p: int) -> int:

@@ -110,7 +110,8 @@ def conv_args(xview, x_lo, table: TapTable, Kc, w, w_lo, w_rows, Co_pad, y_ptr, 
     a.stats = _ptr(stats)
     if tile is None:
         w_phase = (Wo + 1) // 2 if table.n_phases == 4 else Wo
-        tile = pick_tile(w_phase, 128)
+        h_phase = (Ho + 1) // 2 if table.n_phases == 4 else Ho
+        tile = pick_tile(w_phase, 128, h_phase)
     a.TH, a.TW = tile
     a.BN = BN if BN is not None else (Co_pad if Co_pad <= 256 else 256)
     a.tag = tag
@@ -128,7 +129,7 @@ def wgrad_args(dyview, dy_lo, xview, x_lo, table: TapTable, Kc, Co_pad, dw, w_ro
     a.Co_pad, a.split = Co_pad, split
     a.dw, a.w_rows = _ptr(dw), w_rows
     if tile is None:
-        tile = pick_tile(dyview.W, 64)
+        tile = pick_tile(dyview.W, 64, dyview.H)
     a.TH, a.TW = tile
     if BN is None:
         BN = 256 if Kc % 256 == 0 else (128 if Kc % 128 == 0 else 64)

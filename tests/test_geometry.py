@@ -67,6 +67,8 @@ def test_explicit_halo_tables_and_padding_helpers():
     assert [G.pad_in_channels(c) for c in (1, 3, 4, 19, 20, 21, 64)] == [8, 8, 8, 24, 24, 24, 64]
     assert G.pick_tile(64) == (2, 64) and G.pick_tile(31) == (4, 32) and G.pick_tile(256) == (1, 128)
     assert G.pick_tile(30, 64) == (2, 32)
+    assert G.pick_tile(66, 128, 66) in ((16, 8), (8, 16))       # 45 tiles instead of 66
+    assert G.pick_tile(64, 128, 64) == (2, 64) and G.pick_tile(256, 128, 256) == (1, 128)
     # every dgrad phase of the 4x4 stride-2 PatchGAN conv has exactly 4 taps; 3x3 stride-2 has 1/2/2/4
     assert G.taps_conv_dgrad(4, 4, 2, -1).phase_start == [0, 4, 8, 12, 16]
     ps = G.taps_conv_dgrad(3, 3, 2, -1).phase_start
