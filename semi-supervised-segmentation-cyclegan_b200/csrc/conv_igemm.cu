@@ -1,15 +1,19 @@
-// conv_igemm.cu — implicit-GEMM convolution for sm_100a.
+// conv_igemm.cu — implicit-GEMM convolution for sm_100a (persistent, warp-specialised).
 //
-// One CTA computes a 128-pixel x BN-channel output tile.  Roles (192 threads):
+// Each CTA is resident for the whole launch and walks output tiles (128 pixels x BN channels) with a
+// static round-robin schedule.  Roles (192 threads):
 //   warp 0      : TMA producer — per K-block one 4-D box of the NHWC activation view (the box *is*
 //                 the im2col slice: TH x TW pixels x 64 channels of one filter tap, zero-filled
 //                 outside the view, element-strided for stride-2 convolutions) and one 2-D box of
-//                 the weight slab, both landing in 128B-swizzled shared memory.
-//   warp 1      : TMEM allocation + single-thread tcgen05.mma issue (fp32 accumulators in TMEM),
-//                 tcgen05.commit releases pipeline stages and signals the epilogue.
-//   warps 2..5  : epilogue — tcgen05.ld the accumulator, optional bias/activation, InstanceNorm
-//                 partial statistics (warp-shuffle transpose-reduce per channel, one atomicAdd per
-//                 channel per CTA), vectorised NHWC store.
+//                 the weight slab, both landing in 128B-swizzled shared memory.  The smem ring runs
+//                 across tile boundaries, so the loads of tile i+1 are in flight during tile i.
+//   warp 1      : TMEM allocation + single-thread tcgen05.mma issue.  Two fp32 accumulators live in
+//                 TMEM (2 x BN columns); tcgen05.commit releases smem stages and hands a finished
+//                 accumulator to the epilogue while the next tile accumulates into the other one.
+//   warps 2..5  : epilogue — tcgen05.ld the accumulator (then immediately give the TMEM buffer back),
+//                 optional bias/activation, InstanceNorm partial statistics (warp-shuffle
+//                 transpose-reduce per channel, one atomicAdd per channel per tile), vectorised NHWC
+//                 store.
 //
 // Replaces (reference): nn.Conv2d / nn.ConvTranspose2d forward + cuDNN dgrad at
 // arch/ops.py:40-57,63,68; arch/generators.py:74-90; arch/discriminators.py:45-58, with
@@ -29,6 +33,9 @@ struct ConvDev {
     int Co_pad;
     int TH, TW, tw_shift;
     int tiles_h, tiles_w;
+    int tiles_x;    // tiles_h * tiles_w * N
+    int n_ntiles;   // Co_pad / BN
+    int total_tiles;
     void* y;
     int y_fp32;
     long long y_sN, y_sH, y_sW;
@@ -47,12 +54,42 @@ struct IgemmCfg {
     static constexpr int kPlanes = (SPLIT == 3) ? 2 : 1;
     static constexpr int kBBytes = BN * 128;
     static constexpr int kStageBytes = kPlanes * (kABytes + kBBytes);
-    static constexpr int kMaxStages = (200 * 1024) / kStageBytes;
-    static constexpr int kStages = kMaxStages > 6 ? 6 : kMaxStages;
-    static constexpr int kTmemCols = BN < 32 ? 32 : BN;
+    // wide tiles: as deep a ring as fits one CTA per SM; narrow tiles: 4 stages so that 2+ CTAs fit
+    static constexpr int kMaxStages = (BN >= 128 ? 200 * 1024 : 100 * 1024) / kStageBytes;
+    static constexpr int kStages = kMaxStages > 6 ? 6 : (kMaxStages < 2 ? 2 : kMaxStages);
+    static constexpr int kAccCols = BN < 32 ? 32 : BN;          // columns per accumulator
+    static constexpr int kTmemCols = 2 * kAccCols < 32 ? 32 : 2 * kAccCols;
     static constexpr int kStatBytes = 4 * BN * 2 * 4;
     static constexpr int kSmemBytes = 1024 /*align slack*/ + kStages * kStageBytes + kStatBytes + 256;
 };
+
+struct TileInfo {
+    int n, i0, j0, n0, ph, pw, Hph, Wph, tap0, nkb;
+    bool valid;
+};
+
+__device__ __forceinline__ TileInfo decode_tile(const ConvDev& p, int tile, int BN) {
+    TileInfo t;
+    int x = tile % p.tiles_x;
+    int rest = tile / p.tiles_x;
+    const int y = rest % p.n_ntiles;
+    const int z = rest / p.n_ntiles;
+    const int os = (p.n_phases == 4) ? 2 : 1;
+    t.ph = (p.n_phases == 4) ? (z >> 1) : 0;
+    t.pw = (p.n_phases == 4) ? (z & 1) : 0;
+    t.Hph = (p.Ho - t.ph + os - 1) / os;
+    t.Wph = (p.Wo - t.pw + os - 1) / os;
+    const int tj = x % p.tiles_w; x /= p.tiles_w;
+    const int ti = x % p.tiles_h; x /= p.tiles_h;
+    t.n = x;
+    t.i0 = ti * p.TH;
+    t.j0 = tj * p.TW;
+    t.n0 = y * BN;
+    t.tap0 = p.phase_start[z];
+    t.nkb = (p.phase_start[z + 1] - t.tap0) * p.kcb;
+    t.valid = (t.i0 < t.Hph) && (t.j0 < t.Wph);
+    return t;
+}
 
 template <int BN, int SPLIT>
 __global__ void __launch_bounds__(192, 1)
@@ -63,24 +100,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     constexpr int kStages = Cfg::kStages;
     constexpr int kPlanes = Cfg::kPlanes;
 
-    // ---- tile coordinates -------------------------------------------------------------------
-    const int phase = blockIdx.z;
-    const int os = (p.n_phases == 4) ? 2 : 1;
-    const int ph = (p.n_phases == 4) ? (phase >> 1) : 0;
-    const int pw = (p.n_phases == 4) ? (phase & 1) : 0;
-    const int Hph = (p.Ho - ph + os - 1) / os;
-    const int Wph = (p.Wo - pw + os - 1) / os;
-    int t = blockIdx.x;
-    const int tj = t % p.tiles_w; t /= p.tiles_w;
-    const int ti = t % p.tiles_h; t /= p.tiles_h;
-    const int n = t;
-    const int i0 = ti * p.TH, j0 = tj * p.TW;
-    if (i0 >= Hph || j0 >= Wph) return;   // whole CTA exits before touching barriers / TMEM
-    const int n0 = blockIdx.y * BN;
-    const int tap0 = p.phase_start[phase];
-    const int ntaps = p.phase_start[phase + 1] - tap0;
-    const int nkb = ntaps * p.kcb;
-
     // ---- shared memory carve-up ----------------------------------------------------------------
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -88,8 +107,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes + Cfg::kStatBytes);
     uint64_t* full_bar = bars;
     uint64_t* empty_bar = bars + kStages;
-    uint64_t* tmem_full_bar = bars + 2 * kStages;
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 1);
+    uint64_t* tmem_full_bar = bars + 2 * kStages;        // [2]
+    uint64_t* tmem_empty_bar = bars + 2 * kStages + 2;   // [2]
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -102,7 +122,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             mbar_init(smem_u32(&full_bar[s]), 1);
             mbar_init(smem_u32(&empty_bar[s]), 1);
         }
-        mbar_init(smem_u32(tmem_full_bar), 1);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(smem_u32(&tmem_full_bar[s]), 1);
+            mbar_init(smem_u32(&tmem_empty_bar[s]), 128);   // every epilogue thread arrives
+        }
         fence_mbar_init();
     }
     if (warp == 1) {
@@ -118,23 +141,28 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         // ================================ TMA producer ==========================================
         if (lane == 0) {
             int stage = 0; uint32_t par = 0;
-            for (int kb = 0; kb < nkb; ++kb) {
-                const int tp = kb / p.kcb, cb = kb - tp * p.kcb;
-                const SscgTap tap = p.taps[tap0 + tp];
-                mbar_wait(smem_u32(&empty_bar[stage]), par ^ 1, 1);
-                const uint32_t fb = smem_u32(&full_bar[stage]);
-                mbar_arrive_expect_tx(fb, Cfg::kStageBytes);
-                uint8_t* st = smem + stage * Cfg::kStageBytes;
-                const int cw = j0 * p.stride + tap.dw + p.org_w;
-                const int ch = i0 * p.stride + tap.dh + p.org_h;
-                const int brow = tap.brow * p.Co_pad + n0;
-                tma_load_4d(smem_u32(st), &tmA, fb, cb * 64, cw, ch, n);
-                tma_load_2d(smem_u32(st + kPlanes * kABytes), &tmB, fb, cb * 64, brow);
-                if (SPLIT == 3) {
-                    tma_load_4d(smem_u32(st + kABytes), &tmAlo, fb, cb * 64, cw, ch, n);
-                    tma_load_2d(smem_u32(st + kPlanes * kABytes + Cfg::kBBytes), &tmBlo, fb, cb * 64, brow);
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                const TileInfo t = decode_tile(p, tile, BN);
+                if (!t.valid) continue;
+                int tp = 0, cb = 0;
+                for (int kb = 0; kb < t.nkb; ++kb) {
+                    const SscgTap tap = p.taps[t.tap0 + tp];
+                    mbar_wait(smem_u32(&empty_bar[stage]), par ^ 1, 1);
+                    const uint32_t fb = smem_u32(&full_bar[stage]);
+                    mbar_arrive_expect_tx(fb, Cfg::kStageBytes);
+                    uint8_t* st = smem + stage * Cfg::kStageBytes;
+                    const int cw = t.j0 * p.stride + tap.dw + p.org_w;
+                    const int ch = t.i0 * p.stride + tap.dh + p.org_h;
+                    const int brow = tap.brow * p.Co_pad + t.n0;
+                    tma_load_4d(smem_u32(st), &tmA, fb, cb * 64, cw, ch, t.n);
+                    tma_load_2d(smem_u32(st + kPlanes * kABytes), &tmB, fb, cb * 64, brow);
+                    if (SPLIT == 3) {
+                        tma_load_4d(smem_u32(st + kABytes), &tmAlo, fb, cb * 64, cw, ch, t.n);
+                        tma_load_2d(smem_u32(st + kPlanes * kABytes + Cfg::kBBytes), &tmBlo, fb, cb * 64, brow);
+                    }
+                    if (++stage == kStages) { stage = 0; par ^= 1; }
+                    if (++cb == p.kcb) { cb = 0; ++tp; }
                 }
-                if (++stage == kStages) { stage = 0; par ^= 1; }
             }
         }
     } else if (warp == 1) {
@@ -142,140 +170,163 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc_bf16(kTileM, BN < 16 ? 16 : BN, 0, 0);
             int stage = 0; uint32_t par = 0;
-            uint32_t acc = 0;
-            for (int kb = 0; kb < nkb; ++kb) {
-                mbar_wait(smem_u32(&full_bar[stage]), par, 2);
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                const TileInfo t = decode_tile(p, tile, BN);
+                if (!t.valid) continue;
+                const uint32_t acc = it & 1, acc_par = (it >> 1) & 1;
+                ++it;
+                mbar_wait(smem_u32(&tmem_empty_bar[acc]), acc_par ^ 1, 7);   // epilogue drained this buffer
                 tc_fence_after();
-                const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
-                const uint32_t sb = sa + kPlanes * kABytes;
-                const uint64_t da = make_smem_desc_sw128(sa, 0, 1024);
-                const uint64_t db = make_smem_desc_sw128(sb, 0, 1024);
+                const uint32_t d_tmem = tmem_base + acc * Cfg::kAccCols;
+                uint32_t accum = 0;
+                for (int kb = 0; kb < t.nkb; ++kb) {
+                    mbar_wait(smem_u32(&full_bar[stage]), par, 2);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+                    const uint32_t sb = sa + kPlanes * kABytes;
+                    const uint64_t da = make_smem_desc_sw128(sa, 0, 1024);
+                    const uint64_t db = make_smem_desc_sw128(sb, 0, 1024);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {   // 4 x (K = 16) per 64-wide K block; +32 B per step
-                    umma_bf16(tmem_base, da + 2 * k, db + 2 * k, idesc, acc);
-                    acc = 1;
-                    if (SPLIT == 3) {
-                        const uint64_t dalo = make_smem_desc_sw128(sa + kABytes, 0, 1024);
-                        const uint64_t dblo = make_smem_desc_sw128(sb + Cfg::kBBytes, 0, 1024);
-                        umma_bf16(tmem_base, dalo + 2 * k, db + 2 * k, idesc, 1);
-                        umma_bf16(tmem_base, da + 2 * k, dblo + 2 * k, idesc, 1);
+                    for (int k = 0; k < 4; ++k) {   // 4 x (K = 16) per 64-wide K block; +32 B per step
+                        umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, accum);
+                        accum = 1;
+                        if (SPLIT == 3) {
+                            const uint64_t dalo = make_smem_desc_sw128(sa + kABytes, 0, 1024);
+                            const uint64_t dblo = make_smem_desc_sw128(sb + Cfg::kBBytes, 0, 1024);
+                            umma_bf16(d_tmem, dalo + 2 * k, db + 2 * k, idesc, 1);
+                            umma_bf16(d_tmem, da + 2 * k, dblo + 2 * k, idesc, 1);
+                        }
                     }
+                    umma_commit(smem_u32(&empty_bar[stage]));   // stage reusable once these MMAs retire
+                    if (++stage == kStages) { stage = 0; par ^= 1; }
                 }
-                umma_commit(smem_u32(&empty_bar[stage]));   // stage reusable once these MMAs retire
-                if (++stage == kStages) { stage = 0; par ^= 1; }
+                umma_commit(smem_u32(&tmem_full_bar[acc]));     // accumulator complete
             }
-            umma_commit(smem_u32(tmem_full_bar));           // accumulator complete
         }
     } else {
         // ================================ epilogue ==============================================
         const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
         const int m = quad * 32 + lane;            // accumulator row = pixel within the tile
         const int pi = m >> p.tw_shift, pj = m & (p.TW - 1);
-        const int i = i0 + pi, j = j0 + pj;
-        const bool valid = (i < Hph) && (j < Wph);
-        const int ho = i * os + ph, wo = j * os + pw;
-        const long long yoff = (long long)n * p.y_sN + (long long)(ho + p.y_oh) * p.y_sH +
-                               (long long)(wo + p.y_ow) * p.y_sW + n0;
-        mbar_wait(smem_u32(tmem_full_bar), 0, 3);
-        tc_fence_after();
+        const int os = (p.n_phases == 4) ? 2 : 1;
         constexpr int kChunks = (BN + 31) / 32;
+        constexpr int kCols = BN >= 32 ? 32 : BN;
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            const TileInfo t = decode_tile(p, tile, BN);
+            if (!t.valid) continue;
+            const uint32_t acc = it & 1, acc_par = (it >> 1) & 1;
+            ++it;
+            const int i = t.i0 + pi, j = t.j0 + pj;
+            const bool valid = (i < t.Hph) && (j < t.Wph);
+            const int ho = i * os + t.ph, wo = j * os + t.pw;
+            const long long yoff = (long long)t.n * p.y_sN + (long long)(ho + p.y_oh) * p.y_sH +
+                                   (long long)(wo + p.y_ow) * p.y_sW + t.n0;
+            mbar_wait(smem_u32(&tmem_full_bar[acc]), acc_par, 3);
+            tc_fence_after();
+            const uint32_t t_acc = tmem_base + acc * Cfg::kAccCols + (static_cast<uint32_t>(quad * 32) << 16);
 #pragma unroll 1
-        for (int c = 0; c < kChunks; ++c) {
-            uint32_t r[32];
-            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + c * 32;
-            if (BN >= 32) {
-                tmem_ld_32x32(taddr, r);
-            } else {
-                tmem_ld_32x16(taddr, r);
+            for (int c = 0; c < kChunks; ++c) {
+                uint32_t r[32];
+                if (BN >= 32) {
+                    tmem_ld_32x32(t_acc + c * 32, r);
+                } else {
+                    tmem_ld_32x16(t_acc + c * 32, r);
 #pragma unroll
-                for (int q = 16; q < 32; ++q) r[q] = 0;
-            }
-            tmem_ld_wait();
-            float v[32];
-#pragma unroll
-            for (int q = 0; q < 32; ++q) v[q] = __uint_as_float(r[q]);
-            if (p.bias != nullptr) {
-#pragma unroll
-                for (int q = 0; q < 32; ++q) v[q] += __ldg(p.bias + n0 + c * 32 + q);
-            }
-            if (p.act == SSCG_ACT_RELU) {
-#pragma unroll
-                for (int q = 0; q < 32; ++q) v[q] = fmaxf(v[q], 0.f);
-            } else if (p.act == SSCG_ACT_LRELU) {
-#pragma unroll
-                for (int q = 0; q < 32; ++q) v[q] = v[q] > 0.f ? v[q] : v[q] * p.slope;
-            } else if (p.act == SSCG_ACT_TANH) {
-#pragma unroll
-                for (int q = 0; q < 32; ++q) v[q] = tanhf(v[q]);
-            }
-            constexpr int kCols = BN >= 32 ? 32 : BN;
-            if (p.y_fp32) {
-                if (valid) {
-                    float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.y) + yoff + c * 32);
-#pragma unroll
-                    for (int q = 0; q < kCols / 4; ++q)
-                        dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                    for (int q = 16; q < 32; ++q) r[q] = 0;
                 }
-            } else {
-                uint32_t pk[16];
-#pragma unroll
-                for (int q = 0; q < 16; ++q) pk[q] = pack_bf16x2(v[2 * q], v[2 * q + 1]);
-                if (valid) {
-                    uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.y) + yoff + c * 32);
-#pragma unroll
-                    for (int q = 0; q < kCols / 8; ++q)
-                        dst[q] = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+                tmem_ld_wait();
+                if (c == kChunks - 1) {            // accumulator fully read: hand the TMEM buffer back
+                    tc_fence_before();
+                    mbar_arrive(smem_u32(&tmem_empty_bar[acc]));
                 }
-                if (p.stats != nullptr) {   // statistics of the values as stored
+                float v[32];
 #pragma unroll
-                    for (int q = 0; q < 16; ++q) {
-                        v[2 * q] = __uint_as_float(pk[q] << 16);
-                        v[2 * q + 1] = __uint_as_float(pk[q] & 0xffff0000u);
+                for (int q = 0; q < 32; ++q) v[q] = __uint_as_float(r[q]);
+                if (p.bias != nullptr) {
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) v[q] += __ldg(p.bias + t.n0 + c * 32 + q);
+                }
+                if (p.act == SSCG_ACT_RELU) {
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) v[q] = fmaxf(v[q], 0.f);
+                } else if (p.act == SSCG_ACT_LRELU) {
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) v[q] = v[q] > 0.f ? v[q] : v[q] * p.slope;
+                } else if (p.act == SSCG_ACT_TANH) {
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) v[q] = tanhf(v[q]);
+                }
+                if (p.y_fp32) {
+                    if (valid) {
+                        float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.y) + yoff + c * 32);
+#pragma unroll
+                        for (int q = 0; q < kCols / 4; ++q)
+                            dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                    }
+                } else {
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) pk[q] = pack_bf16x2(v[2 * q], v[2 * q + 1]);
+                    if (valid) {
+                        uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.y) + yoff + c * 32);
+#pragma unroll
+                        for (int q = 0; q < kCols / 8; ++q)
+                            dst[q] = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+                    }
+                    if (p.stats != nullptr) {   // statistics of the values as stored
+#pragma unroll
+                        for (int q = 0; q < 16; ++q) {
+                            v[2 * q] = __uint_as_float(pk[q] << 16);
+                            v[2 * q + 1] = __uint_as_float(pk[q] & 0xffff0000u);
+                        }
+                    }
+                }
+                if (p.stats != nullptr) {
+                    float s1[32], s2[32];
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) {
+                        const float x = valid ? v[q] : 0.f;
+                        s1[q] = x;
+                        s2[q] = x * x;
+                    }
+                    // transpose-reduce over the 32 lanes (pixels): lane L ends with column L's sum
+#pragma unroll
+                    for (int off = 16; off >= 1; off >>= 1) {
+                        const bool up = (lane & off) != 0;
+#pragma unroll
+                        for (int q = 0; q < off; ++q) {
+                            const float send1 = up ? s1[q] : s1[q + off];
+                            const float keep1 = up ? s1[q + off] : s1[q];
+                            s1[q] = keep1 + __shfl_xor_sync(0xffffffffu, send1, off);
+                            const float send2 = up ? s2[q] : s2[q + off];
+                            const float keep2 = up ? s2[q + off] : s2[q];
+                            s2[q] = keep2 + __shfl_xor_sync(0xffffffffu, send2, off);
+                        }
+                    }
+                    const int col = c * 32 + lane;
+                    if (col < BN) {
+                        s_stat[(quad * BN + col) * 2 + 0] = s1[0];
+                        s_stat[(quad * BN + col) * 2 + 1] = s2[0];
                     }
                 }
             }
             if (p.stats != nullptr) {
-                float s1[32], s2[32];
+                named_bar_sync(1, 128);               // all four quadrants wrote their partials
+                const int e = threadIdx.x - 64;       // 0..127
+                for (int col = e; col < BN; col += 128) {
+                    float a = 0.f, b = 0.f;
 #pragma unroll
-                for (int q = 0; q < 32; ++q) {
-                    const float x = valid ? v[q] : 0.f;
-                    s1[q] = x;
-                    s2[q] = x * x;
-                }
-                // transpose-reduce over the 32 lanes (pixels): lane L ends with column L's sum
-#pragma unroll
-                for (int off = 16; off >= 1; off >>= 1) {
-                    const bool up = (lane & off) != 0;
-#pragma unroll
-                    for (int q = 0; q < off; ++q) {
-                        const float send1 = up ? s1[q] : s1[q + off];
-                        const float keep1 = up ? s1[q + off] : s1[q];
-                        s1[q] = keep1 + __shfl_xor_sync(0xffffffffu, send1, off);
-                        const float send2 = up ? s2[q] : s2[q + off];
-                        const float keep2 = up ? s2[q + off] : s2[q];
-                        s2[q] = keep2 + __shfl_xor_sync(0xffffffffu, send2, off);
+                    for (int q = 0; q < 4; ++q) {
+                        a += s_stat[(q * BN + col) * 2 + 0];
+                        b += s_stat[(q * BN + col) * 2 + 1];
                     }
+                    float* dst = p.stats + ((long long)t.n * p.Co_pad + t.n0 + col) * 2;
+                    atomicAdd(dst, a);
+                    atomicAdd(dst + 1, b);
                 }
-                const int col = c * 32 + lane;
-                if (col < BN) {
-                    s_stat[(quad * BN + col) * 2 + 0] = s1[0];
-                    s_stat[(quad * BN + col) * 2 + 1] = s2[0];
-                }
-            }
-        }
-        if (p.stats != nullptr) {
-            named_bar_sync(1, 128);
-            const int e = threadIdx.x - 64;   // 0..127
-            for (int col = e; col < BN; col += 128) {
-                float a = 0.f, b = 0.f;
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    a += s_stat[(q * BN + col) * 2 + 0];
-                    b += s_stat[(q * BN + col) * 2 + 1];
-                }
-                float* dst = p.stats + ((long long)n * p.Co_pad + n0 + col) * 2;
-                atomicAdd(dst, a);
-                atomicAdd(dst + 1, b);
+                named_bar_sync(2, 128);               // s_stat may be overwritten by the next tile
             }
         }
         tc_fence_before();
@@ -290,18 +341,36 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
+static int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
+}
+
 template <int BN, int SPLIT>
 static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmAlo, const CUtensorMap& tmB,
-                        const CUtensorMap& tmBlo, const ConvDev& d, dim3 grid, cudaStream_t stream, int tag) {
+                        const CUtensorMap& tmBlo, const ConvDev& d, cudaStream_t stream, int tag) {
     using Cfg = IgemmCfg<BN, SPLIT>;
-    static bool configured = false;
-    if (!configured) {
+    static int occ = 0;
+    if (occ == 0) {
         cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel<BN, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              Cfg::kSmemBytes);
         if (e != cudaSuccess) return set_error("conv_igemm: cudaFuncSetAttribute(smem=%d): %s", Cfg::kSmemBytes,
                                                cudaGetErrorString(e));
-        configured = true;
+        int o = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, conv_igemm_kernel<BN, SPLIT>, 192, Cfg::kSmemBytes);
+        if (e != cudaSuccess || o < 1) o = 1;
+        const int tmem_limit = 512 / Cfg::kTmemCols;     // resident CTAs must all fit their TMEM columns
+        if (o > tmem_limit) o = tmem_limit;
+        if (o > 4) o = 4;
+        occ = o < 1 ? 1 : o;
     }
+    int grid = sm_count() * occ;
+    if (grid > d.total_tiles) grid = d.total_tiles;
     {
         LaunchScope ls(tag, stream);
         conv_igemm_kernel<BN, SPLIT><<<grid, 192, Cfg::kSmemBytes, stream>>>(tmA, tmAlo, tmB, tmBlo, d);
@@ -353,15 +422,18 @@ extern "C" int sscg_conv_igemm(const SscgConvArgs* a, void* stream_) {
     const int Hph = (a->Ho + os - 1) / os, Wph = (a->Wo + os - 1) / os;
     d.tiles_h = (Hph + a->TH - 1) / a->TH;
     d.tiles_w = (Wph + a->TW - 1) / a->TW;
+    d.tiles_x = d.tiles_h * d.tiles_w * d.N;
+    d.n_ntiles = a->Co_pad / a->BN;
+    d.total_tiles = d.tiles_x * d.n_ntiles * a->n_phases;
     d.y = a->y; d.y_fp32 = a->y_fp32;
     d.y_sN = a->y_sN; d.y_sH = a->y_sH; d.y_sW = a->y_sW; d.y_oh = a->y_oh; d.y_ow = a->y_ow;
     d.bias = a->bias; d.act = a->act; d.slope = a->slope; d.stats = a->stats;
+    if (d.total_tiles <= 0) return 0;
 
-    dim3 grid((unsigned)(d.tiles_h * d.tiles_w * d.N), (unsigned)(a->Co_pad / a->BN), (unsigned)a->n_phases);
-#define SSCG_DISPATCH(BN_)                                                                       \
-    case BN_:                                                                                     \
-        return a->split == 3 ? launch_igemm<BN_, 3>(tmA, tmAlo, tmB, tmBlo, d, grid, stream, a->tag)      \
-                             : launch_igemm<BN_, 1>(tmA, tmAlo, tmB, tmBlo, d, grid, stream, a->tag);
+#define SSCG_DISPATCH(BN_)                                                                  \
+    case BN_:                                                                                \
+        return a->split == 3 ? launch_igemm<BN_, 3>(tmA, tmAlo, tmB, tmBlo, d, stream, a->tag) \
+                             : launch_igemm<BN_, 1>(tmA, tmAlo, tmB, tmBlo, d, stream, a->tag);
     switch (a->BN) {
         SSCG_DISPATCH(16)
         SSCG_DISPATCH(32)
