@@ -161,6 +161,7 @@ typedef struct SscgApplyArgs {
     int32_t N, H, W, C;
     int32_t act; float slope;
     uint64_t drop_seed;
+    const uint64_t* drop_ctr;   /* optional device counter mixed into the seed (CUDA-graph replays) */
     SscgView res; const void* res_lo;
     void* dst; void* dst_lo;
     int32_t pad, pad_mode;
@@ -179,6 +180,7 @@ typedef struct SscgBwdArgs {
     int32_t N, H, W, C;
     int32_t act; float slope;
     uint64_t drop_seed;
+    const uint64_t* drop_ctr;
     SscgView dyp; int32_t dyp_fp32;   /* gradient w.r.t. the padded consumer buffer; interior offset = pad */
     int32_t pad, pad_mode;
     SscgView skip; int32_t skip_fp32; /* optional extra gradient on the unpadded output (residual path) */
@@ -220,7 +222,7 @@ int sscg_version(void);
  * prep/apply, 9 = pack/unpack/weight prep).  sscg_prof_end synchronises the device and returns the
  * summed milliseconds and launch counts per tag (arrays of 16). */
 uint64_t sscg_launch_count(void);
-int sscg_prof_begin(void);
+int sscg_prof_begin(uint32_t tag_mask);   /* bit t set: record launches of tag t; 0 = all */
 int sscg_prof_end(float* sum_ms, int32_t* count);
 
 #ifdef __cplusplus

@@ -61,7 +61,7 @@ class ApplyArgs(C.Structure):
         ("stats", C.c_void_p), ("eps", C.c_float),
         ("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("C", C.c_int32),
         ("act", C.c_int32), ("slope", C.c_float),
-        ("drop_seed", C.c_uint64),
+        ("drop_seed", C.c_uint64), ("drop_ctr", C.c_void_p),
         ("res", View), ("res_lo", C.c_void_p),
         ("dst", C.c_void_p), ("dst_lo", C.c_void_p),
         ("pad", C.c_int32), ("pad_mode", C.c_int32),
@@ -74,7 +74,7 @@ class BwdArgs(C.Structure):
         ("stats", C.c_void_p), ("eps", C.c_float),
         ("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("C", C.c_int32),
         ("act", C.c_int32), ("slope", C.c_float),
-        ("drop_seed", C.c_uint64),
+        ("drop_seed", C.c_uint64), ("drop_ctr", C.c_void_p),
         ("dyp", View), ("dyp_fp32", C.c_int32),
         ("pad", C.c_int32), ("pad_mode", C.c_int32),
         ("skip", View), ("skip_fp32", C.c_int32),
@@ -113,7 +113,7 @@ _SIGNATURES = {
     "sscg_fill_zero": [C.c_void_p, C.c_int64, C.c_void_p],
     "sscg_device_error": [],
     "sscg_version": [],
-    "sscg_prof_begin": [],
+    "sscg_prof_begin": [C.c_uint32],
     "sscg_prof_end": [C.POINTER(C.c_float), C.POINTER(C.c_int32)],
 }
 

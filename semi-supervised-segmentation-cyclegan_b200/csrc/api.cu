@@ -73,6 +73,7 @@ constexpr int kProfMax = 8192;
 static struct {
     bool on = false;
     bool created = false;
+    unsigned mask = 0xffffu;
     int n = 0;
     cudaEvent_t ev[2 * kProfMax];
     int tag[kProfMax];
@@ -80,7 +81,7 @@ static struct {
 
 LaunchScope::LaunchScope(int tag, cudaStream_t s) : slot(-1), stream(s) {
     ++g_launches;
-    if (g_prof.on && g_prof.n < kProfMax) {
+    if (g_prof.on && ((g_prof.mask >> (tag & 15)) & 1u) && g_prof.n < kProfMax) {
         slot = g_prof.n++;
         g_prof.tag[slot] = tag & 15;
         cudaEventRecord(g_prof.ev[2 * slot], stream);
@@ -94,8 +95,9 @@ LaunchScope::~LaunchScope() {
 
 extern "C" uint64_t sscg_launch_count(void) { return sscg::g_launches; }
 
-extern "C" int sscg_prof_begin(void) {
+extern "C" int sscg_prof_begin(uint32_t tag_mask) {
     using namespace sscg;
+    g_prof.mask = tag_mask ? tag_mask : 0xffffu;
     if (!g_prof.created) {
         for (int i = 0; i < 2 * kProfMax; ++i)
             if (cudaEventCreate(&g_prof.ev[i]) != cudaSuccess) return set_error("prof_begin: cudaEventCreate failed");

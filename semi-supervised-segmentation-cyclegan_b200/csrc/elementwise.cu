@@ -200,7 +200,8 @@ __global__ void __launch_bounds__(256) in_apply_kernel(const __grid_constant__ A
             for (int q = 0; q < 8; ++q) v[q] = v[q] > 0.f ? v[q] : v[q] * a.slope;
         }
         if (a.drop_seed != 0) {
-            const uint32_t bits = drop_bits(a.drop_seed, (unsigned long long)spix * p.CH + chunk);
+            const uint64_t seed = a.drop_ctr ? (a.drop_seed ^ (*a.drop_ctr * 0x9E3779B97F4A7C15ull)) : a.drop_seed;
+            const uint32_t bits = drop_bits(seed, (unsigned long long)spix * p.CH + chunk);
 #pragma unroll
             for (int q = 0; q < 8; ++q) v[q] = ((bits >> q) & 1u) ? 2.f * v[q] : 0.f;
         }
@@ -284,7 +285,8 @@ __global__ void __launch_bounds__(256) in_bwd_prep_kernel(const __grid_constant_
                 else store8_bf16(a.g_out, nullptr, off, g);
             }
             if (a.drop_seed != 0) {
-                const uint32_t bits = drop_bits(a.drop_seed, (unsigned long long)spix * p.CH + chunk);
+                const uint64_t seed = a.drop_ctr ? (a.drop_seed ^ (*a.drop_ctr * 0x9E3779B97F4A7C15ull)) : a.drop_seed;
+                const uint32_t bits = drop_bits(seed, (unsigned long long)spix * p.CH + chunk);
 #pragma unroll
                 for (int q = 0; q < 8; ++q) g[q] = ((bits >> q) & 1u) ? 2.f * g[q] : 0.f;
             }

@@ -150,6 +150,7 @@ class NetPlan:
         self.Hout, self.Wout = h, w
         self.Cout = specs[-1].Cout
         self.ctx_pool: List[Ctx] = []
+        self.drop_ctr = None      # optional device int64 counter mixed into dropout seeds (CUDA-graph replays)
         self._scratch_ready = False
         self._args_cache = {}
 
@@ -298,6 +299,7 @@ class NetPlan:
             K.run_conv(ca)
             if aa is not None:
                 aa.drop_seed = (c.drop_seed * 1000003 + i + 1) if (s.dropout and c.drop_seed) else 0
+                aa.drop_ctr = self.drop_ctr.data_ptr() if self.drop_ctr is not None else None
                 K.run_apply(aa)
             assert i < nst
         return c
@@ -333,6 +335,7 @@ class NetPlan:
                 self._args_cache[key] = args
             ba, use_apply, wa, da = args
             ba.drop_seed = (c.drop_seed * 1000003 + i + 1) if (s.dropout and c.drop_seed) else 0
+            ba.drop_ctr = self.drop_ctr.data_ptr() if self.drop_ctr is not None else None
             K.run_bwd_prep(ba)
             if use_apply:
                 K.run_bwd_apply(ba, self.draw, self.draw_lo)

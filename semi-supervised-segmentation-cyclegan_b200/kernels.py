@@ -217,8 +217,12 @@ def launch_count():
     return int(L.lib().sscg_launch_count())
 
 
-def prof_begin():
-    L.check(L.lib().sscg_prof_begin(), "sscg_prof_begin")
+def prof_begin(tags=None):
+    """tags: iterable of tag ids to bracket with CUDA events (None = all)."""
+    mask = 0
+    for t in (tags or []):
+        mask |= 1 << t
+    L.check(L.lib().sscg_prof_begin(mask), "sscg_prof_begin")
 
 
 def prof_end():

@@ -39,6 +39,7 @@ class NetRunner:
         self.precision = None
         self._wkey = None
         self.device = None
+        self.drop_ctr = None      # device int64 tensor; when set, dropout masks change with its value
 
     def _setup(self, device, precision):
         if self.specs is not None and self.precision == precision and self.device == device:
@@ -76,6 +77,7 @@ class NetRunner:
             if self._residual_plan is not None:
                 p.res_bwd = self._residual_plan(self.specs)
             self.plans[k] = p
+        p.drop_ctr = self.drop_ctr
         return p
 
     def __call__(self, x, training, use_dropout, precision=None):

@@ -69,6 +69,37 @@ class DevicePool:
         return return_items
 
 
+class GraphPool:
+    """CUDA-graph-safe history pool with the same decisions as Sample_from_Pool (utils.py:278-299).
+    The host draws from numpy's RNG exactly like the reference (`host_decide`, called once per step
+    and pool, in the reference's call order) and hands (use_stored, store, idx) to the device through
+    a small int64 tensor; `device_apply` is made of capturable torch ops on a static [max, ...] store."""
+
+    def __init__(self, max_elements=50):
+        self.max_elements = max_elements
+        self.cur_elements = 0
+        self.storage = None
+        self.dec = None          # device int64 [3] = (use_stored, store, idx)
+
+    def host_decide(self):
+        if self.cur_elements < self.max_elements:
+            idx = self.cur_elements
+            self.cur_elements += 1
+            return (0, 1, idx)
+        if np.random.ranf() > 0.5:
+            return (1, 1, int(np.random.randint(0, self.max_elements)))
+        return (0, 0, 0)
+
+    def device_apply(self, x):
+        if self.storage is None:
+            self.storage = torch.zeros((self.max_elements,) + tuple(x.shape), dtype=x.dtype, device=x.device)
+        idx = self.dec[2:3]
+        old = self.storage.index_select(0, idx)[0]
+        out = torch.where(self.dec[0] != 0, old, x)
+        self.storage.index_copy_(0, idx, torch.where(self.dec[1] != 0, x, old).unsqueeze(0))
+        return out
+
+
 class FlatGrads:
     """All gradients of one optimizer in a single fp32 bucket (p.grad are views into it)."""
 
@@ -94,7 +125,8 @@ class FlatGrads:
 
 class SemiSupCycleGAN:
     def __init__(self, n_classes=21, img_channels=3, ngf=64, ndf=64, variant="classic", use_dropout=True, lr=2e-4,
-                 device="cuda", precision=None, weights=None, keep_dead_forward=True, fused_adam=True):
+                 device="cuda", precision=None, weights=None, keep_dead_forward=True, fused_adam=True,
+                 graph_safe=False):
         assert variant in ("classic", "head")
         self.C, self.variant = n_classes, variant
         self.w = weights or StepWeights()
@@ -122,10 +154,24 @@ class SemiSupCycleGAN:
         g_params = list(itertools.chain(self.Gis.parameters(), self.Gsi.parameters()))
         d_params = list(itertools.chain(self.Di.parameters(), self.Ds.parameters()))
         kw = {"fused": True} if (fused_adam and torch.device(device).type == "cuda") else {}
+        self.graph_safe = graph_safe
+        if graph_safe:
+            kw["capturable"] = True
+            # device-side step counter: mixed into the dropout seeds so that replays draw fresh masks
+            self.step_counter = torch.zeros(1, dtype=torch.int64, device=device)
+            for n in self.nets.values():
+                if getattr(n, "_runner", None) is not None:
+                    n._runner.drop_ctr = self.step_counter
         self.g_optimizer = torch.optim.Adam(g_params, lr=lr, betas=(0.5, 0.999), **kw)       # model.py:286
         self.d_optimizer = torch.optim.Adam(d_params, lr=lr, betas=(0.5, 0.999), **kw)       # model.py:287
         self.g_grads, self.d_grads = FlatGrads(g_params), FlatGrads(d_params)
-        self.pool_recon, self.pool_fake_img, self.pool_fake_gt = DevicePool(), DevicePool(), DevicePool()  # :350-352
+        P = GraphPool if graph_safe else DevicePool
+        self.pool_recon, self.pool_fake_img, self.pool_fake_gt = P(), P(), P()           # model.py:350-352
+        if graph_safe:
+            self.pool_dec = torch.zeros(3, 3, dtype=torch.int64, device=device)
+            self.pool_dec_host = torch.zeros(3, 3, dtype=torch.int64).pin_memory()
+            for i, p in enumerate((self.pool_recon, self.pool_fake_img, self.pool_fake_gt)):
+                p.dec = self.pool_dec[i]
         self.Gsi.train()
         self.Gis.train()                                                                 # model.py:363-364
 
@@ -189,9 +235,15 @@ class SemiSupCycleGAN:
         # ---- discriminator phase (model.py:481-542) ----------------------------------------
         set_grad(frozen_d, True)                                                         # :481
         self.d_grads.zero()                                                              # :482
-        recon_img = self.pool_recon([recon_img.detach()])[0]                             # :490
-        fake_img = self.pool_fake_img([fake_img.detach()])[0]                            # :491
-        fake_gt = self.pool_fake_gt([fake_gt.detach()])[0]                               # :493
+        if self.graph_safe:   # decisions were drawn by feed_pool_decisions() before this step
+            recon_img = self.pool_recon.device_apply(recon_img.detach())                 # :490
+            fake_img = self.pool_fake_img.device_apply(fake_img.detach())                # :491
+            fake_gt = self.pool_fake_gt.device_apply(fake_gt.detach())                   # :493
+            self.step_counter.add_(1)
+        else:
+            recon_img = self.pool_recon([recon_img.detach()])[0]                         # :490
+            fake_img = self.pool_fake_img([fake_img.detach()])[0]                        # :491
+            fake_gt = self.pool_fake_gt([fake_gt.detach()])[0]                           # :493
         unl_img_dis = self.Di(unl_img)                                                   # :499
         fake_img_dis = self.Di(fake_img)                                                 # :500
         real_gt_dis = self.Ds(make_one_hot(l_gt, C).float())                             # :506-507
@@ -219,9 +271,19 @@ class SemiSupCycleGAN:
                 "gt_cycle_loss": gt_cycle_loss.detach(), "lab_loss_CE": lab_loss_CE.detach(),
                 "lab_loss_MSE": lab_loss_MSE.detach()}
 
+    def feed_pool_decisions(self):
+        """graph_safe mode: draw this step's pool decisions on the host (numpy RNG, reference order:
+        recon_img, fake_img, fake_gt — model.py:490-493) and ship them to the device asynchronously."""
+        for i, p in enumerate((self.pool_recon, self.pool_fake_img, self.pool_fake_gt)):
+            d = p.host_decide()
+            self.pool_dec_host[i, 0], self.pool_dec_host[i, 1], self.pool_dec_host[i, 2] = d
+        self.pool_dec.copy_(self.pool_dec_host, non_blocking=True)
+
     def train_step_host(self, l_img_host, l_gt_host, unl_img_host):
         """End-to-end entry: pinned host buffers in, the 9 scalars out on the host."""
         dev = next(self.Gis.parameters()).device
+        if self.graph_safe:
+            self.feed_pool_decisions()
         l_img = l_img_host.to(dev, non_blocking=True)
         l_gt = l_gt_host.to(dev, non_blocking=True)
         unl_img = unl_img_host.to(dev, non_blocking=True)
@@ -229,3 +291,49 @@ class SemiSupCycleGAN:
         stacked = torch.stack([out[k] for k in sorted(out)])
         host = stacked.cpu()
         return {k: float(v) for k, v in zip(sorted(out), host)}
+
+
+class GraphedStep:
+    """The whole training step (both phases, both optimizer updates, NCCL all-reduces) captured once
+    into a CUDA graph and replayed: the ~2000 kernel launches of a step cost one graph launch on the
+    host.  Inputs are copied into static device buffers; the 9 loss scalars come back in a static
+    tensor (`losses`, ordered like sorted(KEYS))."""
+
+    KEYS = ("cycle_img_dis_loss", "gt_cycle_loss", "gt_dis_loss", "gt_gen_loss", "img_cycle_loss", "img_dis_loss",
+            "img_gen_loss", "lab_loss_CE", "lab_loss_MSE")
+
+    def __init__(self, model: SemiSupCycleGAN, l_img, l_gt, unl_img, warmup=3):
+        assert model.graph_safe, "build the model with graph_safe=True"
+        from . import kernels as K
+        self.m = model
+        self.l_img, self.l_gt, self.unl_img = l_img.clone(), l_gt.clone(), unl_img.clone()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):      # real steps: allocate every buffer, reach steady state
+                model.feed_pool_decisions()
+                model.train_step(self.l_img, self.l_gt, self.unl_img)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        model.feed_pool_decisions()
+        l0 = K.launch_count()
+        with torch.cuda.graph(self.graph):
+            out = model.train_step(self.l_img, self.l_gt, self.unl_img)
+            self.losses = torch.stack([out[k] for k in self.KEYS])
+        self.launches_per_step = K.launch_count() - l0
+        torch.cuda.synchronize()
+
+    def __call__(self, l_img, l_gt, unl_img):
+        """Device or pinned-host inputs; returns the static loss tensor (valid after the replay)."""
+        self.l_img.copy_(l_img, non_blocking=True)
+        self.l_gt.copy_(l_gt, non_blocking=True)
+        self.unl_img.copy_(unl_img, non_blocking=True)
+        self.m.feed_pool_decisions()
+        self.graph.replay()
+        return self.losses
+
+    def step_host(self, l_img_host, l_gt_host, unl_img_host):
+        """End-to-end: pinned host buffers in, the 9 scalars on the host out."""
+        host = self(l_img_host, l_gt_host, unl_img_host).cpu()
+        return {k: float(v) for k, v in zip(self.KEYS, host)}
