@@ -147,235 +147,8 @@ __global__ void unpack_kernel(const float* __restrict__ src, int N, int C, int H
     }
 }
 
-// ---------------------------------------------------------------------------------------------
-// InstanceNorm apply (+ act, dropout, residual) with halo write
-// ---------------------------------------------------------------------------------------------
-struct ApplyDev {
-    SscgApplyArgs a;
-    int CH;        // 8-channel vectors per pixel
-    int rows;      // pixels per pass per block
-    int iters;     // passes per block
-};
+#include "norm_kernels.cuh"
 
-__global__ void __launch_bounds__(256) in_apply_kernel(const __grid_constant__ ApplyDev p) {
-    const SscgApplyArgs& a = p.a;
-    const int n = blockIdx.y;
-    const int chunk = threadIdx.x % p.CH;
-    const int row = threadIdx.x / p.CH;
-    if (row >= p.rows) return;
-    const int Hp = a.H + 2 * a.pad, Wp = a.W + 2 * a.pad;
-    const int c0 = chunk * 8;
-    float mean[8], rstd[8];
-    if (a.stats != nullptr) {
-        load_norm(a.stats, a.eps, (long long)n * a.C + c0, 1.f / (float)(a.H * a.W), mean, rstd);
-    }
-    const long long npix = (long long)Hp * Wp;
-    long long pix = (long long)blockIdx.x * p.rows * p.iters + row;
-    for (int it = 0; it < p.iters; ++it, pix += p.rows) {
-        if (pix >= npix) break;
-        const int wp = pix % Wp, hp = pix / Wp;
-        int h = hp - a.pad, w = wp - a.pad;
-        const long long doff = (((long long)n * Hp + hp) * Wp + wp) * a.C + c0;
-        float v[8];
-        if (a.pad_mode == SSCG_PAD_REFLECT) {
-            h = reflect_idx(h, a.H);
-            w = reflect_idx(w, a.W);
-        } else if (h < 0 || h >= a.H || w < 0 || w >= a.W) {
-#pragma unroll
-            for (int q = 0; q < 8; ++q) v[q] = 0.f;
-            store8_bf16(a.dst, a.dst_lo, doff, v);
-            continue;
-        }
-        const long long spix = ((long long)n * a.H + h) * a.W + w;
-        load8(a.raw, a.raw_fp32 != 0, spix * a.C + c0, v);
-        if (a.stats != nullptr) {
-#pragma unroll
-            for (int q = 0; q < 8; ++q) v[q] = (v[q] - mean[q]) * rstd[q];
-        }
-        if (a.act == SSCG_ACT_RELU) {
-#pragma unroll
-            for (int q = 0; q < 8; ++q) v[q] = fmaxf(v[q], 0.f);
-        } else if (a.act == SSCG_ACT_LRELU) {
-#pragma unroll
-            for (int q = 0; q < 8; ++q) v[q] = v[q] > 0.f ? v[q] : v[q] * a.slope;
-        }
-        if (a.drop_seed != 0) {
-            const uint64_t seed = a.drop_ctr ? (a.drop_seed ^ (*a.drop_ctr * 0x9E3779B97F4A7C15ull)) : a.drop_seed;
-            const uint32_t bits = drop_bits(seed, (unsigned long long)spix * p.CH + chunk);
-#pragma unroll
-            for (int q = 0; q < 8; ++q) v[q] = ((bits >> q) & 1u) ? 2.f * v[q] : 0.f;
-        }
-        if (a.res.ptr != nullptr) {
-            float r[8];
-            load8_hilo(a.res.ptr, a.res_lo, (long long)n * a.res.sN + (long long)h * a.res.sH + (long long)w * a.res.sW + c0, r);
-#pragma unroll
-            for (int q = 0; q < 8; ++q) v[q] += r[q];
-        }
-        store8_bf16(a.dst, a.dst_lo, doff, v);
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// backward: dZ and the two per-plane reductions, then dRaw
-// ---------------------------------------------------------------------------------------------
-struct BwdDev {
-    SscgBwdArgs a;
-    void* draw; void* draw_lo;
-    int CH, rows, iters;
-};
-
-// positions of the padded gradient buffer that fold onto source index s (reflect) — at most 3
-__device__ __forceinline__ int fold_positions(int s, int n, int pad, int mode, int (&q)[3]) {
-    int cnt = 0;
-    q[cnt++] = s + pad;
-    if (mode == SSCG_PAD_REFLECT) {
-        if (s >= 1 && s <= pad) q[cnt++] = pad - s;
-        if (s <= n - 2 && s >= n - 1 - pad) q[cnt++] = pad + 2 * (n - 1) - s;
-    }
-    return cnt;
-}
-
-__global__ void __launch_bounds__(256) in_bwd_prep_kernel(const __grid_constant__ BwdDev p) {
-    const SscgBwdArgs& a = p.a;
-    __shared__ float s_red[256 * 2 + 16];
-    const int n = blockIdx.y;
-    const int chunk = threadIdx.x % p.CH;
-    const int row = threadIdx.x / p.CH;
-    const bool active = row < p.rows;
-    const int c0 = chunk * 8;
-    float mean[8], rstd[8];
-    const bool norm = a.stats != nullptr;
-    if (norm && active) load_norm(a.stats, a.eps, (long long)n * a.C + c0, 1.f / (float)(a.H * a.W), mean, rstd);
-    float acc1[8], acc2[8];
-#pragma unroll
-    for (int q = 0; q < 8; ++q) acc1[q] = acc2[q] = 0.f;
-    const long long npix = (long long)a.H * a.W;
-    long long pix = (long long)blockIdx.x * p.rows * p.iters + row;
-    if (active) {
-        for (int it = 0; it < p.iters; ++it, pix += p.rows) {
-            if (pix >= npix) break;
-            const int w = pix % a.W, h = pix / a.W;
-            const long long spix = (long long)n * npix + pix;
-            float g[8];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) g[q] = 0.f;
-            if (a.dyp.ptr != nullptr) {
-                int hq[3], wq[3];
-                const int nh = fold_positions(h, a.H, a.pad, a.pad_mode, hq);
-                const int nw = fold_positions(w, a.W, a.pad, a.pad_mode, wq);
-                for (int x = 0; x < nh; ++x)
-                    for (int y = 0; y < nw; ++y) {
-                        float t[8];
-                        load8(a.dyp.ptr, a.dyp_fp32 != 0,
-                              (long long)n * a.dyp.sN + (long long)hq[x] * a.dyp.sH + (long long)wq[y] * a.dyp.sW + c0, t);
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) g[q] += t[q];
-                    }
-            }
-            if (a.skip.ptr != nullptr) {
-                float t[8];
-                load8(a.skip.ptr, a.skip_fp32 != 0,
-                      (long long)n * a.skip.sN + (long long)h * a.skip.sH + (long long)w * a.skip.sW + c0, t);
-#pragma unroll
-                for (int q = 0; q < 8; ++q) g[q] += t[q];
-            }
-            const long long off = spix * a.C + c0;
-            if (a.g_out != nullptr) {
-                if (a.g_fp32) store8_f32(a.g_out, off, g);
-                else store8_bf16(a.g_out, nullptr, off, g);
-            }
-            if (a.drop_seed != 0) {
-                const uint64_t seed = a.drop_ctr ? (a.drop_seed ^ (*a.drop_ctr * 0x9E3779B97F4A7C15ull)) : a.drop_seed;
-                const uint32_t bits = drop_bits(seed, (unsigned long long)spix * p.CH + chunk);
-#pragma unroll
-                for (int q = 0; q < 8; ++q) g[q] = ((bits >> q) & 1u) ? 2.f * g[q] : 0.f;
-            }
-            float z[8];
-            if (norm || a.act != SSCG_ACT_NONE) {
-                load8(a.raw, a.raw_fp32 != 0, off, z);
-                if (norm) {
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) z[q] = (z[q] - mean[q]) * rstd[q];
-                }
-                if (a.act == SSCG_ACT_RELU) {
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) g[q] = z[q] > 0.f ? g[q] : 0.f;
-                } else if (a.act == SSCG_ACT_LRELU) {
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) g[q] = z[q] > 0.f ? g[q] : g[q] * a.slope;
-                } else if (a.act == SSCG_ACT_TANH) {   // raw holds y = tanh(.)
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) g[q] = g[q] * (1.f - z[q] * z[q]);
-                }
-            } else {
-#pragma unroll
-                for (int q = 0; q < 8; ++q) z[q] = 0.f;
-            }
-            if (a.dz_fp32) store8_f32(a.dz, off, g);
-            else store8_bf16(a.dz, a.dz_lo, off, g);
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                acc1[q] += g[q];
-                acc2[q] += g[q] * z[q];
-            }
-        }
-    }
-    if (a.bstats == nullptr) return;
-    // block reduction over the pixel rows that share a channel vector, then one atomic per channel
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-        __syncthreads();
-        s_red[threadIdx.x * 2] = active ? acc1[q] : 0.f;
-        s_red[threadIdx.x * 2 + 1] = active ? acc2[q] : 0.f;
-        __syncthreads();
-        if (threadIdx.x < p.CH) {
-            float s1 = 0.f, s2 = 0.f;
-            for (int r = 0; r < p.rows; ++r) {
-                s1 += s_red[(r * p.CH + threadIdx.x) * 2];
-                s2 += s_red[(r * p.CH + threadIdx.x) * 2 + 1];
-            }
-            float* dst = a.bstats + ((long long)n * a.C + threadIdx.x * 8 + q) * 2;
-            atomicAdd(dst, s1);
-            atomicAdd(dst + 1, s2);
-        }
-    }
-}
-
-__global__ void __launch_bounds__(256) in_bwd_apply_kernel(const __grid_constant__ BwdDev p) {
-    const SscgBwdArgs& a = p.a;
-    const int n = blockIdx.y;
-    const int chunk = threadIdx.x % p.CH;
-    const int row = threadIdx.x / p.CH;
-    if (row >= p.rows) return;
-    const int c0 = chunk * 8;
-    const float inv_cnt = 1.f / (float)(a.H * a.W);
-    float mean[8], rstd[8], m1[8], m2[8];
-    load_norm(a.stats, a.eps, (long long)n * a.C + c0, inv_cnt, mean, rstd);
-    {
-        const float4* bp = reinterpret_cast<const float4*>(a.bstats + ((long long)n * a.C + c0) * 2);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const float4 s = bp[q];
-            m1[2 * q] = s.x * inv_cnt; m2[2 * q] = s.y * inv_cnt;
-            m1[2 * q + 1] = s.z * inv_cnt; m2[2 * q + 1] = s.w * inv_cnt;
-        }
-    }
-    const long long npix = (long long)a.H * a.W;
-    long long pix = (long long)blockIdx.x * p.rows * p.iters + row;
-    for (int it = 0; it < p.iters; ++it, pix += p.rows) {
-        if (pix >= npix) break;
-        const long long off = ((long long)n * npix + pix) * a.C + c0;
-        float z[8], g[8];
-        load8(a.raw, a.raw_fp32 != 0, off, z);
-        load8(a.dz, a.dz_fp32 != 0, off, g);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const float zz = (z[q] - mean[q]) * rstd[q];
-            g[q] = rstd[q] * (g[q] - m1[q] - zz * m2[q]);
-        }
-        store8_bf16(p.draw, p.draw_lo, off, g);
-    }
-}
 
 __global__ void unpack_fold_kernel(const void* __restrict__ src, int src_fp32, int N, int C, int H, int W, int Cp,
                                    int pad, int pad_mode, float* __restrict__ dst) {

@@ -316,7 +316,8 @@ class GraphedStep:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
-        model.feed_pool_decisions()
+        # capture records the kernels without running them: no pool decision is consumed here (the
+        # captured kernels read whatever decision is in model.pool_dec at replay time)
         l0 = K.launch_count()
         with torch.cuda.graph(self.graph):
             out = model.train_step(self.l_img, self.l_gt, self.unl_img)
