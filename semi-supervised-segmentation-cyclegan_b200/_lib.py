@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsscg_b200.so")
+LIB_PATH = os.environ.get("SSCG_LIB", os.path.join(_HERE, "libsscg_b200.so"))   # SSCG_LIB: tuning builds only
 
 SSCG_MAX_TAPS = 64
 ACT_NONE, ACT_RELU, ACT_LRELU, ACT_TANH = 0, 1, 2, 3

@@ -333,7 +333,10 @@ extern "C" int sscg_in_apply(const SscgApplyArgs* a, void* stream) {
     vec_layout(a->C, (long long)(a->H + 2 * a->pad) * (a->W + 2 * a->pad), d.CH, d.rows, d.iters, gridx);
     {
         LaunchScope ls_(7, static_cast<cudaStream_t>(stream));
-        in_apply_kernel<<<dim3(gridx, a->N), 256, 0, static_cast<cudaStream_t>(stream)>>>(d);
+        if (a->raw_fp32 || a->res_lo || a->dst_lo)
+            in_apply_kernel<true><<<dim3(gridx, a->N), 256, 0, static_cast<cudaStream_t>(stream)>>>(d);
+        else
+            in_apply_kernel<false><<<dim3(gridx, a->N), 256, 0, static_cast<cudaStream_t>(stream)>>>(d);
     }
     SSCG_CHECK_LAUNCH("in_apply");
     return 0;
@@ -347,7 +350,10 @@ extern "C" int sscg_in_bwd_prep(const SscgBwdArgs* a, void* stream) {
     vec_layout(a->C, (long long)a->H * a->W, d.CH, d.rows, d.iters, gridx);
     {
         LaunchScope ls_(8, static_cast<cudaStream_t>(stream));
-        in_bwd_prep_kernel<<<dim3(gridx, a->N), 256, 0, static_cast<cudaStream_t>(stream)>>>(d);
+        if (a->raw_fp32 || a->dyp_fp32 || a->skip_fp32 || a->g_fp32 || a->dz_fp32 || a->dz_lo)
+            in_bwd_prep_kernel<true><<<dim3(gridx, a->N), 256, 0, static_cast<cudaStream_t>(stream)>>>(d);
+        else
+            in_bwd_prep_kernel<false><<<dim3(gridx, a->N), 256, 0, static_cast<cudaStream_t>(stream)>>>(d);
     }
     SSCG_CHECK_LAUNCH("in_bwd_prep");
     return 0;
@@ -362,7 +368,10 @@ extern "C" int sscg_in_bwd_apply(const SscgBwdArgs* a, void* draw, void* draw_lo
     vec_layout(a->C, (long long)a->H * a->W, d.CH, d.rows, d.iters, gridx);
     {
         LaunchScope ls_(8, static_cast<cudaStream_t>(stream));
-        in_bwd_apply_kernel<<<dim3(gridx, a->N), 256, 0, static_cast<cudaStream_t>(stream)>>>(d);
+        if (a->raw_fp32 || a->dz_fp32 || draw_lo)
+            in_bwd_apply_kernel<true><<<dim3(gridx, a->N), 256, 0, static_cast<cudaStream_t>(stream)>>>(d);
+        else
+            in_bwd_apply_kernel<false><<<dim3(gridx, a->N), 256, 0, static_cast<cudaStream_t>(stream)>>>(d);
     }
     SSCG_CHECK_LAUNCH("in_bwd_apply");
     return 0;

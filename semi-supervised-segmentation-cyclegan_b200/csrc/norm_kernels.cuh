@@ -1,12 +1,56 @@
-// norm_kernels.cuh — InstanceNorm apply / backward kernels (included by elementwise.cu).
+// norm_kernels.cuh — InstanceNorm apply / backward kernels (included by elementwise.cu inside
+// namespace sscg, after its load/store helpers).
 //
 // All three are streaming kernels over NHWC planes: a thread owns one 8-channel vector (16 B of
 // bf16) and walks pixels.  They are HBM/L2-bandwidth kernels, so each thread keeps a batch of
-// independent 16-byte loads in flight (kBatch pixels) before it touches any of them — with one
-// load in flight per thread the SMs cannot cover the ~1 us memory latency and the kernels stall
-// at ~2.5 TB/s (measured, profiles/r01_*).
+// independent 16-byte loads in flight before it touches any of them — with one load in flight per
+// thread the SMs cannot cover the ~1 us memory latency (2.5 TB/s measured).  The loads are kept as
+// packed 128-bit registers until they are consumed, so that the batch does not cost occupancy.
+// Template parameter ANYF32: false = every tensor is bf16 (fast mode, 4 registers per vector in
+// flight); true = per-tensor runtime dtype flags (bf16x3 parity mode and mixed cases).
 #pragma once
-// (included inside namespace sscg, after the load/store helpers of elementwise.cu)
+
+template <bool ANYF32>
+struct RawVec;
+template <>
+struct RawVec<false> {
+    uint4 a;
+};
+template <>
+struct RawVec<true> {
+    uint4 a, b;
+};
+
+template <bool ANYF32>
+__device__ __forceinline__ void raw_load(RawVec<ANYF32>& r, const void* base, bool fp32, long long off) {
+    if constexpr (ANYF32) {
+        if (fp32) {
+            const uint4* p = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(base) + off);
+            r.a = p[0];
+            r.b = p[1];
+            return;
+        }
+    }
+    r.a = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(base) + off);
+}
+template <bool ANYF32>
+__device__ __forceinline__ void raw_cvt(const RawVec<ANYF32>& r, bool fp32, float (&v)[8]) {
+    if constexpr (ANYF32) {
+        if (fp32) {
+            v[0] = __uint_as_float(r.a.x); v[1] = __uint_as_float(r.a.y);
+            v[2] = __uint_as_float(r.a.z); v[3] = __uint_as_float(r.a.w);
+            v[4] = __uint_as_float(r.b.x); v[5] = __uint_as_float(r.b.y);
+            v[6] = __uint_as_float(r.b.z); v[7] = __uint_as_float(r.b.w);
+            return;
+        }
+    }
+    const uint32_t w[4] = {r.a.x, r.a.y, r.a.z, r.a.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        v[2 * q] = __uint_as_float(w[q] << 16);
+        v[2 * q + 1] = __uint_as_float(w[q] & 0xffff0000u);
+    }
+}
 
 // ---------------------------------------------------------------------------------------------
 // forward: y = dropout(act(instance_norm(raw))) (+ residual), written with halo
@@ -15,12 +59,19 @@ struct ApplyDev {
     SscgApplyArgs a;
     int CH;        // 8-channel vectors per pixel
     int rows;      // pixels per pass per block
-    int iters;     // passes per block (multiple of kApplyBatch)
+    int iters;     // passes per block (multiple of the batch)
 };
 
-constexpr int kApplyBatch = 4;
+#ifndef SSCG_APPLY_BATCH
+#define SSCG_APPLY_BATCH 4
+#endif
+#ifndef SSCG_APPLY_MINB
+#define SSCG_APPLY_MINB 3
+#endif
+constexpr int kApplyBatch = SSCG_APPLY_BATCH;
 
-__global__ void __launch_bounds__(256) in_apply_kernel(const __grid_constant__ ApplyDev p) {
+template <bool ANYF32>
+__global__ void __launch_bounds__(256, SSCG_APPLY_MINB) in_apply_kernel(const __grid_constant__ ApplyDev p) {
     const SscgApplyArgs& a = p.a;
     const int n = blockIdx.y;
     const int chunk = threadIdx.x % p.CH;
@@ -32,68 +83,88 @@ __global__ void __launch_bounds__(256) in_apply_kernel(const __grid_constant__ A
     const bool norm = a.stats != nullptr;
     if (norm) load_norm(a.stats, a.eps, (long long)n * a.C + c0, 1.f / (float)(a.H * a.W), mean, rstd);
     const bool has_res = a.res.ptr != nullptr;
+    const bool res_lo = ANYF32 && a.res_lo != nullptr;
+    const bool raw_f32 = ANYF32 && a.raw_fp32 != 0;
+    void* dst_lo = ANYF32 ? a.dst_lo : nullptr;
     const uint64_t seed = (a.drop_seed != 0 && a.drop_ctr) ? (a.drop_seed ^ (*a.drop_ctr * 0x9E3779B97F4A7C15ull))
                                                            : a.drop_seed;
-    const long long npix = (long long)Hp * Wp;
-    const long long pix0 = (long long)blockIdx.x * p.rows * p.iters + row;
+    const int npix = Hp * Wp;
+    const int pix0 = blockIdx.x * p.rows * p.iters + row;   // per-sample pixel index: 32-bit div/mod below
     for (int it0 = 0; it0 < p.iters; it0 += kApplyBatch) {
-        float v[kApplyBatch][8], r[kApplyBatch][8];
-        long long spix[kApplyBatch], doff[kApplyBatch];
+        RawVec<ANYF32> rv[kApplyBatch];
+        RawVec<false> rr[kApplyBatch], rl[kApplyBatch];
+        long long spix[kApplyBatch];
         int state[kApplyBatch];   // 0: skip, 1: zero halo, 2: data
         // ---- issue all loads of the batch ----------------------------------------------------
 #pragma unroll
         for (int b = 0; b < kApplyBatch; ++b) {
-            const long long pix = pix0 + (long long)(it0 + b) * p.rows;
+            const int pix = pix0 + (it0 + b) * p.rows;
             state[b] = 0;
-            if (pix >= npix) continue;
-            const int wp = pix % Wp, hp = pix / Wp;
-            int h = hp - a.pad, w = wp - a.pad;
-            doff[b] = (((long long)n * Hp + hp) * Wp + wp) * a.C + c0;
-            if (a.pad_mode == SSCG_PAD_REFLECT) {
-                h = reflect_idx(h, a.H);
-                w = reflect_idx(w, a.W);
-            } else if (h < 0 || h >= a.H || w < 0 || w >= a.W) {
-                state[b] = 1;
-                continue;
+            spix[b] = 0;
+            if (pix < npix) {
+                const int wp = pix % Wp, hp = pix / Wp;
+                int h = hp - a.pad, w = wp - a.pad;
+                bool inside = true;
+                if (a.pad_mode == SSCG_PAD_REFLECT) {
+                    h = reflect_idx(h, a.H);
+                    w = reflect_idx(w, a.W);
+                } else {
+                    inside = !(h < 0 || h >= a.H || w < 0 || w >= a.W);
+                }
+                state[b] = inside ? 2 : 1;
+                if (inside) {
+                    spix[b] = ((long long)n * a.H + h) * a.W + w;
+                    raw_load<ANYF32>(rv[b], a.raw, raw_f32, spix[b] * a.C + c0);
+                    if (has_res) {
+                        const long long ro = (long long)n * a.res.sN + (long long)h * a.res.sH + (long long)w * a.res.sW + c0;
+                        raw_load<false>(rr[b], a.res.ptr, false, ro);
+                        if (res_lo) raw_load<false>(rl[b], a.res_lo, false, ro);
+                    }
+                }
             }
-            state[b] = 2;
-            spix[b] = ((long long)n * a.H + h) * a.W + w;
-            load8(a.raw, a.raw_fp32 != 0, spix[b] * a.C + c0, v[b]);
-            if (has_res)
-                load8_hilo(a.res.ptr, a.res_lo,
-                           (long long)n * a.res.sN + (long long)h * a.res.sH + (long long)w * a.res.sW + c0, r[b]);
         }
         // ---- compute + store -------------------------------------------------------------------
 #pragma unroll
         for (int b = 0; b < kApplyBatch; ++b) {
             if (state[b] == 0) continue;
+            const int pix = pix0 + (it0 + b) * p.rows;
+            const long long doff = ((long long)n * npix + pix) * a.C + c0;
+            float v[8];
             if (state[b] == 1) {
 #pragma unroll
-                for (int q = 0; q < 8; ++q) v[b][q] = 0.f;
-                store8_bf16(a.dst, a.dst_lo, doff[b], v[b]);
+                for (int q = 0; q < 8; ++q) v[q] = 0.f;
+                store8_bf16(a.dst, dst_lo, doff, v);
                 continue;
             }
+            raw_cvt<ANYF32>(rv[b], raw_f32, v);
             if (norm) {
 #pragma unroll
-                for (int q = 0; q < 8; ++q) v[b][q] = (v[b][q] - mean[q]) * rstd[q];
+                for (int q = 0; q < 8; ++q) v[q] = (v[q] - mean[q]) * rstd[q];
             }
             if (a.act == SSCG_ACT_RELU) {
 #pragma unroll
-                for (int q = 0; q < 8; ++q) v[b][q] = fmaxf(v[b][q], 0.f);
+                for (int q = 0; q < 8; ++q) v[q] = fmaxf(v[q], 0.f);
             } else if (a.act == SSCG_ACT_LRELU) {
 #pragma unroll
-                for (int q = 0; q < 8; ++q) v[b][q] = v[b][q] > 0.f ? v[b][q] : v[b][q] * a.slope;
+                for (int q = 0; q < 8; ++q) v[q] = v[q] > 0.f ? v[q] : v[q] * a.slope;
             }
             if (seed != 0) {
                 const uint32_t bits = drop_bits(seed, (unsigned long long)spix[b] * p.CH + chunk);
 #pragma unroll
-                for (int q = 0; q < 8; ++q) v[b][q] = ((bits >> q) & 1u) ? 2.f * v[b][q] : 0.f;
+                for (int q = 0; q < 8; ++q) v[q] = ((bits >> q) & 1u) ? 2.f * v[q] : 0.f;
             }
             if (has_res) {
+                float r[8];
+                raw_cvt<false>(rr[b], false, r);
 #pragma unroll
-                for (int q = 0; q < 8; ++q) v[b][q] += r[b][q];
+                for (int q = 0; q < 8; ++q) v[q] += r[q];
+                if (res_lo) {
+                    raw_cvt<false>(rl[b], false, r);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) v[q] += r[q];
+                }
             }
-            store8_bf16(a.dst, a.dst_lo, doff[b], v[b]);
+            store8_bf16(a.dst, dst_lo, doff, v);
         }
     }
 }
@@ -118,9 +189,16 @@ __device__ __forceinline__ int fold_positions(int s, int n, int pad, int mode, i
     return cnt;
 }
 
-constexpr int kPrepBatch = 2;
+#ifndef SSCG_PREP_BATCH
+#define SSCG_PREP_BATCH 4
+#endif
+#ifndef SSCG_PREP_MINB
+#define SSCG_PREP_MINB 2
+#endif
+constexpr int kPrepBatch = SSCG_PREP_BATCH;
 
-__global__ void __launch_bounds__(256, 2) in_bwd_prep_kernel(const __grid_constant__ BwdDev p) {
+template <bool ANYF32>
+__global__ void __launch_bounds__(256, SSCG_PREP_MINB) in_bwd_prep_kernel(const __grid_constant__ BwdDev p) {
     const SscgBwdArgs& a = p.a;
     __shared__ float s_red[256 * 16];
     const int n = blockIdx.y;
@@ -132,34 +210,48 @@ __global__ void __launch_bounds__(256, 2) in_bwd_prep_kernel(const __grid_consta
     const bool norm = a.stats != nullptr;
     const bool need_raw = norm || a.act != SSCG_ACT_NONE;
     const bool fold = (a.pad_mode == SSCG_PAD_REFLECT) && a.pad > 0;
+    const bool has_dyp = a.dyp.ptr != nullptr, has_skip = a.skip.ptr != nullptr;
+    const bool dyp_f32 = ANYF32 && a.dyp_fp32 != 0, skip_f32 = ANYF32 && a.skip_fp32 != 0;
+    const bool raw_f32 = ANYF32 && a.raw_fp32 != 0;
     if (norm && active) load_norm(a.stats, a.eps, (long long)n * a.C + c0, 1.f / (float)(a.H * a.W), mean, rstd);
     const uint64_t seed = (a.drop_seed != 0 && a.drop_ctr) ? (a.drop_seed ^ (*a.drop_ctr * 0x9E3779B97F4A7C15ull))
                                                            : a.drop_seed;
     float acc1[8], acc2[8];
 #pragma unroll
     for (int q = 0; q < 8; ++q) acc1[q] = acc2[q] = 0.f;
-    const long long npix = (long long)a.H * a.W;
-    const long long pix0 = (long long)blockIdx.x * p.rows * p.iters + row;
+    const int npix = a.H * a.W;
+    const int pix0 = blockIdx.x * p.rows * p.iters + row;   // per-sample pixel index: 32-bit div/mod below
     if (active) {
         for (int it0 = 0; it0 < p.iters; it0 += kPrepBatch) {
-            float g[kPrepBatch][8], z[kPrepBatch][8], sk[kPrepBatch][8];
-            long long off[kPrepBatch], spix[kPrepBatch];
-            bool live[kPrepBatch];
-            // ---- loads -------------------------------------------------------------------------
+            RawVec<ANYF32> rg[kPrepBatch], rs[kPrepBatch], rz[kPrepBatch];
+            // ---- loads (interior gradient position, skip gradient, raw activation) -------------
 #pragma unroll
             for (int b = 0; b < kPrepBatch; ++b) {
-                const long long pix = pix0 + (long long)(it0 + b) * p.rows;
-                live[b] = pix < npix;
-                if (!live[b]) continue;
-                const int w = pix % a.W, h = pix / a.W;
-                spix[b] = (long long)n * npix + pix;
-                off[b] = spix[b] * a.C + c0;
-                if (a.dyp.ptr != nullptr) {
-                    // interior position first (always present), halo positions only near the border
-                    load8(a.dyp.ptr, a.dyp_fp32 != 0,
-                          (long long)n * a.dyp.sN + (long long)(h + a.pad) * a.dyp.sH + (long long)(w + a.pad) * a.dyp.sW + c0,
-                          g[b]);
-                    if (fold) {
+                const int pix = pix0 + (it0 + b) * p.rows;
+                if (pix < npix) {
+                    const int w = pix % a.W, h = pix / a.W;
+                    if (has_dyp)
+                        raw_load<ANYF32>(rg[b], a.dyp.ptr, dyp_f32,
+                                         (long long)n * a.dyp.sN + (long long)(h + a.pad) * a.dyp.sH +
+                                             (long long)(w + a.pad) * a.dyp.sW + c0);
+                    if (has_skip)
+                        raw_load<ANYF32>(rs[b], a.skip.ptr, skip_f32,
+                                         (long long)n * a.skip.sN + (long long)h * a.skip.sH + (long long)w * a.skip.sW + c0);
+                    if (need_raw) raw_load<ANYF32>(rz[b], a.raw, raw_f32, ((long long)n * npix + pix) * a.C + c0);
+                }
+            }
+            // ---- compute + store ---------------------------------------------------------------
+#pragma unroll
+            for (int b = 0; b < kPrepBatch; ++b) {
+                const int pix = pix0 + (it0 + b) * p.rows;
+                if (pix >= npix) continue;
+                const long long spix = (long long)n * npix + pix;
+                const long long off = spix * a.C + c0;
+                float g[8], z[8];
+                if (has_dyp) {
+                    raw_cvt<ANYF32>(rg[b], dyp_f32, g);
+                    if (fold) {   // halo positions that mirror onto this pixel (border pixels only)
+                        const int w = pix % a.W, h = pix / a.W;
                         int hq[3], wq[3];
                         const int nh = fold_positions(h, a.H, a.pad, a.pad_mode, hq);
                         const int nw = fold_positions(w, a.W, a.pad, a.pad_mode, wq);
@@ -168,64 +260,58 @@ __global__ void __launch_bounds__(256, 2) in_bwd_prep_kernel(const __grid_consta
                                 for (int y = 0; y < nw; ++y) {
                                     if (x == 0 && y == 0) continue;
                                     float t[8];
-                                    load8(a.dyp.ptr, a.dyp_fp32 != 0,
+                                    load8(a.dyp.ptr, dyp_f32,
                                           (long long)n * a.dyp.sN + (long long)hq[x] * a.dyp.sH + (long long)wq[y] * a.dyp.sW + c0, t);
 #pragma unroll
-                                    for (int q = 0; q < 8; ++q) g[b][q] += t[q];
+                                    for (int q = 0; q < 8; ++q) g[q] += t[q];
                                 }
                         }
                     }
                 } else {
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) g[b][q] = 0.f;
+                    for (int q = 0; q < 8; ++q) g[q] = 0.f;
                 }
-                if (a.skip.ptr != nullptr)
-                    load8(a.skip.ptr, a.skip_fp32 != 0,
-                          (long long)n * a.skip.sN + (long long)h * a.skip.sH + (long long)w * a.skip.sW + c0, sk[b]);
-                if (need_raw) load8(a.raw, a.raw_fp32 != 0, off[b], z[b]);
-            }
-            // ---- compute + store ---------------------------------------------------------------
+                if (has_skip) {
+                    float t[8];
+                    raw_cvt<ANYF32>(rs[b], skip_f32, t);
 #pragma unroll
-            for (int b = 0; b < kPrepBatch; ++b) {
-                if (!live[b]) continue;
-                if (a.skip.ptr != nullptr) {
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) g[b][q] += sk[b][q];
+                    for (int q = 0; q < 8; ++q) g[q] += t[q];
                 }
                 if (a.g_out != nullptr) {
-                    if (a.g_fp32) store8_f32(a.g_out, off[b], g[b]);
-                    else store8_bf16(a.g_out, nullptr, off[b], g[b]);
+                    if (ANYF32 && a.g_fp32) store8_f32(a.g_out, off, g);
+                    else store8_bf16(a.g_out, nullptr, off, g);
                 }
                 if (seed != 0) {
-                    const uint32_t bits = drop_bits(seed, (unsigned long long)spix[b] * p.CH + chunk);
+                    const uint32_t bits = drop_bits(seed, (unsigned long long)spix * p.CH + chunk);
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) g[b][q] = ((bits >> q) & 1u) ? 2.f * g[b][q] : 0.f;
+                    for (int q = 0; q < 8; ++q) g[q] = ((bits >> q) & 1u) ? 2.f * g[q] : 0.f;
                 }
                 if (need_raw) {
+                    raw_cvt<ANYF32>(rz[b], raw_f32, z);
                     if (norm) {
 #pragma unroll
-                        for (int q = 0; q < 8; ++q) z[b][q] = (z[b][q] - mean[q]) * rstd[q];
+                        for (int q = 0; q < 8; ++q) z[q] = (z[q] - mean[q]) * rstd[q];
                     }
                     if (a.act == SSCG_ACT_RELU) {
 #pragma unroll
-                        for (int q = 0; q < 8; ++q) g[b][q] = z[b][q] > 0.f ? g[b][q] : 0.f;
+                        for (int q = 0; q < 8; ++q) g[q] = z[q] > 0.f ? g[q] : 0.f;
                     } else if (a.act == SSCG_ACT_LRELU) {
 #pragma unroll
-                        for (int q = 0; q < 8; ++q) g[b][q] = z[b][q] > 0.f ? g[b][q] : g[b][q] * a.slope;
+                        for (int q = 0; q < 8; ++q) g[q] = z[q] > 0.f ? g[q] : g[q] * a.slope;
                     } else if (a.act == SSCG_ACT_TANH) {   // raw holds y = tanh(.)
 #pragma unroll
-                        for (int q = 0; q < 8; ++q) g[b][q] = g[b][q] * (1.f - z[b][q] * z[b][q]);
+                        for (int q = 0; q < 8; ++q) g[q] = g[q] * (1.f - z[q] * z[q]);
                     }
                 } else {
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) z[b][q] = 0.f;
+                    for (int q = 0; q < 8; ++q) z[q] = 0.f;
                 }
-                if (a.dz_fp32) store8_f32(a.dz, off[b], g[b]);
-                else store8_bf16(a.dz, a.dz_lo, off[b], g[b]);
+                if (ANYF32 && a.dz_fp32) store8_f32(a.dz, off, g);
+                else store8_bf16(a.dz, ANYF32 ? a.dz_lo : nullptr, off, g);
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
-                    acc1[q] += g[b][q];
-                    acc2[q] += g[b][q] * z[b][q];
+                    acc1[q] += g[q];
+                    acc2[q] += g[q] * z[q];
                 }
             }
         }
@@ -241,7 +327,7 @@ __global__ void __launch_bounds__(256, 2) in_bwd_prep_kernel(const __grid_consta
         }
     }
     __syncthreads();
-    const int nout = p.CH * 16;    // (chunk, q, {sum, sum*z}) pairs for this block
+    const int nout = p.CH * 16;    // (chunk, q, {sum, sum*z}) values of this block
     for (int o = threadIdx.x; o < nout; o += 256) {
         const int ch = o >> 4, e = o & 15;
         float s = 0.f;
@@ -251,9 +337,16 @@ __global__ void __launch_bounds__(256, 2) in_bwd_prep_kernel(const __grid_consta
     }
 }
 
-constexpr int kBwdApplyBatch = 4;
+#ifndef SSCG_BAPPLY_BATCH
+#define SSCG_BAPPLY_BATCH 4
+#endif
+#ifndef SSCG_BAPPLY_MINB
+#define SSCG_BAPPLY_MINB 3
+#endif
+constexpr int kBwdApplyBatch = SSCG_BAPPLY_BATCH;
 
-__global__ void __launch_bounds__(256) in_bwd_apply_kernel(const __grid_constant__ BwdDev p) {
+template <bool ANYF32>
+__global__ void __launch_bounds__(256, SSCG_BAPPLY_MINB) in_bwd_apply_kernel(const __grid_constant__ BwdDev p) {
     const SscgBwdArgs& a = p.a;
     const int n = blockIdx.y;
     const int chunk = threadIdx.x % p.CH;
@@ -261,6 +354,7 @@ __global__ void __launch_bounds__(256) in_bwd_apply_kernel(const __grid_constant
     if (row >= p.rows) return;
     const int c0 = chunk * 8;
     const float inv_cnt = 1.f / (float)(a.H * a.W);
+    const bool raw_f32 = ANYF32 && a.raw_fp32 != 0, dz_f32 = ANYF32 && a.dz_fp32 != 0;
     float mean[8], rstd[8], m1[8], m2[8];
     load_norm(a.stats, a.eps, (long long)n * a.C + c0, inv_cnt, mean, rstd);
     {
@@ -272,31 +366,33 @@ __global__ void __launch_bounds__(256) in_bwd_apply_kernel(const __grid_constant
             m1[2 * q + 1] = s.z * inv_cnt; m2[2 * q + 1] = s.w * inv_cnt;
         }
     }
-    const long long npix = (long long)a.H * a.W;
-    const long long pix0 = (long long)blockIdx.x * p.rows * p.iters + row;
+    const int npix = a.H * a.W;
+    const int pix0 = blockIdx.x * p.rows * p.iters + row;   // per-sample pixel index: 32-bit div/mod below
     for (int it0 = 0; it0 < p.iters; it0 += kBwdApplyBatch) {
-        float z[kBwdApplyBatch][8], g[kBwdApplyBatch][8];
-        long long off[kBwdApplyBatch];
-        bool live[kBwdApplyBatch];
+        RawVec<ANYF32> rz[kBwdApplyBatch], rg[kBwdApplyBatch];
 #pragma unroll
         for (int b = 0; b < kBwdApplyBatch; ++b) {
-            const long long pix = pix0 + (long long)(it0 + b) * p.rows;
-            live[b] = pix < npix;
-            if (!live[b]) continue;
-            off[b] = ((long long)n * npix + pix) * a.C + c0;
-            load8(a.raw, a.raw_fp32 != 0, off[b], z[b]);
-            load8(a.dz, a.dz_fp32 != 0, off[b], g[b]);
+            const int pix = pix0 + (it0 + b) * p.rows;
+            if (pix < npix) {
+                const long long off = ((long long)n * npix + pix) * a.C + c0;
+                raw_load<ANYF32>(rz[b], a.raw, raw_f32, off);
+                raw_load<ANYF32>(rg[b], a.dz, dz_f32, off);
+            }
         }
 #pragma unroll
         for (int b = 0; b < kBwdApplyBatch; ++b) {
-            if (!live[b]) continue;
+            const int pix = pix0 + (it0 + b) * p.rows;
+            if (pix >= npix) continue;
+            const long long off = ((long long)n * npix + pix) * a.C + c0;
+            float z[8], g[8];
+            raw_cvt<ANYF32>(rz[b], raw_f32, z);
+            raw_cvt<ANYF32>(rg[b], dz_f32, g);
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
-                const float zz = (z[b][q] - mean[q]) * rstd[q];
-                g[b][q] = rstd[q] * (g[b][q] - m1[q] - zz * m2[q]);
+                const float zz = (z[q] - mean[q]) * rstd[q];
+                g[q] = rstd[q] * (g[q] - m1[q] - zz * m2[q]);
             }
-            store8_bf16(p.draw, p.draw_lo, off[b], g[b]);
+            store8_bf16(p.draw, ANYF32 ? p.draw_lo : nullptr, off, g);
         }
     }
 }
-
