@@ -37,6 +37,11 @@ struct WgradCfg {
     static constexpr int kMaxStages = (200 * 1024) / kStageBytes;
     static constexpr int kStages = kMaxStages > 6 ? 6 : kMaxStages;
     static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + 256;
+    static constexpr int kTmemCols = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : BN <= 256 ? 256 : 512;
+    static constexpr int kN0 = BN > 256 ? 256 : BN;     // one tcgen05.mma covers at most N = 256 columns
+    static constexpr int kN1 = BN - kN0;
+    static_assert(kStages >= 2, "wgrad tile does not leave room for a 2-stage pipeline");
+    static_assert(SPLIT == 1 || kN1 == 0, "wide wgrad tiles are bf16-mode only");
 };
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
@@ -91,7 +96,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
         fence_mbar_init();
     }
     if (warp == 1) {
-        tmem_alloc(smem_u32(tmem_ptr_smem), BN < 32 ? 32 : BN);
+        tmem_alloc(smem_u32(tmem_ptr_smem), Cfg::kTmemCols);
         tmem_relinquish();
     }
     tc_fence_before();
@@ -136,7 +141,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_bf16(128, BN, 1, 1);
+            constexpr uint32_t idesc = make_idesc_bf16(128, Cfg::kN0, 1, 1);
+            constexpr uint32_t idesc1 = make_idesc_bf16(128, Cfg::kN1 > 0 ? Cfg::kN1 : 16, 1, 1);
             int stage = 0; uint32_t par = 0;
             uint32_t acc = 0;
             for (int kb = 0; kb < nkb; ++kb) {
@@ -149,6 +155,10 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {   // 16 pixels per MMA: +2048 B
                     umma_bf16(tmem_base, da + 128 * k, db + 128 * k, idesc, acc);
+                    if (Cfg::kN1 > 0) {   // columns 256.. of a wide tile (second group of 64-channel atoms)
+                        const uint64_t db1 = make_smem_desc_sw128(st + kBOff + 4 * kWgAtomBytes, kWgAtomBytes, 1024);
+                        umma_bf16(tmem_base + 256, da + 128 * k, db1 + 128 * k, idesc1, acc);
+                    }
                     acc = 1;
                     if (SPLIT == 3) {
                         const uint64_t dalo = make_smem_desc_sw128(st + kLoOff + kAOff, kWgAtomBytes, 1024);
@@ -187,7 +197,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, BN < 32 ? 32 : BN);
+        tmem_dealloc(tmem_base, Cfg::kTmemCols);
     }
 }
 
@@ -256,6 +266,12 @@ extern "C" int sscg_conv_wgrad(const SscgWgradArgs* a, void* stream_) {
         SSCG_WG(64)
         SSCG_WG(128)
         SSCG_WG(256)
+        case 192:
+            if (a->split == 3) return set_error("conv_wgrad: BN=192 is bf16-mode only");
+            return launch_wgrad<192, 1>(tmDy, tmDyLo, tmX, tmXLo, d, grid, stream, a->tag);
+        case 448:
+            if (a->split == 3) return set_error("conv_wgrad: BN=448 is bf16-mode only");
+            return launch_wgrad<448, 1>(tmDy, tmDyLo, tmX, tmXLo, d, grid, stream, a->tag);
         default: return set_error("conv_wgrad: unsupported BN=%d", a->BN);
     }
 #undef SSCG_WG

@@ -101,6 +101,15 @@ class StageWeights:
             self.wg_Kc = self.Kc
             self.wg_taps = self.ntaps_fwd
             wmode = fmode
+        # 7x7 head conv (64 input channels, explicit halo): its weight gradient reads the activation as
+        # a row window of k*64 contiguous elements, so one CTA handles a whole filter row and dY is
+        # fetched once per row instead of once per tap
+        self.wg_window = (s.kind == "conv" and s.in_halo > 0 and s.stride == 1 and self.Cp_in == 64
+                          and k * 64 <= 448 and k > 3 and not split)
+        if self.wg_window:
+            self.wg_Kc = k * 64
+            self.wg_taps = k
+            wmode = 1
         self.dw = torch.zeros(self.wg_taps * self.wg_rows * self.wg_Kc, dtype=torch.float32, device=device)
         self.unpack_wg = K.wprep_args(None, self.transposed, s.Cout, s.Cin, k, k, wmode, self.Cp_in, self.wg_rows,
                                       self.wg_Kc, None)
@@ -417,6 +426,9 @@ class NetPlan:
                                   split=sp, tag=6)
             else:
                 table = self._fwd_table(s)
+                if wt.wg_window:
+                    table = G.taps_conv_fwd_window(s.k, 1, 0)
+                    xview, xlo = c.act[i].window_view(wt.wg_Kc), None
                 wa = K.wgrad_args(dview, dlo, xview, xlo, table, wt.wg_Kc, wt.wg_rows, wt.dw, wt.wg_taps * wt.wg_rows,
                                   split=sp, tag=3 if s.name.startswith("res") else 6)
         # ---- 3. dgrad ------------------------------------------------------------------------

@@ -132,7 +132,10 @@ def wgrad_args(dyview, dy_lo, xview, x_lo, table: TapTable, Kc, Co_pad, dw, w_ro
         tile = pick_tile(dyview.W, 64, dyview.H)
     a.TH, a.TW = tile
     if BN is None:
-        BN = 256 if Kc % 256 == 0 else (128 if Kc % 128 == 0 else 64)
+        if split == 1 and Kc in (192, 448):
+            BN = Kc                       # one wide tile: dY is read once per tap row
+        else:
+            BN = 256 if Kc % 256 == 0 else (128 if Kc % 128 == 0 else 64)
     a.BN = BN
     if ksplit is None:
         blocks = dyview.N * ((dyview.H + a.TH - 1) // a.TH) * ((dyview.W + a.TW - 1) // a.TW)

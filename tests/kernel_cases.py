@@ -408,7 +408,9 @@ CASES = {
     "wgrad_cout21": lambda: case_conv_wgrad(Cin=64, Cout=21, k=7, pad=3),
     "wgrad_ksplit1": lambda: case_conv_wgrad(ksplit=1),
     "wgrad_window_c3": lambda: case_wgrad_window(),
-    "wgrad_window_c21": lambda: case_wgrad_window(Cin=21),
+    "wgrad_window_c21": lambda: case_wgrad_window(Cin=21),            # Kc = 192 -> one 192-wide tile
+    "wgrad_window_c64_wide": lambda: case_wgrad_window(Cin=64, Cout=21),   # head conv: Kc = 448 -> 448-wide tile
+    "wgrad_window_c64_wide_big": lambda: case_wgrad_window(N=2, H=24, W=40, Cin=64, Cout=3),
     # elementwise
     "apply_fwd_relu_reflect": lambda: case_apply_fwd(),
     "apply_fwd_res": lambda: case_apply_fwd(act=L.ACT_NONE, residual=True),
