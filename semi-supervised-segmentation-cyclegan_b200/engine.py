@@ -331,8 +331,11 @@ class NetPlan:
             K.pack_nchw(grad_out.contiguous(), self.gout, L.PAD_ZERO)
         self.bstats.zero_()
         if need_dw and not accumulate_dw:
-            for wt in self.weights:
-                wt.dw.zero_()
+            if getattr(self, "dw_flat", None) is not None:
+                self.dw_flat.zero_()
+            else:
+                for wt in self.weights:
+                    wt.dw.zero_()
         nst = len(self.specs)
         for i in range(nst - 1, -1, -1):
             s, wt = self.specs[i], self.weights[i]

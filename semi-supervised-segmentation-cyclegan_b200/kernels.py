@@ -140,10 +140,27 @@ def wgrad_args(dyview, dy_lo, xview, x_lo, table: TapTable, Kc, Co_pad, dw, w_ro
     if ksplit is None:
         blocks = dyview.N * ((dyview.H + a.TH - 1) // a.TH) * ((dyview.W + a.TW - 1) // a.TW)
         ctas = len(table.taps) * ((Co_pad + 127) // 128) * (Kc // BN)
-        ksplit = max(1, min(blocks, (148 * 2 + ctas - 1) // ctas))
+        ksplit = pick_ksplit(ctas, blocks)
     a.ksplit = ksplit
     a.tag = tag
     return a
+
+
+def pick_ksplit(ctas, blocks, sms=148):
+    """Split-K factor for the weight-gradient GEMM: one CTA per SM at a time (the tile needs most of
+    the shared memory), so the grid should be a whole number of waves.  Prefer the fewest waves that
+    still leaves every CTA a K loop of >= 8 pixel blocks; never exceed the number of blocks."""
+    best = None
+    for waves in (1, 2, 3, 4):
+        ks = max(1, (sms * waves) // ctas)
+        ks = min(ks, blocks)
+        grid = ctas * ks
+        eff = grid / (sms * ((grid + sms - 1) // sms))
+        loop = blocks / ks
+        score = eff - (0.15 if loop < 8 else 0.0) - 0.02 * (waves - 1)
+        if best is None or score > best[0] + 1e-9:
+            best = (score, ks)
+    return best[1]
 
 
 def run_conv(a):

@@ -40,6 +40,10 @@ class NetRunner:
         self._wkey = None
         self.device = None
         self.drop_ctr = None      # device int64 tensor; when set, dropout masks change with its value
+        self.dw_flat = None
+        # direct_grad: backward adds weight gradients straight into the (pre-allocated) p.grad tensors and
+        # returns None to autograd for them — saves one zero-fill and one add per parameter per backward
+        self.direct_grad = False
 
     def _setup(self, device, precision):
         if self.specs is not None and self.precision == precision and self.device == device:
@@ -50,6 +54,14 @@ class NetRunner:
         self.device = device
         split = precision == "bf16x3"
         self.weights = [StageWeights(s, split, True, device, first=(i == 0)) for i, s in enumerate(self.specs)]
+        # one flat fp32 buffer behind all weight-gradient slabs: a single fill zeroes them
+        total = sum(w.dw.numel() for w in self.weights)
+        self.dw_flat = torch.zeros(total, dtype=torch.float32, device=device)
+        off = 0
+        for w in self.weights:
+            n = w.dw.numel()
+            w.dw = self.dw_flat[off:off + n]
+            off += n
         self.plans = {}
         self._wkey = None
 
@@ -78,6 +90,7 @@ class NetRunner:
                 p.res_bwd = self._residual_plan(self.specs)
             self.plans[k] = p
         p.drop_ctr = self.drop_ctr
+        p.dw_flat = self.dw_flat
         return p
 
     def __call__(self, x, training, use_dropout, precision=None):
@@ -138,7 +151,11 @@ class _FusedNet(torch.autograd.Function):
         need_dw = any(ctx.needs_input_grad[3:])
         gx = plan.backward(c, gy.float(), need_dx=need_dx, need_dw=need_dw)
         grads = []
-        if need_dw:
+        if need_dw and runner.direct_grad and all(p.grad is not None for p in runner.params() if p.requires_grad):
+            into = [(s.weight.grad, s.bias.grad if s.bias is not None else None) for s in plan.specs]
+            plan.param_grads(into=into)
+            grads = [None] * (len(ctx.needs_input_grad) - 3)
+        elif need_dw:
             pg = plan.param_grads()
             flags = list(ctx.needs_input_grad[3:])
             j = 0

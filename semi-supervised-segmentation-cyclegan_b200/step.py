@@ -165,6 +165,9 @@ class SemiSupCycleGAN:
         self.g_optimizer = torch.optim.Adam(g_params, lr=lr, betas=(0.5, 0.999), **kw)       # model.py:286
         self.d_optimizer = torch.optim.Adam(d_params, lr=lr, betas=(0.5, 0.999), **kw)       # model.py:287
         self.g_grads, self.d_grads = FlatGrads(g_params), FlatGrads(d_params)
+        for n in (self.Gis, self.Gsi, self.Di, self.Ds):          # p.grad are persistent views: accumulate in place
+            if getattr(n, "_runner", None) is not None:
+                n._runner.direct_grad = True
         P = GraphPool if graph_safe else DevicePool
         self.pool_recon, self.pool_fake_img, self.pool_fake_gt = P(), P(), P()           # model.py:350-352
         if graph_safe:
