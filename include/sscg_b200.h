@@ -88,6 +88,16 @@ typedef struct SscgConvArgs {
     int32_t TH, TW;        /* output tile, TH*TW == 128 */
     int32_t BN;            /* N tile: 16, 32, 64, 128 or 256 */
     int32_t tag;           /* profiling class (0..15), see sscg_prof_begin */
+    /* Row-shift mode (0 = off): for stride-1 convolutions with shift_kw (= 7) horizontal taps per filter
+     * row, `taps` holds ONE entry per filter row (dh, leftmost dw, slab index of the leftmost tap); the
+     * kernel loads a (TW + shift_kw - 1)-pixel row box once and feeds the shift_kw taps from shifted
+     * shared-memory descriptors; tap j uses weight slab brow + j * shift_brow_step.  Needs TH = 1,
+     * TW = 128, BN in {16, 32}, split == 1. */
+    int32_t shift_kw;
+    int32_t shift_brow_step;
+    int32_t shift_base_mode;   /* 2 (use this): descriptor base_offset 0 — the 128B swizzle is a pure function of the
+                                * shared-memory address (verified on B200, tools/shift_probe.py); 1: base_offset = row
+                                * phase (diagnostic only: produces wrong results) */
 } SscgConvArgs;
 
 int sscg_conv_igemm(const SscgConvArgs* a, void* stream);

@@ -41,6 +41,7 @@ class ConvArgs(C.Structure):
         ("bias", C.c_void_p), ("act", C.c_int32), ("slope", C.c_float),
         ("stats", C.c_void_p),
         ("TH", C.c_int32), ("TW", C.c_int32), ("BN", C.c_int32), ("tag", C.c_int32),
+        ("shift_kw", C.c_int32), ("shift_brow_step", C.c_int32), ("shift_base_mode", C.c_int32),
     ]
 
 

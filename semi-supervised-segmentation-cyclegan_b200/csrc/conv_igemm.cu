@@ -33,6 +33,8 @@ struct ConvDev {
     int Co_pad;
     int TH, TW, tw_shift;
     int tiles_h, tiles_w;
+    int shift_brow_step;   // row-shift mode: weight slab step between consecutive kw taps (+1 / -1)
+    int shift_base_mode;   // row-shift mode: 1 = descriptor base_offset carries the row phase, 2 = base_offset 0
     int tiles_x;    // tiles_h * tiles_w * N
     int n_ntiles;   // Co_pad / BN
     int total_tiles;
@@ -49,13 +51,20 @@ struct ConvDev {
 constexpr int kTileM = 128;
 constexpr int kABytes = kTileM * 128;   // 128 pixels x 64 bf16
 
-template <int BN, int SPLIT>
+// SKW > 0 selects the row-shift mode (1 x 128 pixel tiles, stride 1): one TMA box of 128 + SKW - 1
+// pixels per filter row and channel block is shared by the SKW horizontal taps, which read it through
+// descriptors whose start address is shifted by one 128-byte pixel row per tap.
+template <int BN, int SPLIT, int SKW = 0>
 struct IgemmCfg {
     static constexpr int kPlanes = (SPLIT == 3) ? 2 : 1;
     static constexpr int kBBytes = BN * 128;
-    static constexpr int kStageBytes = kPlanes * (kABytes + kBBytes);
+    static constexpr int kARows = SKW > 0 ? kTileM + SKW - 1 : kTileM;
+    static constexpr int kAStage = SKW > 0 ? ((kARows * 128 + 1023) / 1024) * 1024 : kABytes;
+    static constexpr int kBStage = SKW > 0 ? SKW * kBBytes : kBBytes;
+    static constexpr int kStageBytes = kPlanes * (kAStage + kBStage);
+    static constexpr int kTxBytes = kPlanes * (kARows * 128 + kBStage);
     // wide tiles: as deep a ring as fits one CTA per SM; narrow tiles: 4 stages so that 2+ CTAs fit
-    static constexpr int kMaxStages = (BN >= 128 ? 200 * 1024 : 100 * 1024) / kStageBytes;
+    static constexpr int kMaxStages = ((BN >= 128 || SKW > 0) ? 200 * 1024 : 100 * 1024) / kStageBytes;
     static constexpr int kStages = kMaxStages > 6 ? 6 : (kMaxStages < 2 ? 2 : kMaxStages);
     static constexpr int kAccCols = BN < 32 ? 32 : BN;          // columns per accumulator
     static constexpr int kTmemCols = 2 * kAccCols < 32 ? 32 : 2 * kAccCols;
@@ -91,14 +100,15 @@ __device__ __forceinline__ TileInfo decode_tile(const ConvDev& p, int tile, int 
     return t;
 }
 
-template <int BN, int SPLIT>
+template <int BN, int SPLIT, int SKW>
 __global__ void __launch_bounds__(192, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
                   const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo,
                   const __grid_constant__ ConvDev p) {
-    using Cfg = IgemmCfg<BN, SPLIT>;
+    using Cfg = IgemmCfg<BN, SPLIT, SKW>;
     constexpr int kStages = Cfg::kStages;
     constexpr int kPlanes = Cfg::kPlanes;
+    static_assert(SKW == 0 || SPLIT == 1, "row-shift mode is bf16-mode only");
 
     // ---- shared memory carve-up ----------------------------------------------------------------
     extern __shared__ uint8_t smem_raw[];
@@ -149,13 +159,20 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     const SscgTap tap = p.taps[t.tap0 + tp];
                     mbar_wait(smem_u32(&empty_bar[stage]), par ^ 1, 1);
                     const uint32_t fb = smem_u32(&full_bar[stage]);
-                    mbar_arrive_expect_tx(fb, Cfg::kStageBytes);
+                    mbar_arrive_expect_tx(fb, Cfg::kTxBytes);
                     uint8_t* st = smem + stage * Cfg::kStageBytes;
                     const int cw = t.j0 * p.stride + tap.dw + p.org_w;
                     const int ch = t.i0 * p.stride + tap.dh + p.org_h;
                     const int brow = tap.brow * p.Co_pad + t.n0;
                     tma_load_4d(smem_u32(st), &tmA, fb, cb * 64, cw, ch, t.n);
-                    tma_load_2d(smem_u32(st + kPlanes * kABytes), &tmB, fb, cb * 64, brow);
+                    if (SKW > 0) {   // one weight box per horizontal tap of this filter row
+#pragma unroll
+                        for (int j = 0; j < (SKW > 0 ? SKW : 1); ++j)
+                            tma_load_2d(smem_u32(st + Cfg::kAStage + j * Cfg::kBBytes), &tmB, fb, cb * 64,
+                                        (tap.brow + j * p.shift_brow_step) * p.Co_pad + t.n0);
+                    } else {
+                        tma_load_2d(smem_u32(st + kPlanes * kABytes), &tmB, fb, cb * 64, brow);
+                    }
                     if (SPLIT == 3) {
                         tma_load_4d(smem_u32(st + kABytes), &tmAlo, fb, cb * 64, cw, ch, t.n);
                         tma_load_2d(smem_u32(st + kPlanes * kABytes + Cfg::kBBytes), &tmBlo, fb, cb * 64, brow);
@@ -184,6 +201,24 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     mbar_wait(smem_u32(&full_bar[stage]), par, 2);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+                    if (SKW > 0) {
+                        const uint32_t sbw = sa + Cfg::kAStage;
+#pragma unroll
+                        for (int j = 0; j < (SKW > 0 ? SKW : 1); ++j) {
+                            // tap j reads pixel rows j .. j+127 of the shared row box
+                            const uint64_t daj = make_smem_desc_sw128(sa + j * 128, 0, 1024,
+                                                                      p.shift_base_mode == 1 ? (uint32_t)j : 0u);
+                            const uint64_t dbj = make_smem_desc_sw128(sbw + j * Cfg::kBBytes, 0, 1024);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                umma_bf16(d_tmem, daj + 2 * k, dbj + 2 * k, idesc, accum);
+                                accum = 1;
+                            }
+                        }
+                        umma_commit(smem_u32(&empty_bar[stage]));
+                        if (++stage == kStages) { stage = 0; par ^= 1; }
+                        continue;
+                    }
                     const uint32_t sb = sa + kPlanes * kABytes;
                     const uint64_t da = make_smem_desc_sw128(sa, 0, 1024);
                     const uint64_t db = make_smem_desc_sw128(sb, 0, 1024);
@@ -351,18 +386,18 @@ static int sm_count() {
     return n;
 }
 
-template <int BN, int SPLIT>
+template <int BN, int SPLIT, int SKW = 0>
 static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmAlo, const CUtensorMap& tmB,
                         const CUtensorMap& tmBlo, const ConvDev& d, cudaStream_t stream, int tag) {
-    using Cfg = IgemmCfg<BN, SPLIT>;
+    using Cfg = IgemmCfg<BN, SPLIT, SKW>;
     static int occ = 0;
     if (occ == 0) {
-        cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel<BN, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel<BN, SPLIT, SKW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              Cfg::kSmemBytes);
         if (e != cudaSuccess) return set_error("conv_igemm: cudaFuncSetAttribute(smem=%d): %s", Cfg::kSmemBytes,
                                                cudaGetErrorString(e));
         int o = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, conv_igemm_kernel<BN, SPLIT>, 192, Cfg::kSmemBytes);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, conv_igemm_kernel<BN, SPLIT, SKW>, 192, Cfg::kSmemBytes);
         if (e != cudaSuccess || o < 1) o = 1;
         const int tmem_limit = 512 / Cfg::kTmemCols;     // resident CTAs must all fit their TMEM columns
         if (o > tmem_limit) o = tmem_limit;
@@ -373,7 +408,7 @@ static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmAlo, const 
     if (grid > d.total_tiles) grid = d.total_tiles;
     {
         LaunchScope ls(tag, stream);
-        conv_igemm_kernel<BN, SPLIT><<<grid, 192, Cfg::kSmemBytes, stream>>>(tmA, tmAlo, tmB, tmBlo, d);
+        conv_igemm_kernel<BN, SPLIT, SKW><<<grid, 192, Cfg::kSmemBytes, stream>>>(tmA, tmAlo, tmB, tmBlo, d);
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_error("conv_igemm<%d,%d> launch: %s", BN, SPLIT, cudaGetErrorString(e));
@@ -396,8 +431,15 @@ extern "C" int sscg_conv_igemm(const SscgConvArgs* a, void* stream_) {
     if (a->phase_start[a->n_phases] > SSCG_MAX_TAPS) return set_error("conv_igemm: too many taps");
     if (a->stride * a->TW > 256 || a->stride * a->TH > 256) return set_error("conv_igemm: box too large");
 
+    const int skw = a->shift_kw;
+    if (skw != 0) {
+        if (skw != 7 || a->split != 1 || a->stride != 1 || a->n_phases != 1 || a->TH != 1 || a->TW != 128 ||
+            (a->BN != 16 && a->BN != 32))
+            return set_error("conv_igemm: row-shift mode needs kw=7, bf16, stride 1, 1x128 tiles, BN 16/32");
+    }
     CUtensorMap tmA, tmAlo, tmB, tmBlo;
-    const uint32_t boxA[4] = {64u, (uint32_t)(a->TW * a->stride), (uint32_t)(a->TH * a->stride), 1u};
+    const uint32_t boxA[4] = {64u, (uint32_t)(skw ? a->TW + skw - 1 : a->TW * a->stride),
+                              (uint32_t)(a->TH * a->stride), 1u};
     const uint32_t esA[4] = {1u, (uint32_t)a->stride, (uint32_t)a->stride, 1u};
     if (int rc = encode_view_4d(&tmA, a->x, a->x.ptr, boxA, esA)) return rc;
     tmAlo = tmA;
@@ -422,6 +464,8 @@ extern "C" int sscg_conv_igemm(const SscgConvArgs* a, void* stream_) {
     const int Hph = (a->Ho + os - 1) / os, Wph = (a->Wo + os - 1) / os;
     d.tiles_h = (Hph + a->TH - 1) / a->TH;
     d.tiles_w = (Wph + a->TW - 1) / a->TW;
+    d.shift_brow_step = a->shift_brow_step;
+    d.shift_base_mode = a->shift_base_mode;
     d.tiles_x = d.tiles_h * d.tiles_w * d.N;
     d.n_ntiles = a->Co_pad / a->BN;
     d.total_tiles = d.tiles_x * d.n_ntiles * a->n_phases;
@@ -429,6 +473,10 @@ extern "C" int sscg_conv_igemm(const SscgConvArgs* a, void* stream_) {
     d.y_sN = a->y_sN; d.y_sH = a->y_sH; d.y_sW = a->y_sW; d.y_oh = a->y_oh; d.y_ow = a->y_ow;
     d.bias = a->bias; d.act = a->act; d.slope = a->slope; d.stats = a->stats;
     if (d.total_tiles <= 0) return 0;
+    if (skw == 7) {
+        if (a->BN == 16) return launch_igemm<16, 1, 7>(tmA, tmAlo, tmB, tmBlo, d, stream, a->tag);
+        return launch_igemm<32, 1, 7>(tmA, tmAlo, tmB, tmBlo, d, stream, a->tag);
+    }
 
 #define SSCG_DISPATCH(BN_)                                                                  \
     case BN_:                                                                                \

@@ -20,9 +20,18 @@ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
     x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
     return x ^ (x >> 31);
 }
-// 8 keep-bits for the 8 channels of one vector; element id = vector index in the unpadded tensor
+// 8 keep-bits for the 8 channels of one vector; element id = vector index in the unpadded tensor.
+// Counter-based: murmur3's 32-bit finaliser over (index, seed) — cheap enough for a bandwidth kernel
+// (a 64-bit splitmix cost 20 % of in_apply), identical in forward and backward.
 __device__ __forceinline__ uint32_t drop_bits(uint64_t seed, uint64_t vec_index) {
-    return static_cast<uint32_t>(splitmix64(seed ^ (vec_index * 0xD1342543DE82EF95ull)) >> 24) & 0xffu;
+    uint32_t x = static_cast<uint32_t>(vec_index) * 0x9E3779B1u + static_cast<uint32_t>(seed);
+    x ^= x >> 16; x *= 0x85EBCA6Bu;
+    x ^= x >> 13; x *= 0xC2B2AE35u;
+    x ^= x >> 16;
+    x ^= static_cast<uint32_t>(seed >> 32) * 0x27D4EB2Fu;
+    x ^= x >> 15; x *= 0x2C1B3C6Du;
+    x ^= x >> 12;
+    return (x >> 11) & 0xffu;
 }
 __device__ __forceinline__ void load8(const void* base, bool fp32, long long off, float (&v)[8]) {
     if (fp32) {
@@ -249,7 +258,10 @@ static void vec_layout(int C, long long npix, int& CH, int& rows, int& iters, in
     CH = C / 8;
     rows = 256 / CH;
     if (rows < 1) rows = 1;
-    iters = 8;
+    // pixels per thread: enough to amortise the per-thread statistics setup and the per-block atomics,
+    // while keeping >= ~2 blocks per SM in flight for a 16-sample batch (grid.y = N multiplies this)
+    iters = 32;
+    while (iters > 8 && npix / ((long long)rows * iters) < 16) iters /= 2;
     long long per_block = (long long)rows * iters;
     gridx = (int)((npix + per_block - 1) / per_block);
     if (gridx < 1) gridx = 1;

@@ -250,8 +250,9 @@ __global__ void __launch_bounds__(256, SSCG_PREP_MINB) in_bwd_prep_kernel(const 
                 float g[8], z[8];
                 if (has_dyp) {
                     raw_cvt<ANYF32>(rg[b], dyp_f32, g);
-                    if (fold) {   // halo positions that mirror onto this pixel (border pixels only)
-                        const int w = pix % a.W, h = pix / a.W;
+                    const int w = pix % a.W, h = pix / a.W;
+                    // halo positions that mirror onto this pixel exist only within `pad` of the border
+                    if (fold && (h <= a.pad || w <= a.pad || h >= a.H - 1 - a.pad || w >= a.W - 1 - a.pad)) {
                         int hq[3], wq[3];
                         const int nh = fold_positions(h, a.H, a.pad, a.pad_mode, hq);
                         const int nw = fold_positions(w, a.W, a.pad, a.pad_mode, wq);

@@ -180,8 +180,10 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // K-major, SWIZZLE_128B, 64 bf16 (=128 B) per row: 8-row atoms of 1024 B, SBO = 1024, LBO unused.
 // MN-major, SWIZZLE_128B: 64 MN-elements (128 B) x 8 K-rows atoms; SBO = stride between 8-K-row
 // groups (1024 B for dense rows), LBO = stride between 64-wide MN atoms.
-__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                         uint32_t base_offset = 0) {
     uint64_t d = 0;
+    d |= static_cast<uint64_t>(base_offset & 7u) << 49;   // phase of the 8-row swizzle pattern at the start address
     d |= static_cast<uint64_t>((saddr >> 4) & 0x3fff);
     d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3fff) << 16;
     d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3fff) << 32;

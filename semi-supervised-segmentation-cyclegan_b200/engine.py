@@ -169,6 +169,12 @@ class NetPlan:
         consumer gets hi/lo planes."""
         return (not s.norm) and (s.final or self.split == 1)
 
+    def _rowshift_ok(self, s: StageSpec, n_cols: int) -> bool:
+        """7x7 stride-1 convolutions in bf16 mode run in row-shift mode (see SscgConvArgs.shift_kw) when
+        the GEMM's N fits the 16/32-column tiles of that mode (dgrad splits wider N into 32-column tiles)."""
+        return (self.split == 1 and s.k == 7 and s.stride == 1 and s.kind in ("conv", "window")
+                and n_cols in (16, 32))
+
     # ------------------------------------------------------------------ buffers
     def _new_ctx(self) -> Ctx:
         c = Ctx()
@@ -299,9 +305,13 @@ class NetPlan:
                 else:
                     dst = c.out if s.final else c.act[i + 1]
                     assert dst.pad == 0
+                    kw = {}
+                    if self._rowshift_ok(s, wt.Co_pad):      # 7x7 head: one row box feeds the 7 horizontal taps
+                        table = G.taps_rowshift_fwd(s.k, s.k, 0 if s.in_halo else -s.pad)
+                        kw = dict(shift_kw=s.k, shift_brow_step=1, BN=min(wt.Co_pad, 32))
                     ca = K.conv_args(view, lo, table, wt.Kc, wt.w_fwd, wt.w_fwd_lo, wt.ntaps_fwd * wt.Co_pad, wt.Co_pad,
                                      dst.hi.data_ptr(), dst.fp32, (dst.sN, dst.sH, dst.sW), (0, 0), ho, wo,
-                                     bias=wt.bias_pad, act=s.act, split=sp, tag=4)
+                                     bias=wt.bias_pad, act=s.act, split=sp, tag=4, **kw)
                     args = (ca, None)
                 self._args_cache[key] = args
             ca, aa = args
@@ -436,6 +446,7 @@ class NetPlan:
                                   split=sp, tag=3 if s.name.startswith("res") else 6)
         # ---- 3. dgrad ------------------------------------------------------------------------
         da = None
+        dkw = {}
         if (i > 0 or need_dx) and wt.need_dgrad:
             gin = self.gact[i]
             dview = self._draw_view(i)
@@ -447,13 +458,16 @@ class NetPlan:
             else:
                 org = 0 if s.in_halo else -s.pad
                 table = G.taps_conv_dgrad(s.k, s.k, s.stride, org)
+                if self._rowshift_ok(s, 16):
+                    table = G.taps_rowshift_dgrad(s.k, s.k, org)
+                    dkw = dict(shift_kw=s.k, shift_brow_step=-1, BN=min(wt.Ci_pad, 32))
                 if s.in_halo:
                     Ho_d, Wo_d, yoff = gin.Hp, gin.Wp, (0, 0)
                 else:
                     Ho_d, Wo_d, yoff = hin, win, (0, 0)
             da = K.conv_args(dview, dlo, table, wt.Kc_d, wt.w_dg, wt.w_dg_lo, s.k * s.k * wt.Ci_pad, wt.Ci_pad,
                              gin.hi.data_ptr(), gin.fp32, (gin.sN, gin.sH, gin.sW), yoff, Ho_d, Wo_d, split=sp,
-                             tag=2 if s.name.startswith("res") else 5)
+                             tag=2 if s.name.startswith("res") else 5, **dkw)
         return ba, use_apply, wa, da
 
     def _resolve_t(self, tag, like):

@@ -137,3 +137,17 @@ def taps_convT_dgrad(kh: int, kw: int, stride: int, pad: int) -> TapTable:
     """Gradient w.r.t. the input of ConvTranspose2d: dX[i] = sum_k dY[s*i - pad + k] W[k] — a strided
     forward-style gather over dY."""
     return taps_conv_fwd(kh, kw, stride, -pad)
+
+
+def taps_rowshift_fwd(kh: int, kw: int, org: int) -> TapTable:
+    """Row-shift mode, forward stride-1 conv: one entry per filter row = (dh, leftmost dw, slab of the
+    leftmost tap); tap j of the row is slab brow + j (see SscgConvArgs.shift_kw)."""
+    taps = [(a, 0, a * kw) for a in range(kh)]
+    return TapTable(1, [0, kh, kh, kh, kh], taps, 1, org, org)
+
+
+def taps_rowshift_dgrad(kh: int, kw: int, org: int) -> TapTable:
+    """Row-shift mode, stride-1 dgrad: dX[i] = sum_k dY[i - k - org] W[k]; leftmost input column is
+    dw = -(kw-1) - org and belongs to tap kw-1, so slabs run backwards (shift_brow_step = -1)."""
+    taps = [(-a - org, -(kw - 1) - org, a * kw + kw - 1) for a in range(kh)]
+    return TapTable(1, [0, kh, kh, kh, kh], taps, 1, 0, 0)

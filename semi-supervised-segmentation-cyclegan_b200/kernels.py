@@ -90,7 +90,8 @@ def fill_taps(dst_taps, table: TapTable):
 
 
 def conv_args(xview, x_lo, table: TapTable, Kc, w, w_lo, w_rows, Co_pad, y_ptr, y_fp32, y_strides, y_off, Ho, Wo,
-              bias=None, act=L.ACT_NONE, slope=0.2, stats=None, BN=None, tile=None, split=1, tag=4):
+              bias=None, act=L.ACT_NONE, slope=0.2, stats=None, BN=None, tile=None, split=1, tag=4,
+              shift_kw=0, shift_brow_step=1, shift_base_mode=2):
     a = L.ConvArgs()
     a.x = xview
     a.x_lo = x_lo
@@ -115,6 +116,9 @@ def conv_args(xview, x_lo, table: TapTable, Kc, w, w_lo, w_rows, Co_pad, y_ptr, 
     a.TH, a.TW = tile
     a.BN = BN if BN is not None else (Co_pad if Co_pad <= 256 else 256)
     a.tag = tag
+    a.shift_kw, a.shift_brow_step, a.shift_base_mode = shift_kw, shift_brow_step, shift_base_mode
+    if shift_kw:
+        a.TH, a.TW = 1, 128
     return a
 
 

@@ -55,7 +55,7 @@ def _result(got, ref, tol):
 
 # ------------------------------------------------------------------------------------------------
 def case_conv_fwd(N=2, H=16, W=16, Cin=64, Cout=64, k=3, stride=1, pad=1, reflect=True, explicit=True,
-                  out_fp32=True, bias=False, act=L.ACT_NONE, stats=False, split=1):
+                  out_fp32=True, bias=False, act=L.ACT_NONE, stats=False, split=1, shift=0):
     """Conv2d forward, regular mode. explicit=True: halo materialised in the buffer (org 0);
     explicit=False: interior view + zero fill (org = -pad)."""
     _setup()
@@ -81,10 +81,12 @@ def case_conv_fwd(N=2, H=16, W=16, Cin=64, Cout=64, k=3, stride=1, pad=1, reflec
         bias_pad = torch.zeros(Co_pad, device=DEV)
         bias_pad[:Cout] = b
     table = G.taps_conv_fwd(k, k, stride, 0 if explicit else -pad)
+    if shift:
+        table = G.taps_rowshift_fwd(k, k, 0 if explicit else -pad)
     view = buf.view(interior=False) if explicit else buf.view(interior=True)
     a = K.conv_args(view, buf.lo_ptr(interior=not explicit), table, Kc, slab, slab_lo, k * k * Co_pad, Co_pad,
                     y.data_ptr(), out_fp32, (Ho * Wo * Co_pad, Wo * Co_pad, Co_pad), (0, 0), Ho, Wo, bias=bias_pad,
-                    act=act, stats=st, split=split)
+                    act=act, stats=st, split=split, shift_kw=(k if shift else 0), shift_base_mode=2)
     K.run_conv(a)
     torch.cuda.synchronize()
     xp = F.pad(x, (pad,) * 4, mode="reflect" if reflect else "constant") if pad else x
@@ -156,7 +158,7 @@ def case_convT_fwd(N=2, H=8, W=8, Cin=128, Cout=64):
     return _result(y[..., :Cout].permute(0, 3, 1, 2), ref, 2e-4)
 
 
-def case_conv_dgrad(N=2, H=16, W=16, Cin=64, Cout=128, k=3, stride=1, pad=1):
+def case_conv_dgrad(N=2, H=16, W=16, Cin=64, Cout=128, k=3, stride=1, pad=1, shift=0):
     """Gradient w.r.t. the (zero-padded, implicit halo) input of a Conv2d."""
     _setup()
     Ho, Wo = G.conv_out(H, k, stride, pad), G.conv_out(W, k, stride, pad)
@@ -169,8 +171,12 @@ def case_conv_dgrad(N=2, H=16, W=16, Cin=64, Cout=128, k=3, stride=1, pad=1):
     slab, _, _ = _wslab(w, False, 2, 0, Ci_pad, Kc, k, k, Cout, Cin)
     dx = torch.zeros(N, H, W, Ci_pad, device=DEV)
     table = G.taps_conv_dgrad(k, k, stride, -pad)
+    kw = {}
+    if shift:
+        table = G.taps_rowshift_dgrad(k, k, -pad)
+        kw = dict(shift_kw=k, shift_brow_step=-1, shift_base_mode=2, BN=min(Ci_pad, 32))
     a = K.conv_args(buf.view(interior=True), None, table, Kc, slab, None, k * k * Ci_pad, Ci_pad, dx.data_ptr(), True,
-                    (H * W * Ci_pad, W * Ci_pad, Ci_pad), (0, 0), H, W)
+                    (H * W * Ci_pad, W * Ci_pad, Ci_pad), (0, 0), H, W, **kw)
     K.run_conv(a)
     torch.cuda.synchronize()
     ref = torch.nn.grad.conv2d_input((N, Cin, H, W), w, dy, stride=stride, padding=pad)
@@ -382,6 +388,14 @@ CASES = {
     "fwd_bf16_lrelu_bias": lambda: case_conv_fwd(Cin=64, Cout=64, out_fp32=False, bias=True, act=L.ACT_LRELU),
     "fwd_wide_image": lambda: case_conv_fwd(N=1, H=8, W=256, Cin=64, Cout=64),
     "fwd_split3": lambda: case_conv_fwd(Cin=128, Cout=128, split=3),
+    # row-shift mode (7x7, one row box shared by the 7 horizontal taps)
+    "shift_fwd_head21": lambda: case_conv_fwd(N=2, H=12, W=200, Cin=64, Cout=21, k=7, pad=3, bias=True, shift=1),
+    "shift_fwd_head3_tanh": lambda: case_conv_fwd(N=1, H=9, W=300, Cin=64, Cout=3, k=7, pad=3, bias=True,
+                                                  act=L.ACT_TANH, shift=1),
+    "shift_fwd_oob": lambda: case_conv_fwd(N=2, H=10, W=70, Cin=64, Cout=21, k=7, pad=3, reflect=False, explicit=False,
+                                           shift=1),
+    "shift_dgrad_head": lambda: case_conv_dgrad(N=2, H=12, W=150, Cin=64, Cout=21, k=7, pad=3, shift=1),
+    "shift_dgrad_stem": lambda: case_conv_dgrad(N=2, H=10, W=140, Cin=3, Cout=64, k=7, pad=3, shift=1),
     # window mode
     "win_stem_c3": lambda: case_conv_window(),
     "win_stem_c21": lambda: case_conv_window(Cin=21),
