@@ -458,7 +458,7 @@ class NetPlan:
             else:
                 org = 0 if s.in_halo else -s.pad
                 table = G.taps_conv_dgrad(s.k, s.k, s.stride, org)
-                if self._rowshift_ok(s, 16):
+                if self._rowshift_ok(s, wt.Ci_pad):     # narrow N only (stem dgrad); N = 64 is faster in regular mode
                     table = G.taps_rowshift_dgrad(s.k, s.k, org)
                     dkw = dict(shift_kw=s.k, shift_brow_step=-1, BN=min(wt.Ci_pad, 32))
                 if s.in_halo:
