@@ -117,3 +117,30 @@ def test_graphed_step_matches_eager_losses():
     # step 5 of training from identical weights on a fixed batch: graph replays == eager launches
     for k in KEYS:
         assert abs(outs[0][k] - outs[1][k]) <= 2e-3 * max(1.0, abs(outs[0][k])), (k, outs[0][k], outs[1][k])
+
+
+@pytest.mark.parametrize("name,C,cimg,H,W", [("cityscapes_19", 19, 3, 128, 256), ("cityscapes_20", 20, 3, 128, 256),
+                                             ("acdc", 4, 1, 128, 128), ("voc_large", 21, 3, 256, 256)])
+def test_other_baseline_configs_run(name, C, cimg, H, W):
+    """BASELINE.json configs #3-#5 (class counts 19/20/4, 1-channel input, non-square and larger crops) at
+    reduced batch/size: forward parity of Gsi in parity mode + one finite bf16 training step."""
+    import sscg_b200  # noqa: F401
+    from oracle import ref_arch as RA
+    from sscg_b200.step import SemiSupCycleGAN
+    torch.manual_seed(0)
+    m = SemiSupCycleGAN(n_classes=C, img_channels=cimg, variant="classic", use_dropout=False, device="cuda:0",
+                        precision="bf16x3")
+    x = torch.rand(1, cimg, H // 2, W // 2) * 2 - 1
+    m.Gsi.eval()
+    with torch.no_grad():
+        y = m.Gsi(x.cuda()).cpu()
+    yr = RA.resnet_generator({k: v.detach().cpu() for k, v in m.Gsi.state_dict().items()}, x, 9, tanh=False)
+    assert float((y - yr).abs().max() / yr.abs().max()) <= 1e-3
+    for net in m.nets.values():
+        net.precision = "bf16"
+    m.Gsi.train()
+    l_img = (torch.rand(2, cimg, H, W) * 2 - 1).cuda()
+    unl = (torch.rand(2, cimg, H, W) * 2 - 1).cuda()
+    l_gt = torch.randint(0, C, (2, 1, H, W)).cuda()
+    out = m.train_step(l_img, l_gt, unl)
+    assert all(bool(torch.isfinite(v)) for v in out.values()), out
