@@ -188,6 +188,15 @@ class SemiSupCycleGAN:
     def train_step(self, l_img, l_gt, unl_img):
         """One optimisation step on device tensors: l_img, unl_img N x Cimg x H x W fp32 in [-1, 1],
         l_gt N x 1 x H x W int64.  Returns the 9 logged scalars (model.py:548-550) as 0-d device tensors."""
+        for point in self.step_segments(l_img, l_gt, unl_img):
+            (self.g_grads if point == "g" else self.d_grads).allreduce_mean()
+        return self.last_losses
+
+    def step_segments(self, l_img, l_gt, unl_img):
+        """The step as a generator that yields at the two points where gradients must be all-reduced
+        ("g" after gen_loss.backward(), "d" after discriminator_loss.backward()).  The eager driver
+        (train_step) and the CUDA-graph driver (GraphedStep: one graph per segment, collectives between
+        them stay eager) share this single body.  Results land in self.last_losses."""
         C, w = self.C, self.w
         head = self.variant == "head"
         frozen_d = [self.Di, self.Ds] + ([self.old_Di] if head else [])
@@ -233,7 +242,7 @@ class SemiSupCycleGAN:
                                 + gt_cycle_loss * w.lamda_gt)
         gen_loss = fullsupervisedloss + unsupervisedloss                                 # :468
         gen_loss.backward()                                                              # :472
-        self.g_grads.allreduce_mean()
+        yield "g"
         self.g_optimizer.step()                                                          # :474
         # ---- discriminator phase (model.py:481-542) ----------------------------------------
         set_grad(frozen_d, True)                                                         # :481
@@ -266,9 +275,9 @@ class SemiSupCycleGAN:
             cycle_img_dis_loss = torch.zeros((), device=l_img.device)
             discriminator_loss = w.discriminator_weight * (img_dis_loss + gt_dis_loss)
         discriminator_loss.backward()                                                    # :539
-        self.d_grads.allreduce_mean()
+        yield "d"
         self.d_optimizer.step()                                                          # :542
-        return {"img_dis_loss": img_dis_loss.detach(), "gt_dis_loss": gt_dis_loss.detach(),
+        self.last_losses = {"img_dis_loss": img_dis_loss.detach(), "gt_dis_loss": gt_dis_loss.detach(),
                 "cycle_img_dis_loss": cycle_img_dis_loss.detach(), "img_gen_loss": img_gen_loss.detach(),
                 "gt_gen_loss": gt_gen_loss.detach(), "img_cycle_loss": img_cycle_loss.detach(),
                 "gt_cycle_loss": gt_cycle_loss.detach(), "lab_loss_CE": lab_loss_CE.detach(),
@@ -318,13 +327,33 @@ class GraphedStep:
                 model.train_step(self.l_img, self.l_gt, self.unl_img)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        self.graph = torch.cuda.CUDAGraph()
+        import torch.distributed as dist
+        self.world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
         # capture records the kernels without running them: no pool decision is consumed here (the
         # captured kernels read whatever decision is in model.pool_dec at replay time)
         l0 = K.launch_count()
-        with torch.cuda.graph(self.graph):
-            out = model.train_step(self.l_img, self.l_gt, self.unl_img)
-            self.losses = torch.stack([out[k] for k in self.KEYS])
+        if self.world == 1:
+            self.graphs = [torch.cuda.CUDAGraph()]
+            with torch.cuda.graph(self.graphs[0]):
+                out = model.train_step(self.l_img, self.l_gt, self.unl_img)
+                self.losses = torch.stack([out[k] for k in self.KEYS])
+            self.points = []
+        else:
+            # NCCL collectives stay outside the graphs: segment | all-reduce G | segment | all-reduce D | segment
+            pool = torch.cuda.graph_pool_handle()
+            gen = model.step_segments(self.l_img, self.l_gt, self.unl_img)
+            self.graphs, self.points = [], []
+            done = False
+            while not done:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, pool=pool):
+                    try:
+                        self.points.append(next(gen))
+                    except StopIteration:
+                        done = True
+                        out = model.last_losses
+                        self.losses = torch.stack([out[k] for k in self.KEYS])
+                self.graphs.append(g)
         self.launches_per_step = K.launch_count() - l0
         torch.cuda.synchronize()
 
@@ -334,7 +363,10 @@ class GraphedStep:
         self.l_gt.copy_(l_gt, non_blocking=True)
         self.unl_img.copy_(unl_img, non_blocking=True)
         self.m.feed_pool_decisions()
-        self.graph.replay()
+        for i, g in enumerate(self.graphs):
+            g.replay()
+            if i < len(self.points):
+                (self.m.g_grads if self.points[i] == "g" else self.m.d_grads).allreduce_mean()
         return self.losses
 
     def step_host(self, l_img_host, l_gt_host, unl_img_host):
