@@ -52,6 +52,19 @@ __device__ __forceinline__ void raw_cvt(const RawVec<ANYF32>& r, bool fp32, floa
     }
 }
 
+// Running (row, column) of a thread's pixel sequence pix0, pix0 + step, pix0 + 2*step, ...: one
+// div/mod at the start, then additions only (the per-pixel 64-bit index arithmetic and divisions
+// were a third of the instructions of these kernels).
+struct PixWalk {
+    int pix, h, w;
+    __device__ __forceinline__ PixWalk(int pix0, int W) : pix(pix0), h(pix0 / W), w(pix0 % W) {}
+    __device__ __forceinline__ void advance(int step, int W) {
+        pix += step;
+        w += step;
+        while (w >= W) { w -= W; ++h; }
+    }
+};
+
 // ---------------------------------------------------------------------------------------------
 // forward: y = dropout(act(instance_norm(raw))) (+ residual), written with halo
 // ---------------------------------------------------------------------------------------------
@@ -89,21 +102,22 @@ __global__ void __launch_bounds__(256, SSCG_APPLY_MINB) in_apply_kernel(const __
     const uint64_t seed = (a.drop_seed != 0 && a.drop_ctr) ? (a.drop_seed ^ (*a.drop_ctr * 0x9E3779B97F4A7C15ull))
                                                            : a.drop_seed;
     const int npix = Hp * Wp;
-    const int pix0 = blockIdx.x * p.rows * p.iters + row;   // per-sample pixel index: 32-bit div/mod below
+    PixWalk walk(blockIdx.x * p.rows * p.iters + row, Wp);      // walks the PADDED destination pixels
+    const long long dbase = (long long)n * npix * a.C + c0;
+    const long long sbase = (long long)n * a.H * a.W;
     for (int it0 = 0; it0 < p.iters; it0 += kApplyBatch) {
         RawVec<ANYF32> rv[kApplyBatch];
         RawVec<false> rr[kApplyBatch], rl[kApplyBatch];
-        long long spix[kApplyBatch];
+        int spix[kApplyBatch], dpix[kApplyBatch];
         int state[kApplyBatch];   // 0: skip, 1: zero halo, 2: data
         // ---- issue all loads of the batch ----------------------------------------------------
 #pragma unroll
         for (int b = 0; b < kApplyBatch; ++b) {
-            const int pix = pix0 + (it0 + b) * p.rows;
             state[b] = 0;
             spix[b] = 0;
-            if (pix < npix) {
-                const int wp = pix % Wp, hp = pix / Wp;
-                int h = hp - a.pad, w = wp - a.pad;
+            dpix[b] = walk.pix;
+            if (walk.pix < npix) {
+                int h = walk.h - a.pad, w = walk.w - a.pad;
                 bool inside = true;
                 if (a.pad_mode == SSCG_PAD_REFLECT) {
                     h = reflect_idx(h, a.H);
@@ -113,8 +127,8 @@ __global__ void __launch_bounds__(256, SSCG_APPLY_MINB) in_apply_kernel(const __
                 }
                 state[b] = inside ? 2 : 1;
                 if (inside) {
-                    spix[b] = ((long long)n * a.H + h) * a.W + w;
-                    raw_load<ANYF32>(rv[b], a.raw, raw_f32, spix[b] * a.C + c0);
+                    spix[b] = h * a.W + w;
+                    raw_load<ANYF32>(rv[b], a.raw, raw_f32, (sbase + spix[b]) * a.C + c0);
                     if (has_res) {
                         const long long ro = (long long)n * a.res.sN + (long long)h * a.res.sH + (long long)w * a.res.sW + c0;
                         raw_load<false>(rr[b], a.res.ptr, false, ro);
@@ -122,13 +136,13 @@ __global__ void __launch_bounds__(256, SSCG_APPLY_MINB) in_apply_kernel(const __
                     }
                 }
             }
+            walk.advance(p.rows, Wp);
         }
         // ---- compute + store -------------------------------------------------------------------
 #pragma unroll
         for (int b = 0; b < kApplyBatch; ++b) {
             if (state[b] == 0) continue;
-            const int pix = pix0 + (it0 + b) * p.rows;
-            const long long doff = ((long long)n * npix + pix) * a.C + c0;
+            const long long doff = dbase + (long long)dpix[b] * a.C;
             float v[8];
             if (state[b] == 1) {
 #pragma unroll
@@ -149,7 +163,7 @@ __global__ void __launch_bounds__(256, SSCG_APPLY_MINB) in_apply_kernel(const __
                 for (int q = 0; q < 8; ++q) v[q] = v[q] > 0.f ? v[q] : v[q] * a.slope;
             }
             if (seed != 0) {
-                const uint32_t bits = drop_bits(seed, (unsigned long long)spix[b] * p.CH + chunk);
+                const uint32_t bits = drop_bits(seed, (unsigned long long)(sbase + spix[b]) * p.CH + chunk);
 #pragma unroll
                 for (int q = 0; q < 8; ++q) v[q] = ((bits >> q) & 1u) ? 2.f * v[q] : 0.f;
             }
@@ -220,37 +234,40 @@ __global__ void __launch_bounds__(256, SSCG_PREP_MINB) in_bwd_prep_kernel(const 
 #pragma unroll
     for (int q = 0; q < 8; ++q) acc1[q] = acc2[q] = 0.f;
     const int npix = a.H * a.W;
-    const int pix0 = blockIdx.x * p.rows * p.iters + row;   // per-sample pixel index: 32-bit div/mod below
     if (active) {
+        PixWalk walk(blockIdx.x * p.rows * p.iters + row, a.W);
+        const long long obase = (long long)n * npix * a.C + c0;                 // raw / dz / g_out (unpadded NHWC)
+        const long long ybase = (long long)n * a.dyp.sN + (long long)a.pad * a.dyp.sH + (long long)a.pad * a.dyp.sW + c0;
+        const long long kbase = (long long)n * a.skip.sN + c0;
         for (int it0 = 0; it0 < p.iters; it0 += kPrepBatch) {
             RawVec<ANYF32> rg[kPrepBatch], rs[kPrepBatch], rz[kPrepBatch];
+            int ph[kPrepBatch], pw[kPrepBatch], pp[kPrepBatch];
             // ---- loads (interior gradient position, skip gradient, raw activation) -------------
 #pragma unroll
             for (int b = 0; b < kPrepBatch; ++b) {
-                const int pix = pix0 + (it0 + b) * p.rows;
-                if (pix < npix) {
-                    const int w = pix % a.W, h = pix / a.W;
+                ph[b] = walk.h; pw[b] = walk.w; pp[b] = walk.pix;
+                if (walk.pix < npix) {
                     if (has_dyp)
                         raw_load<ANYF32>(rg[b], a.dyp.ptr, dyp_f32,
-                                         (long long)n * a.dyp.sN + (long long)(h + a.pad) * a.dyp.sH +
-                                             (long long)(w + a.pad) * a.dyp.sW + c0);
+                                         ybase + (long long)walk.h * a.dyp.sH + (long long)walk.w * a.dyp.sW);
                     if (has_skip)
                         raw_load<ANYF32>(rs[b], a.skip.ptr, skip_f32,
-                                         (long long)n * a.skip.sN + (long long)h * a.skip.sH + (long long)w * a.skip.sW + c0);
-                    if (need_raw) raw_load<ANYF32>(rz[b], a.raw, raw_f32, ((long long)n * npix + pix) * a.C + c0);
+                                         kbase + (long long)walk.h * a.skip.sH + (long long)walk.w * a.skip.sW);
+                    if (need_raw) raw_load<ANYF32>(rz[b], a.raw, raw_f32, obase + (long long)walk.pix * a.C);
                 }
+                walk.advance(p.rows, a.W);
             }
             // ---- compute + store ---------------------------------------------------------------
 #pragma unroll
             for (int b = 0; b < kPrepBatch; ++b) {
-                const int pix = pix0 + (it0 + b) * p.rows;
+                const int pix = pp[b];
                 if (pix >= npix) continue;
                 const long long spix = (long long)n * npix + pix;
-                const long long off = spix * a.C + c0;
+                const long long off = obase + (long long)pix * a.C;
                 float g[8], z[8];
                 if (has_dyp) {
                     raw_cvt<ANYF32>(rg[b], dyp_f32, g);
-                    const int w = pix % a.W, h = pix / a.W;
+                    const int w = pw[b], h = ph[b];
                     // halo positions that mirror onto this pixel exist only within `pad` of the border
                     if (fold && (h <= a.pad || w <= a.pad || h >= a.H - 1 - a.pad || w >= a.W - 1 - a.pad)) {
                         int hq[3], wq[3];
@@ -368,14 +385,15 @@ __global__ void __launch_bounds__(256, SSCG_BAPPLY_MINB) in_bwd_apply_kernel(con
         }
     }
     const int npix = a.H * a.W;
-    const int pix0 = blockIdx.x * p.rows * p.iters + row;   // per-sample pixel index: 32-bit div/mod below
+    const int pix0 = blockIdx.x * p.rows * p.iters + row;
+    const long long obase = (long long)n * npix * a.C + c0;
     for (int it0 = 0; it0 < p.iters; it0 += kBwdApplyBatch) {
         RawVec<ANYF32> rz[kBwdApplyBatch], rg[kBwdApplyBatch];
 #pragma unroll
         for (int b = 0; b < kBwdApplyBatch; ++b) {
             const int pix = pix0 + (it0 + b) * p.rows;
             if (pix < npix) {
-                const long long off = ((long long)n * npix + pix) * a.C + c0;
+                const long long off = obase + (long long)pix * a.C;
                 raw_load<ANYF32>(rz[b], a.raw, raw_f32, off);
                 raw_load<ANYF32>(rg[b], a.dz, dz_f32, off);
             }
@@ -384,7 +402,7 @@ __global__ void __launch_bounds__(256, SSCG_BAPPLY_MINB) in_bwd_apply_kernel(con
         for (int b = 0; b < kBwdApplyBatch; ++b) {
             const int pix = pix0 + (it0 + b) * p.rows;
             if (pix >= npix) continue;
-            const long long off = ((long long)n * npix + pix) * a.C + c0;
+            const long long off = obase + (long long)pix * a.C;
             float z[8], g[8];
             raw_cvt<ANYF32>(rz[b], raw_f32, z);
             raw_cvt<ANYF32>(rg[b], dz_f32, g);
