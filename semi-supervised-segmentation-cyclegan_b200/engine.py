@@ -160,6 +160,7 @@ class NetPlan:
         self.Cout = specs[-1].Cout
         self.ctx_pool: List[Ctx] = []
         self.drop_ctr = None      # optional device int64 counter mixed into dropout seeds (CUDA-graph replays)
+        self.overlap_wgrad = True  # run the weight-gradient GEMMs on a side stream (see backward)
         self._scratch_ready = False
         self._args_cache = {}
 
@@ -228,8 +229,14 @@ class NetPlan:
         self.gout = K.ActBuf(N, self.Hout, self.Wout, last.Co_pitch, 0, dev, fp32=sp)
         mx = max(self.geom[i][2] * self.geom[i][3] * self.weights[i].Co_pitch for i in range(len(self.specs)))
         self.dz = torch.zeros(N * mx + K.SLACK, dtype=torch.float32 if sp else torch.bfloat16, device=dev)
-        self.draw = torch.zeros(N * mx + K.SLACK, dtype=torch.bfloat16, device=dev)
-        self.draw_lo = torch.zeros_like(self.draw) if sp else None
+        # dRaw scratch, double-buffered by stage parity: the weight-gradient GEMM of stage i (side stream)
+        # reads buffer i%2 while the main stream already produces dRaw of stage i-1 in the other one
+        self.draws = [torch.zeros(N * mx + K.SLACK, dtype=torch.bfloat16, device=dev) for _ in range(2)]
+        self.draws_lo = [torch.zeros_like(d) if sp else None for d in self.draws]
+        self.draw, self.draw_lo = self.draws[0], self.draws_lo[0]     # (diagnostics: last written buffer)
+        self.wstream = torch.cuda.Stream(device=dev) if torch.device(dev).type == "cuda" else None
+        self.ev_draw = [torch.cuda.Event() for _ in range(2)] if self.wstream is not None else None
+        self.ev_wg = [torch.cuda.Event() for _ in range(2)] if self.wstream is not None else None
         self.tbuf = [None, None]   # residual-path total gradients (ping-pong), allocated lazily
         nb = sum(N * wt.Co_pitch * 2 for wt in self.weights)
         self.bstats = torch.zeros(nb, dtype=torch.float32, device=dev)
@@ -347,6 +354,7 @@ class NetPlan:
                 for wt in self.weights:
                     wt.dw.zero_()
         nst = len(self.specs)
+        wg_pending = [False, False]
         for i in range(nst - 1, -1, -1):
             s, wt = self.specs[i], self.weights[i]
             hin, win, ho, wo = self.geom[i]
@@ -358,15 +366,33 @@ class NetPlan:
             ba, use_apply, wa, da = args
             ba.drop_seed = (c.drop_seed * 1000003 + i + 1) if (s.dropout and c.drop_seed) else 0
             ba.drop_ctr = self.drop_ctr.data_ptr() if self.drop_ctr is not None else None
+            par = i & 1
+            overlap = self.overlap_wgrad and self.wstream is not None and debug_hook is None
+            main = torch.cuda.current_stream()
+            if overlap and wg_pending[par]:
+                main.wait_event(self.ev_wg[par])          # the wgrad that last read this dRaw buffer is done
+                wg_pending[par] = False
             K.run_bwd_prep(ba)
             if use_apply:
-                K.run_bwd_apply(ba, self.draw, self.draw_lo)
+                K.run_bwd_apply(ba, self.draws[par], self.draws_lo[par])
+            self.draw, self.draw_lo = self.draws[par], self.draws_lo[par]
             if wa is not None:
-                K.run_wgrad(wa)
+                if overlap:
+                    self.ev_draw[par].record(main)
+                    with torch.cuda.stream(self.wstream):
+                        self.wstream.wait_event(self.ev_draw[par])
+                        K.run_wgrad(wa)
+                        self.ev_wg[par].record(self.wstream)
+                    wg_pending[par] = True
+                else:
+                    K.run_wgrad(wa)
             if da is not None:
                 K.run_conv(da)
             if debug_hook is not None:
                 debug_hook(i, self)
+        for par in (0, 1):                                  # join the side stream before anyone reads dw
+            if wg_pending[par]:
+                torch.cuda.current_stream().wait_event(self.ev_wg[par])
         gx = None
         if need_dx:
             s0 = self.specs[0]
@@ -377,7 +403,7 @@ class NetPlan:
     def _draw_view(self, i, lo=False):
         wt = self.weights[i]
         _, _, ho, wo = self.geom[i]
-        t = self.draw_lo if lo else self.draw
+        t = self.draws_lo[i & 1] if lo else self.draws[i & 1]
         cp = wt.Co_pitch
         return L.make_view(t.data_ptr(), self.N, ho, wo, cp, ho * wo * cp, wo * cp, cp)
 
@@ -424,15 +450,15 @@ class NetPlan:
             src = c.out if s.final else (c.act[i + 1] if self._direct(s) else c.raw[i])
             ba.raw, ba.raw_fp32 = src.hi.data_ptr(), 1 if src.fp32 else 0
             ba.stats = None
-            ba.dz, ba.dz_fp32 = self.draw.data_ptr(), 0
-            ba.dz_lo = self.draw_lo.data_ptr() if self.draw_lo is not None else None
+            ba.dz, ba.dz_fp32 = self.draws[i & 1].data_ptr(), 0
+            ba.dz_lo = self.draws_lo[i & 1].data_ptr() if self.draws_lo[i & 1] is not None else None
             use_apply = False
         # ---- 2. wgrad ------------------------------------------------------------------------
         wa = None
         if need_dw:
             xview, xlo = self._x_view(s, wt, c.act[i])
             dview = self._draw_view(i)
-            dlo = self.draw_lo.data_ptr() if self.draw_lo is not None else None
+            dlo = self.draws_lo[i & 1].data_ptr() if self.draws_lo[i & 1] is not None else None
             if s.kind == "convT":
                 table = G.taps_convT_dgrad(s.k, s.k, s.stride, s.pad)
                 wa = K.wgrad_args(xview, xlo, dview, dlo, table, wt.wg_Kc, wt.wg_rows, wt.dw, wt.wg_taps * wt.wg_rows,
@@ -450,7 +476,7 @@ class NetPlan:
         if (i > 0 or need_dx) and wt.need_dgrad:
             gin = self.gact[i]
             dview = self._draw_view(i)
-            dlo = self.draw_lo.data_ptr() if self.draw_lo is not None else None
+            dlo = self.draws_lo[i & 1].data_ptr() if self.draws_lo[i & 1] is not None else None
             if s.kind == "convT":
                 table = G.taps_convT_dgrad(s.k, s.k, s.stride, s.pad)
                 Ho_d, Wo_d = hin, win
