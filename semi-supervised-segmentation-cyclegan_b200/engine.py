@@ -376,18 +376,20 @@ class NetPlan:
             if use_apply:
                 K.run_bwd_apply(ba, self.draws[par], self.draws_lo[par])
             self.draw, self.draw_lo = self.draws[par], self.draws_lo[par]
-            if wa is not None:
-                if overlap:
-                    self.ev_draw[par].record(main)
-                    with torch.cuda.stream(self.wstream):
-                        self.wstream.wait_event(self.ev_draw[par])
-                        K.run_wgrad(wa)
-                        self.ev_wg[par].record(self.wstream)
-                    wg_pending[par] = True
-                else:
-                    K.run_wgrad(wa)
+            if wa is not None and not overlap:
+                K.run_wgrad(wa)
             if da is not None:
                 K.run_conv(da)
+            if wa is not None and overlap:
+                # fork AFTER the dgrad: the side-stream wgrad then runs next to the memory-bound
+                # prep/apply kernels of stage i-1 (they co-reside with a GEMM CTA on an SM) instead of
+                # fighting the dgrad GEMM on the critical path for whole SMs
+                self.ev_draw[par].record(main)
+                with torch.cuda.stream(self.wstream):
+                    self.wstream.wait_event(self.ev_draw[par])
+                    K.run_wgrad(wa)
+                    self.ev_wg[par].record(self.wstream)
+                wg_pending[par] = True
             if debug_hook is not None:
                 debug_hook(i, self)
         for par in (0, 1):                                  # join the side stream before anyone reads dw
