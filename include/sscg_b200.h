@@ -92,7 +92,7 @@ typedef struct SscgConvArgs {
      * row, `taps` holds ONE entry per filter row (dh, leftmost dw, slab index of the leftmost tap); the
      * kernel loads a (TW + shift_kw - 1)-pixel row box once and feeds the shift_kw taps from shifted
      * shared-memory descriptors; tap j uses weight slab brow + j * shift_brow_step.  Needs TH = 1,
-     * TW = 128, BN in {16, 32}, split == 1. */
+     * TW = 128, BN in {16, 32, 64}, split == 1. */
     int32_t shift_kw;
     int32_t shift_brow_step;
     int32_t shift_base_mode;   /* 2 (use this): descriptor base_offset 0 — the 128B swizzle is a pure function of the

@@ -434,8 +434,8 @@ extern "C" int sscg_conv_igemm(const SscgConvArgs* a, void* stream_) {
     const int skw = a->shift_kw;
     if (skw != 0) {
         if (skw != 7 || a->split != 1 || a->stride != 1 || a->n_phases != 1 || a->TH != 1 || a->TW != 128 ||
-            (a->BN != 16 && a->BN != 32))
-            return set_error("conv_igemm: row-shift mode needs kw=7, bf16, stride 1, 1x128 tiles, BN 16/32");
+            (a->BN != 16 && a->BN != 32 && a->BN != 64))
+            return set_error("conv_igemm: row-shift mode needs kw=7, bf16, stride 1, 1x128 tiles, BN 16/32/64");
     }
     CUtensorMap tmA, tmAlo, tmB, tmBlo;
     const uint32_t boxA[4] = {64u, (uint32_t)(skw ? a->TW + skw - 1 : a->TW * a->stride),
@@ -475,6 +475,7 @@ extern "C" int sscg_conv_igemm(const SscgConvArgs* a, void* stream_) {
     if (d.total_tiles <= 0) return 0;
     if (skw == 7) {
         if (a->BN == 16) return launch_igemm<16, 1, 7>(tmA, tmAlo, tmB, tmBlo, d, stream, a->tag);
+        if (a->BN == 64) return launch_igemm<64, 1, 7>(tmA, tmAlo, tmB, tmBlo, d, stream, a->tag);
         return launch_igemm<32, 1, 7>(tmA, tmAlo, tmB, tmBlo, d, stream, a->tag);
     }
 

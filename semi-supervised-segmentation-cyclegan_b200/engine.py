@@ -160,7 +160,7 @@ class NetPlan:
         self.Cout = specs[-1].Cout
         self.ctx_pool: List[Ctx] = []
         self.drop_ctr = None      # optional device int64 counter mixed into dropout seeds (CUDA-graph replays)
-        self.overlap_wgrad = True  # run the weight-gradient GEMMs on a side stream (see backward)
+        self.overlap_wgrad = False  # side-stream wgrad: measured no gain on B200 (power-capped, GEMMs contend); kept as an option
         self._scratch_ready = False
         self._args_cache = {}
 
@@ -486,9 +486,9 @@ class NetPlan:
             else:
                 org = 0 if s.in_halo else -s.pad
                 table = G.taps_conv_dgrad(s.k, s.k, s.stride, org)
-                if self._rowshift_ok(s, wt.Ci_pad):     # narrow N only (stem dgrad); N = 64 is faster in regular mode
+                if self._rowshift_ok(s, min(wt.Ci_pad, 32)) and wt.Ci_pad <= 64:
                     table = G.taps_rowshift_dgrad(s.k, s.k, org)
-                    dkw = dict(shift_kw=s.k, shift_brow_step=-1, BN=min(wt.Ci_pad, 32))
+                    dkw = dict(shift_kw=s.k, shift_brow_step=-1, BN=wt.Ci_pad)   # 16 / 32 (stems), 64 (head)
                 if s.in_halo:
                     Ho_d, Wo_d, yoff = gin.Hp, gin.Wp, (0, 0)
                 else:

@@ -174,7 +174,7 @@ def case_conv_dgrad(N=2, H=16, W=16, Cin=64, Cout=128, k=3, stride=1, pad=1, shi
     kw = {}
     if shift:
         table = G.taps_rowshift_dgrad(k, k, -pad)
-        kw = dict(shift_kw=k, shift_brow_step=-1, shift_base_mode=2, BN=min(Ci_pad, 32))
+        kw = dict(shift_kw=k, shift_brow_step=-1, shift_base_mode=2, BN=min(Ci_pad, 64))
     a = K.conv_args(buf.view(interior=True), None, table, Kc, slab, None, k * k * Ci_pad, Ci_pad, dx.data_ptr(), True,
                     (H * W * Ci_pad, W * Ci_pad, Ci_pad), (0, 0), H, W, **kw)
     K.run_conv(a)
