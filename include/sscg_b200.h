@@ -220,6 +220,17 @@ int sscg_wprep(const SscgWprepArgs* a, void* stream);
 /* inverse mapping for gradients: fp32 slab [rows][Kc] -> += into the parameter-shaped gradient */
 int sscg_wgrad_unpack(const SscgWprepArgs* a, const float* slab, float* grad, float scale, void* stream);
 
+/* sscg_seg_head_fwd / _bwd: fused segmentation-head loss on NCHW fp32 logits — softmax over classes
+ * (nn.Softmax2d, model.py:273,401-402), mean cross-entropy against the label map
+ * (nn.CrossEntropyLoss, model.py:272,398,455) and first-max argmax (model.py:435,509) in one pass;
+ * backward = cross-entropy gradient + softmax Jacobian of an incoming probability gradient.
+ *   labels [N][H][W] int64 or NULL; probs / argmax / loss_sum (fp32 accumulator of sum -log p[label]) or NULL.
+ *   dloss: device scalar, gradient of the MEAN cross-entropy (or NULL); dprobs or NULL. */
+int sscg_seg_head_fwd(const float* logits, const int64_t* labels, int32_t N, int32_t C, int64_t HW, float* probs,
+                      int64_t* argmax, float* loss_sum, void* stream);
+int sscg_seg_head_bwd(const float* probs, const int64_t* labels, const float* dloss, const float* dprobs, int32_t N,
+                      int32_t C, int64_t HW, float* dlogits, void* stream);
+
 /* utility */
 int sscg_fill_zero(void* ptr, int64_t bytes, void* stream);
 const char* sscg_last_error(void);

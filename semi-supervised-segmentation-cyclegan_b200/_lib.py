@@ -112,6 +112,10 @@ _SIGNATURES = {
     "sscg_wprep": [C.POINTER(WprepArgs), C.c_void_p],
     "sscg_wgrad_unpack": [C.POINTER(WprepArgs), C.c_void_p, C.c_void_p, C.c_float, C.c_void_p],
     "sscg_fill_zero": [C.c_void_p, C.c_int64, C.c_void_p],
+    "sscg_seg_head_fwd": [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                          C.c_void_p],
+    "sscg_seg_head_bwd": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_void_p,
+                          C.c_void_p],
     "sscg_device_error": [],
     "sscg_version": [],
     "sscg_prof_begin": [C.c_uint32],

@@ -24,6 +24,7 @@ import torch
 import torch.nn as nn
 
 from .arch import define_Dis, define_Gen, set_grad
+from .losses import seg_head
 
 
 @dataclass
@@ -209,9 +210,15 @@ class SemiSupCycleGAN:
         fake_gt = self.Gsi(unl_img.float())                                              # :386
         lab_gt = self.Gsi(l_img)                                                         # :387
         assert fake_img.shape[2:] == l_img.shape[2:] and fake_gt.shape[2:] == l_img.shape[2:]   # interp == identity
-        lab_loss_CE = self.CE(lab_gt, l_gt.squeeze(1))                                   # :398
-        lab_gt = self.softmax(lab_gt)                                                    # :401
-        fake_gt = self.softmax(fake_gt)                                                  # :402
+        fused = l_img.is_cuda            # fused softmax + cross-entropy + argmax kernel (losses.py)
+        if fused:
+            lab_loss_CE, lab_gt, _ = seg_head(lab_gt, l_gt)                              # :398,401
+            _, fake_gt, fake_gt_arg = seg_head(fake_gt, None)                            # :402,435
+        else:
+            lab_loss_CE = self.CE(lab_gt, l_gt.squeeze(1))                               # :398
+            lab_gt = self.softmax(lab_gt)                                                # :401
+            fake_gt = self.softmax(fake_gt)                                              # :402
+            fake_gt_arg = fake_gt.data.max(1)[1]                                         # :435
         recon_img = self.Gis(fake_gt.float())                                            # :408
         if self.keep_dead_forward:
             with torch.no_grad():
@@ -224,11 +231,14 @@ class SemiSupCycleGAN:
                 resnet_recon_img = self.old_Gis(resnet_fake_gt.float())
                 self.old_Gis(resnet_lab_gt.float())                                      # resnet_recon_lab_img: unused
         fake_img_dis = self.Di(fake_img)                                                 # :431
-        fake_gt_disc = make_one_hot(fake_gt.data.max(1)[1].unsqueeze(1), C)              # :435-437
+        fake_gt_disc = make_one_hot(fake_gt_arg.unsqueeze(1), C)                         # :435-437
         fake_gt_dis = self.Ds(fake_gt_disc.float())                                      # :438
         img_gen_loss = self.MSE(fake_img_dis, self._ones(fake_img_dis))                  # :445
         gt_gen_loss = self.MSE(fake_gt_dis, self._ones(fake_gt_dis))                     # :446
-        gt_cycle_loss = self.CE(recon_gt, l_gt.squeeze(1))                               # :455
+        if fused:
+            gt_cycle_loss, _, _ = seg_head(recon_gt, l_gt)                               # :455
+        else:
+            gt_cycle_loss = self.CE(recon_gt, l_gt.squeeze(1))                           # :455
         lab_loss_MSE = self.L1(fake_img, l_img)                                          # :461
         fullsupervisedloss = w.lab_CE_weight * lab_loss_CE + w.lab_MSE_weight * lab_loss_MSE      # :464
         if head:

@@ -371,7 +371,35 @@ def case_pack_unpack(N=2, Cc=21, H=10, W=12, pad=3):
     return max(e1, e2, e3), 1.0, 1e-6
 
 
+def case_seg_head(N=2, Cc=21, H=24, W=40):
+    """Fused softmax + cross-entropy + argmax (forward and backward) vs torch."""
+    _setup()
+    from sscg_b200.losses import seg_head
+    logits = (torch.randn(N, Cc, H, W, device=DEV) * 3).requires_grad_(True)
+    labels = torch.randint(0, Cc, (N, 1, H, W), device=DEV)
+    wprobe = torch.randn(N, Cc, H, W, device=DEV)
+    loss, probs, am = seg_head(logits, labels)
+    (loss * 1.7 + (probs * wprobe).sum()).backward()
+    ref = logits.detach().clone().requires_grad_(True)
+    rl = F.cross_entropy(ref, labels.squeeze(1))
+    rp = F.softmax(ref, dim=1)
+    (rl * 1.7 + (rp * wprobe).sum()).backward()
+    e = max((probs - rp).abs().max().item(), abs(float(loss) - float(rl)),
+            (logits.grad - ref.grad).abs().max().item() / max(1e-6, ref.grad.abs().max().item()) * 1e-1)
+    exact = torch.equal(am, ref.detach().max(1)[1])
+    # probabilities-only use (no labels): gradient must be the pure softmax Jacobian
+    l2 = logits.detach().clone().requires_grad_(True)
+    _, p2, _ = seg_head(l2, None)
+    (p2 * wprobe).sum().backward()
+    r2 = logits.detach().clone().requires_grad_(True)
+    (F.softmax(r2, dim=1) * wprobe).sum().backward()
+    e = max(e, (l2.grad - r2.grad).abs().max().item())
+    return (e if exact else 1.0), 1.0, 2e-5
+
+
 CASES = {
+    "seg_head_loss_c21": lambda: case_seg_head(),
+    "seg_head_loss_c4": lambda: case_seg_head(N=3, Cc=4, H=17, W=9),
     # forward conv, regular mode
     "fwd_3x3_reflect_64": lambda: case_conv_fwd(),
     "fwd_3x3_reflect_256": lambda: case_conv_fwd(N=2, H=16, W=16, Cin=256, Cout=256),
