@@ -505,13 +505,14 @@ class NetPlan:
         return self.gact[idx]   # ("g", stage index): a dgrad output used directly as a total gradient
 
     # ------------------------------------------------------------------ gradients -> parameters
-    def param_grads(self, scale=1.0, into=None):
+    def param_grads(self, scale=1.0, into=None, weights=True):
         """Unpack the wgrad slabs into parameter-shaped fp32 gradients.  Returns a list aligned with
         [(weight, bias) for every stage]; biases cancelled by InstanceNorm get exact zeros."""
         out = []
         for i, (s, wt) in enumerate(zip(self.specs, self.weights)):
             gw = torch.zeros_like(s.weight, dtype=torch.float32) if into is None else into[i][0]
-            K.run_wgrad_unpack(wt.unpack_wg, wt.dw, gw, scale)
+            if weights:
+                K.run_wgrad_unpack(wt.unpack_wg, wt.dw, gw, scale)
             gb = None
             if s.bias is not None:
                 gb = torch.zeros_like(s.bias, dtype=torch.float32) if into is None else into[i][1]

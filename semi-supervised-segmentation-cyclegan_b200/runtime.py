@@ -44,6 +44,10 @@ class NetRunner:
         # direct_grad: backward adds weight gradients straight into the (pre-allocated) p.grad tensors and
         # returns None to autograd for them — saves one zero-fill and one add per parameter per backward
         self.direct_grad = False
+        # defer_unpack (with direct_grad): backward passes only ACCUMULATE the weight-gradient slabs; the
+        # owner calls flush_wgrad() once per optimizer step (one re-layout per stage instead of one per pass)
+        self.defer_unpack = False
+        self._dw_dirty = False
 
     def _setup(self, device, precision):
         if self.specs is not None and self.precision == precision and self.device == device:
@@ -80,6 +84,17 @@ class NetRunner:
                 for w in self.weights:
                     w.prepare()
             self._wkey = key
+
+    def flush_wgrad(self, scale=1.0):
+        """Fold the accumulated weight-gradient slabs into the parameters' .grad and clear the slabs."""
+        if not self._dw_dirty:
+            return
+        from . import kernels as K
+        for s, wt in zip(self.specs, self.weights):
+            if s.weight.grad is not None:
+                K.run_wgrad_unpack(wt.unpack_wg, wt.dw, s.weight.grad, scale)
+        self.dw_flat.zero_()
+        self._dw_dirty = False
 
     def plan(self, N, H, W) -> NetPlan:
         k = (N, H, W)
@@ -149,11 +164,14 @@ class _FusedNet(torch.autograd.Function):
             raise RuntimeError("fused network: backward called twice on the same graph (activations were released)")
         need_dx = ctx.needs_input_grad[2]
         need_dw = any(ctx.needs_input_grad[3:])
-        gx = plan.backward(c, gy.float(), need_dx=need_dx, need_dw=need_dw)
+        direct = need_dw and runner.direct_grad and all(p.grad is not None for p in runner.params() if p.requires_grad)
+        defer = direct and runner.defer_unpack
+        gx = plan.backward(c, gy.float(), need_dx=need_dx, need_dw=need_dw, accumulate_dw=defer)
         grads = []
-        if need_dw and runner.direct_grad and all(p.grad is not None for p in runner.params() if p.requires_grad):
+        if direct:
             into = [(s.weight.grad, s.bias.grad if s.bias is not None else None) for s in plan.specs]
-            plan.param_grads(into=into)
+            plan.param_grads(into=into, weights=not defer)
+            runner._dw_dirty = runner._dw_dirty or defer
             grads = [None] * (len(ctx.needs_input_grad) - 3)
         elif need_dw:
             pg = plan.param_grads()

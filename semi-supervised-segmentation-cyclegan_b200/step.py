@@ -169,6 +169,7 @@ class SemiSupCycleGAN:
         for n in (self.Gis, self.Gsi, self.Di, self.Ds):          # p.grad are persistent views: accumulate in place
             if getattr(n, "_runner", None) is not None:
                 n._runner.direct_grad = True
+                n._runner.defer_unpack = True
         P = GraphPool if graph_safe else DevicePool
         self.pool_recon, self.pool_fake_img, self.pool_fake_gt = P(), P(), P()           # model.py:350-352
         if graph_safe:
@@ -178,6 +179,13 @@ class SemiSupCycleGAN:
                 p.dec = self.pool_dec[i]
         self.Gsi.train()
         self.Gis.train()                                                                 # model.py:363-364
+
+    @staticmethod
+    def _flush_wgrad(nets):
+        for n in nets:
+            r = getattr(n, "_runner", None)
+            if r is not None and r.specs is not None:
+                r.flush_wgrad()
 
     def load_state(self, sds):
         for k, sd in sds.items():
@@ -252,6 +260,7 @@ class SemiSupCycleGAN:
                                 + gt_cycle_loss * w.lamda_gt)
         gen_loss = fullsupervisedloss + unsupervisedloss                                 # :468
         gen_loss.backward()                                                              # :472
+        self._flush_wgrad((self.Gis, self.Gsi))
         yield "g"
         self.g_optimizer.step()                                                          # :474
         # ---- discriminator phase (model.py:481-542) ----------------------------------------
@@ -285,6 +294,7 @@ class SemiSupCycleGAN:
             cycle_img_dis_loss = torch.zeros((), device=l_img.device)
             discriminator_loss = w.discriminator_weight * (img_dis_loss + gt_dis_loss)
         discriminator_loss.backward()                                                    # :539
+        self._flush_wgrad((self.Di, self.Ds))
         yield "d"
         self.d_optimizer.step()                                                          # :542
         self.last_losses = {"img_dis_loss": img_dis_loss.detach(), "gt_dis_loss": gt_dis_loss.detach(),
