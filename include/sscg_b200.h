@@ -201,6 +201,11 @@ typedef struct SscgBwdArgs {
 } SscgBwdArgs;
 int sscg_in_bwd_prep(const SscgBwdArgs* a, void* stream);
 int sscg_in_bwd_apply(const SscgBwdArgs* a, void* draw, void* draw_lo, void* stream);
+/* sscg_in_bwd_fused: prep + apply in ONE launch (normalised stages only).  All CTAs of a sample stay
+ * resident, meet at a per-sample arrival counter (sync_ctr: uint32[N], zeroed by the call) once the plane
+ * sums are complete, and sweep their pixels a second time out of L2 to write dRaw — no dZ round trip.
+ * Returns 3 (no error string) if N exceeds the number of co-resident CTAs: use prep + apply instead. */
+int sscg_in_bwd_fused(const SscgBwdArgs* a, void* draw, void* draw_lo, uint32_t* sync_ctr, void* stream);
 
 /* weight preparation: fp32 master weights -> bf16 GEMM operand slabs (see DESIGN.md "weight slabs") */
 typedef struct SscgWprepArgs {

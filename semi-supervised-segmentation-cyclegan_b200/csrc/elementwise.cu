@@ -357,17 +357,62 @@ extern "C" int sscg_in_apply(const SscgApplyArgs* a, void* stream) {
 extern "C" int sscg_in_bwd_prep(const SscgBwdArgs* a, void* stream) {
     if (a->C % 8 || a->C > 2048) return set_error("in_bwd_prep: C=%d must be a multiple of 8 (<= 2048)", a->C);
     BwdDev d;
-    d.a = *a; d.draw = nullptr; d.draw_lo = nullptr;
+    d.a = *a; d.draw = nullptr; d.draw_lo = nullptr; d.sync = nullptr;
     int gridx;
     vec_layout(a->C, (long long)a->H * a->W, d.CH, d.rows, d.iters, gridx);
     {
         LaunchScope ls_(8, static_cast<cudaStream_t>(stream));
         if (a->raw_fp32 || a->dyp_fp32 || a->skip_fp32 || a->g_fp32 || a->dz_fp32 || a->dz_lo)
-            in_bwd_prep_kernel<true><<<dim3(gridx, a->N), 256, 0, static_cast<cudaStream_t>(stream)>>>(d);
+            in_bwd_prep_kernel<true, false><<<dim3(gridx, a->N), 256, 0, static_cast<cudaStream_t>(stream)>>>(d);
         else
-            in_bwd_prep_kernel<false><<<dim3(gridx, a->N), 256, 0, static_cast<cudaStream_t>(stream)>>>(d);
+            in_bwd_prep_kernel<false, false><<<dim3(gridx, a->N), 256, 0, static_cast<cudaStream_t>(stream)>>>(d);
     }
     SSCG_CHECK_LAUNCH("in_bwd_prep");
+    return 0;
+}
+
+// One-launch InstanceNorm backward (see in_bwd_prep_kernel<., true>).  Returns 3 when the samples' CTAs
+// cannot all be resident (caller falls back to prep + apply).
+extern "C" int sscg_in_bwd_fused(const SscgBwdArgs* a, void* draw, void* draw_lo, uint32_t* sync_ctr, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (a->C % 8 || a->C > 2048) return set_error("in_bwd_fused: C=%d must be a multiple of 8 (<= 2048)", a->C);
+    if (!a->stats || !a->bstats || !sync_ctr) return set_error("in_bwd_fused: needs stats, bstats and sync counters");
+    const bool any = a->raw_fp32 || a->dyp_fp32 || a->skip_fp32 || a->g_fp32 || draw_lo;
+    static int occ[2] = {0, 0};
+    if (occ[any] == 0) {
+        int o = 0;
+        cudaError_t e = any ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, in_bwd_prep_kernel<true, true>, 256, 0)
+                            : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, in_bwd_prep_kernel<false, true>, 256, 0);
+        if (e != cudaSuccess || o < 1) o = 1;
+        occ[any] = o;
+    }
+    int sms = 148, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int capacity = sms * occ[any];
+    if (a->N > capacity) return 3;
+    BwdDev d;
+    d.a = *a; d.draw = draw; d.draw_lo = draw_lo; d.sync = sync_ctr;
+    d.CH = a->C / 8;
+    d.rows = 256 / d.CH; if (d.rows < 1) d.rows = 1;
+    const long long npix = (long long)a->H * a->W;
+    int cps = capacity / a->N;                                   // CTAs per sample, all co-resident
+    const long long min_pix = (long long)d.rows * 8;             // at least 8 pixels per thread
+    if ((long long)cps * min_pix > npix) cps = (int)((npix + min_pix - 1) / min_pix);
+    if (cps < 1) cps = 1;
+    long long per = (npix + cps - 1) / cps;                      // pixels per CTA
+    int iters = (int)((per + d.rows - 1) / d.rows);
+    iters = ((iters + kPrepBatch - 1) / kPrepBatch) * kPrepBatch;
+    d.iters = iters;
+    cps = (int)((npix + (long long)d.rows * iters - 1) / ((long long)d.rows * iters));
+    cudaError_t e = cudaMemsetAsync(sync_ctr, 0, sizeof(uint32_t) * a->N, stream);
+    if (e != cudaSuccess) return set_error("in_bwd_fused: memset: %s", cudaGetErrorString(e));
+    {
+        LaunchScope ls_(8, stream);
+        if (any) in_bwd_prep_kernel<true, true><<<dim3(cps, a->N), 256, 0, stream>>>(d);
+        else in_bwd_prep_kernel<false, true><<<dim3(cps, a->N), 256, 0, stream>>>(d);
+    }
+    SSCG_CHECK_LAUNCH("in_bwd_fused");
     return 0;
 }
 
@@ -375,7 +420,7 @@ extern "C" int sscg_in_bwd_apply(const SscgBwdArgs* a, void* draw, void* draw_lo
     if (a->C % 8 || a->C > 2048) return set_error("in_bwd_apply: C=%d must be a multiple of 8 (<= 2048)", a->C);
     if (!a->stats || !a->bstats) return set_error("in_bwd_apply: needs stats and bstats");
     BwdDev d;
-    d.a = *a; d.draw = draw; d.draw_lo = draw_lo;
+    d.a = *a; d.draw = draw; d.draw_lo = draw_lo; d.sync = nullptr;
     int gridx;
     vec_layout(a->C, (long long)a->H * a->W, d.CH, d.rows, d.iters, gridx);
     {

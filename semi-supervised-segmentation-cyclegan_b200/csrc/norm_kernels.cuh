@@ -190,6 +190,7 @@ struct BwdDev {
     SscgBwdArgs a;
     void* draw; void* draw_lo;
     int CH, rows, iters;
+    unsigned int* sync;      // fused mode: one arrival counter per sample (zeroed before the launch)
 };
 
 // positions of the padded gradient buffer that fold onto source index s (reflect) — at most 3
@@ -211,7 +212,13 @@ __device__ __forceinline__ int fold_positions(int s, int n, int pad, int mode, i
 #endif
 constexpr int kPrepBatch = SSCG_PREP_BATCH;
 
-template <bool ANYF32>
+// FUSED = false: first half of the two-kernel backward (writes dZ, accumulates the plane sums).
+// FUSED = true : whole InstanceNorm backward in one launch.  All CTAs of a sample are co-resident
+//   (grid.x <= resident capacity / N, checked by the host); after the sums are accumulated they meet at a
+//   per-sample arrival counter, then sweep their pixels a second time — the operands were just read by
+//   the same SM partition and largely come from L2 — and write dRaw directly.  Saves the dZ write + read
+//   and one launch per stage.
+template <bool ANYF32, bool FUSED>
 __global__ void __launch_bounds__(256, SSCG_PREP_MINB) in_bwd_prep_kernel(const __grid_constant__ BwdDev p) {
     const SscgBwdArgs& a = p.a;
     __shared__ float s_red[256 * 16];
@@ -234,7 +241,8 @@ __global__ void __launch_bounds__(256, SSCG_PREP_MINB) in_bwd_prep_kernel(const 
 #pragma unroll
     for (int q = 0; q < 8; ++q) acc1[q] = acc2[q] = 0.f;
     const int npix = a.H * a.W;
-    if (active) {
+    float m1[8], m2[8];      // plane means of dZ and dZ*Z (second sweep of the fused mode)
+    auto sweep = [&](const int pass) {
         PixWalk walk(blockIdx.x * p.rows * p.iters + row, a.W);
         const long long obase = (long long)n * npix * a.C + c0;                 // raw / dz / g_out (unpadded NHWC)
         const long long ybase = (long long)n * a.dyp.sN + (long long)a.pad * a.dyp.sH + (long long)a.pad * a.dyp.sW + c0;
@@ -295,7 +303,7 @@ __global__ void __launch_bounds__(256, SSCG_PREP_MINB) in_bwd_prep_kernel(const 
 #pragma unroll
                     for (int q = 0; q < 8; ++q) g[q] += t[q];
                 }
-                if (a.g_out != nullptr) {
+                if (a.g_out != nullptr && pass == 1) {
                     if (ANYF32 && a.g_fp32) store8_f32(a.g_out, off, g);
                     else store8_bf16(a.g_out, nullptr, off, g);
                 }
@@ -324,8 +332,16 @@ __global__ void __launch_bounds__(256, SSCG_PREP_MINB) in_bwd_prep_kernel(const 
 #pragma unroll
                     for (int q = 0; q < 8; ++q) z[q] = 0.f;
                 }
-                if (ANYF32 && a.dz_fp32) store8_f32(a.dz, off, g);
-                else store8_bf16(a.dz, ANYF32 ? a.dz_lo : nullptr, off, g);
+                if (FUSED && pass == 2) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) g[q] = rstd[q] * (g[q] - m1[q] - z[q] * m2[q]);
+                    store8_bf16(p.draw, ANYF32 ? p.draw_lo : nullptr, off, g);
+                    continue;
+                }
+                if (!FUSED) {
+                    if (ANYF32 && a.dz_fp32) store8_f32(a.dz, off, g);
+                    else store8_bf16(a.dz, ANYF32 ? a.dz_lo : nullptr, off, g);
+                }
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
                     acc1[q] += g[q];
@@ -333,7 +349,8 @@ __global__ void __launch_bounds__(256, SSCG_PREP_MINB) in_bwd_prep_kernel(const 
                 }
             }
         }
-    }
+    };
+    if (active) sweep(1);
     if (a.bstats == nullptr) return;
     // block reduction over the pixel rows that share a channel vector: one smem pass, one sync
     {
@@ -353,6 +370,35 @@ __global__ void __launch_bounds__(256, SSCG_PREP_MINB) in_bwd_prep_kernel(const 
         // e = 2*q + k  ->  bstats[(n*C + ch*8 + q)*2 + k]
         atomicAdd(a.bstats + ((long long)n * a.C + ch * 8) * 2 + e, s);
     }
+    if (!FUSED) return;
+    // ---- all CTAs of this sample have added their partial sums? ------------------------------------
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        atomicAdd(p.sync + n, 1u);
+        const uint64_t t0 = globaltimer_ns();
+        unsigned int spins = 0;
+        while (*reinterpret_cast<volatile unsigned int*>(p.sync + n) < gridDim.x) {
+            if ((++spins & 0xfff) == 0 && globaltimer_ns() - t0 > SSCG_WAIT_TIMEOUT_NS) {
+                atomicCAS(&g_sscg_dev_error, 0u, (9u << 16) | (blockIdx.x & 0xffff) | 0x80000000u);
+                __threadfence_system();
+                __trap();
+            }
+        }
+        __threadfence();
+    }
+    __syncthreads();
+    if (!active) return;
+    {
+        const float inv_cnt = 1.f / (float)npix;
+        const float* bp = a.bstats + ((long long)n * a.C + c0) * 2;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            m1[q] = __ldcg(bp + 2 * q) * inv_cnt;       // L2 (the sums were produced by atomics of other SMs)
+            m2[q] = __ldcg(bp + 2 * q + 1) * inv_cnt;
+        }
+    }
+    sweep(2);
 }
 
 #ifndef SSCG_BAPPLY_BATCH

@@ -160,6 +160,7 @@ class NetPlan:
         self.Cout = specs[-1].Cout
         self.ctx_pool: List[Ctx] = []
         self.drop_ctr = None      # optional device int64 counter mixed into dropout seeds (CUDA-graph replays)
+        self.fused_in_bwd = True   # one-launch InstanceNorm backward (sscg_in_bwd_fused)
         self.overlap_wgrad = False  # side-stream wgrad: measured no gain on B200 (power-capped, GEMMs contend); kept as an option
         self._scratch_ready = False
         self._args_cache = {}
@@ -237,6 +238,7 @@ class NetPlan:
         self.wstream = torch.cuda.Stream(device=dev) if torch.device(dev).type == "cuda" else None
         self.ev_draw = [torch.cuda.Event() for _ in range(2)] if self.wstream is not None else None
         self.ev_wg = [torch.cuda.Event() for _ in range(2)] if self.wstream is not None else None
+        self.sync_ctr = torch.zeros(max(N, 1), dtype=torch.int32, device=dev)
         self.tbuf = [None, None]   # residual-path total gradients (ping-pong), allocated lazily
         nb = sum(N * wt.Co_pitch * 2 for wt in self.weights)
         self.bstats = torch.zeros(nb, dtype=torch.float32, device=dev)
@@ -372,9 +374,11 @@ class NetPlan:
             if overlap and wg_pending[par]:
                 main.wait_event(self.ev_wg[par])          # the wgrad that last read this dRaw buffer is done
                 wg_pending[par] = False
-            K.run_bwd_prep(ba)
-            if use_apply:
-                K.run_bwd_apply(ba, self.draws[par], self.draws_lo[par])
+            if not (use_apply and self.fused_in_bwd and
+                    K.run_bwd_fused(ba, self.draws[par], self.draws_lo[par], self.sync_ctr)):
+                K.run_bwd_prep(ba)
+                if use_apply:
+                    K.run_bwd_apply(ba, self.draws[par], self.draws_lo[par])
             self.draw, self.draw_lo = self.draws[par], self.draws_lo[par]
             if wa is not None and not overlap:
                 K.run_wgrad(wa)

@@ -187,6 +187,15 @@ def run_bwd_apply(a, draw, draw_lo=None):
     L.check(L.lib().sscg_in_bwd_apply(C.byref(a), _ptr(draw), _ptr(draw_lo), _stream()), "sscg_in_bwd_apply")
 
 
+def run_bwd_fused(a, draw, draw_lo, sync_ctr):
+    """One-launch InstanceNorm backward; returns False when the caller must fall back to prep + apply."""
+    rc = L.lib().sscg_in_bwd_fused(C.byref(a), _ptr(draw), _ptr(draw_lo), _ptr(sync_ctr), _stream())
+    if rc == 3:
+        return False
+    L.check(rc, "sscg_in_bwd_fused")
+    return True
+
+
 def wprep_args(w, transposed, Co, Ci, KH, KW, mode, Cp, rows_pad, Kc, dst, dst_lo=None):
     a = L.WprepArgs()
     a.w, a.transposed = _ptr(w), 1 if transposed else 0

@@ -305,7 +305,7 @@ def case_apply_fwd(N=2, H=12, W=12, Cc=64, pad=1, reflect=True, act=L.ACT_RELU, 
     return _result(got, ref, 2e-2)
 
 
-def case_apply_bwd(N=2, H=12, W=12, Cc=64, pad=1, act=L.ACT_RELU, skip=True):
+def case_apply_bwd(N=2, H=12, W=12, Cc=64, pad=1, act=L.ACT_RELU, skip=True, fused=False):
     """Backward of pad(act(IN(raw))) (+ skip gradient): dRaw vs autograd."""
     _setup()
     raw = _bf(torch.randn(N, Cc, H, W, device=DEV) * 2 + 0.5)
@@ -339,9 +339,13 @@ def case_apply_bwd(N=2, H=12, W=12, Cc=64, pad=1, act=L.ACT_RELU, skip=True):
     bst = torch.zeros(N, Cc, 2, device=DEV)
     a.dz, a.dz_fp32, a.dz_lo = dz.data_ptr(), 1, None
     a.bstats = bst.data_ptr()
-    K.run_bwd_prep(a)
     draw = torch.zeros(N, H, W, Cc, device=DEV, dtype=torch.bfloat16)
-    K.run_bwd_apply(a, draw)
+    if fused:
+        sync = torch.zeros(N, dtype=torch.int32, device=DEV)
+        assert K.run_bwd_fused(a, draw, None, sync)
+    else:
+        K.run_bwd_prep(a)
+        K.run_bwd_apply(a, draw)
     torch.cuda.synchronize()
     return _result(draw.float().permute(0, 3, 1, 2), rr.grad, 2e-2)
 
@@ -461,5 +465,9 @@ CASES = {
     "apply_bwd_relu": lambda: case_apply_bwd(),
     "apply_bwd_nopad": lambda: case_apply_bwd(pad=0, act=L.ACT_LRELU, skip=False),
     "apply_bwd_pad3": lambda: case_apply_bwd(pad=3, act=L.ACT_RELU, skip=False),
+    "apply_bwd_fused_relu": lambda: case_apply_bwd(fused=True),
+    "apply_bwd_fused_big": lambda: case_apply_bwd(N=16, H=64, W=64, Cc=256, pad=1, fused=True),
+    "apply_bwd_fused_lrelu_nopad": lambda: case_apply_bwd(N=3, H=31, W=31, Cc=512, pad=0, act=L.ACT_LRELU, skip=False,
+                                                          fused=True),
     "pack_unpack": lambda: case_pack_unpack(),
 }

@@ -50,10 +50,13 @@ def run(N, H, W, C, pad, residual, skip, drop=12345, act=None, norm=True):
     draw = torch.zeros(N, H, W, C, device=dev, dtype=torch.bfloat16)
     t_bapply = timeit(lambda: K.run_bwd_apply(ba, draw))
     b_bapply = N * H * W * C * 2 * 3
+    sync = torch.zeros(N, dtype=torch.int32, device=dev)
+    t_fused = timeit(lambda: (bst.zero_(), K.run_bwd_fused(ba, draw, None, sync)))
     return {"shape": [N, H, W, C, pad, residual, skip, drop, act, norm],
             "apply_us": round(t_apply, 1), "apply_GBs": round(b_apply / t_apply / 1e3),
             "prep_us": round(t_prep, 1), "prep_GBs": round(b_prep / t_prep / 1e3),
-            "bapply_us": round(t_bapply, 1), "bapply_GBs": round(b_bapply / t_bapply / 1e3)}
+            "bapply_us": round(t_bapply, 1), "bapply_GBs": round(b_bapply / t_bapply / 1e3),
+            "fused_us(+zero)": round(t_fused, 1)}
 
 if __name__ == "__main__":
     print(os.environ.get("SSCG_LIB", "default"))
