@@ -160,7 +160,7 @@ class NetPlan:
         self.Cout = specs[-1].Cout
         self.ctx_pool: List[Ctx] = []
         self.drop_ctr = None      # optional device int64 counter mixed into dropout seeds (CUDA-graph replays)
-        self.fused_in_bwd = True   # one-launch InstanceNorm backward (sscg_in_bwd_fused)
+        self.fused_in_bwd = False  # one-launch InstanceNorm backward (sscg_in_bwd_fused): correct but slower than prep+apply on B200 (78 vs 64 us per residual stage), kept as an option
         self.overlap_wgrad = False  # side-stream wgrad: measured no gain on B200 (power-capped, GEMMs contend); kept as an option
         self._scratch_ready = False
         self._args_cache = {}
