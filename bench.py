@@ -306,6 +306,20 @@ def run_ours(args):
             model.feed_pool_decisions()
         model.train_step(*dev_batches[i % 3])
     prof, prof_complete = K.prof_end()
+    # ---- north-star sub-metric: one fused generator forward (Gsi, bs 16, 256x256, train mode) ----
+    gen_ms = None
+    with torch.no_grad():
+        x_img = dev_batches[0][0]
+        for _ in range(3):
+            model.Gsi(x_img)
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        g0.record()
+        for _ in range(10):
+            model.Gsi(x_img)
+        g1.record()
+        torch.cuda.synchronize()
+        gen_ms = g0.elapsed_time(g1) / 10
     dev_err = K.device_error()
     if rank != 0:
         if world > 1:
@@ -345,6 +359,11 @@ def run_ours(args):
                        "step_tflops_achieved": tf_step / (ms_step / 1e3),
                        "step_frac_of_sustained_peak": tf_step / (ms_step / 1e3) / peaks["bf16_tflops_sustained"]},
             "roofline": roof,
+            "generator_forward": {"what": "Gsi = resnet_9blocks_softmax forward incl. NCHW<->NHWC boundary, bs %d, 256x256, "
+                                          "eager launches" % args.batch,
+                                  "ms": gen_ms, "tflops": f_gen(H, W, 3, NCLS) * args.batch / 1e12 / (gen_ms / 1e3),
+                                  "frac_of_sustained_peak": f_gen(H, W, 3, NCLS) * args.batch / 1e12 / (gen_ms / 1e3)
+                                  / peaks["bf16_tflops_sustained"]},
             "kernel_time_ms_per_step": {k: v[0] / prof_steps for k, v in prof.items()},
             "kernel_launches_per_step": {k: v[1] / prof_steps for k, v in prof.items()},
             "kernel_profile_complete": prof_complete,

@@ -203,3 +203,22 @@ def test_state_dict_roundtrip_and_dropout_determinism():
     y = g(x.requires_grad_(True))
     y.sum().backward()
     assert all(p.grad is None for p in g.parameters()) and x.grad is not None
+
+
+@pytest.mark.parametrize("N,H,W", [(3, 72, 88), (1, 200, 200), (2, 36, 132)])
+def test_generator_odd_shapes_and_inference_path(N, H, W):
+    """Sizes that are not multiples of the 128-pixel tile (reference examples are 200x200; any multiple of
+    4 is legal for the two stride-2 stages), batch 1 and 3, eval + no_grad (testing.py:61 style call)."""
+    _setup()
+    from sscg_b200.arch import define_Gen
+    torch.manual_seed(2)
+    g = define_Gen(3, 21, 64, "resnet_9blocks_softmax", norm="instance", use_dropout=True, gpu_ids=[0])
+    g.precision = "bf16x3"
+    g.eval()
+    x = torch.rand(N, 3, H, W) * 2 - 1
+    with torch.no_grad():
+        y = g(x.cuda())
+    sd = {k: v.detach().cpu() for k, v in g.state_dict().items()}
+    yr = RA.resnet_generator(sd, x, 9, tanh=False, use_dropout=True)
+    assert y.shape == (N, 21, H, W)
+    assert _max_rel(y, yr) <= 1e-3
