@@ -110,6 +110,7 @@ _SIGNATURES = {
     "sscg_in_bwd_prep": [C.POINTER(BwdArgs), C.c_void_p],
     "sscg_in_bwd_apply": [C.POINTER(BwdArgs), C.c_void_p, C.c_void_p, C.c_void_p],
     "sscg_in_bwd_fused": [C.POINTER(BwdArgs), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
+    "sscg_set_stream_norm": [C.c_int32],
     "sscg_wprep": [C.POINTER(WprepArgs), C.c_void_p],
     "sscg_wgrad_unpack": [C.POINTER(WprepArgs), C.c_void_p, C.c_void_p, C.c_float, C.c_void_p],
     "sscg_fill_zero": [C.c_void_p, C.c_int64, C.c_void_p],

@@ -396,13 +396,31 @@ static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmAlo, const 
                                              Cfg::kSmemBytes);
         if (e != cudaSuccess) return set_error("conv_igemm: cudaFuncSetAttribute(smem=%d): %s", Cfg::kSmemBytes,
                                                cudaGetErrorString(e));
+        // without an explicit carve-out the driver sizes shared memory for ONE block of this kernel and the
+        // occupancy query answers 1 even when two blocks would fit the 228 KB
+        cudaFuncSetAttribute(conv_igemm_kernel<BN, SPLIT, SKW>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             cudaSharedmemCarveoutMaxShared);
         int o = 0;
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, conv_igemm_kernel<BN, SPLIT, SKW>, 192, Cfg::kSmemBytes);
+        const int o_api = o;
+        const int e_api = (int)e;
         if (e != cudaSuccess || o < 1) o = 1;
+        // The occupancy query answers 1 for these kernels (driver 580) even where two blocks fit by shared
+        // memory, registers and TMEM columns (ncu: launch__occupancy_limit_* = 2; a second resident CTA measurably
+        // overlaps one tile's epilogue with the other's main loop: +20..40 % on the narrow small-K layers).
+        // Size the grid by shared memory; registers (<= 168 x 192 threads) and TMEM are checked here.
+        {
+            const int by_smem = (int)(233472 / (Cfg::kSmemBytes + 1024));
+            const char* ov = getenv("SSCG_IGEMM_OCC");
+            if (by_smem > o && !(ov && atoi(ov) == 1)) o = by_smem > 2 ? 2 : by_smem;
+        }
         const int tmem_limit = 512 / Cfg::kTmemCols;     // resident CTAs must all fit their TMEM columns
         if (o > tmem_limit) o = tmem_limit;
         if (o > 4) o = 4;
         occ = o < 1 ? 1 : o;
+        if (getenv("SSCG_DEBUG"))
+            fprintf(stderr, "[sscg] conv_igemm<%d,%d,%d>: smem %d B, stages %d, tmem cols %d, occupancy %d (api %d, err %d)\n", BN, SPLIT,
+                    SKW, Cfg::kSmemBytes, Cfg::kStages, Cfg::kTmemCols, occ, o_api, e_api);
     }
     int grid = sm_count() * occ;
     if (grid > d.total_tiles) grid = d.total_tiles;

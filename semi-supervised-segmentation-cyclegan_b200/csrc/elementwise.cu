@@ -157,6 +157,7 @@ __global__ void unpack_kernel(const float* __restrict__ src, int N, int C, int H
 }
 
 #include "norm_kernels.cuh"
+#include "norm_stream.cuh"
 
 
 __global__ void unpack_fold_kernel(const void* __restrict__ src, int src_fp32, int N, int C, int H, int W, int Cp,
@@ -267,6 +268,68 @@ static void vec_layout(int C, long long npix, int& CH, int& rows, int& iters, in
     if (gridx < 1) gridx = 1;
 }
 
+// ---- bulk-pipelined variants (norm_stream.cuh): geometry + eligibility -----------------------------
+static int g_stream_norm = -1;     // -1: read SSCG_STREAM_NORM from the environment on first use
+static bool stream_enabled() {
+    if (g_stream_norm < 0) {
+        const char* e = getenv("SSCG_STREAM_NORM");
+        g_stream_norm = (e && e[0] >= '0' && e[0] <= '2') ? (e[0] - '0') : 1;
+    }
+    return g_stream_norm != 0;
+}
+// The pipelined first backward half matches the register-batched kernel's speed but does not beat it
+// (both issue-bound at ~240 instructions per 8-channel vector), so it is opt-in: value 2 (or
+// SSCG_STREAM_NORM=2) selects it too.
+static bool stream_prep_enabled() { return stream_enabled() && g_stream_norm >= 2; }
+static int ew_sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
+}
+// Unit = 1/d of an image row (d = smallest divisor of W that brings the unit under kStrUnitMax; a whole
+// row of up to 48 KB when W has no such divisor).  Returns false when the shape does not suit the ring.
+static bool stream_geom(int N, int H, int W, int C, int ntens, int threads, StreamGeom& g) {
+    if (!stream_enabled() || C % 8 || N < 1 || H < 1 || W < 1) return false;
+    const int CH = C / 8;
+    if (CH > 64 || threads % CH) return false;
+    const long long row = (long long)W * C * 2;
+    long long unit_max = kStrSmemBudget / (3 * ntens);       // at least three stages in the ring
+    if (unit_max > kStrUnitMax) unit_max = kStrUnitMax;
+    int d = 0;
+    for (int t = 1; t <= W; ++t)
+        if (W % t == 0 && row / t <= unit_max) { d = t; break; }
+    if (d == 0 || row / d < 4096) {
+        if (row > 48 * 1024 || row < 4096) return false;
+        d = 1;
+    }
+    g.upr = d;
+    g.seg_px = W / d;
+    g.ub = g.seg_px * C * 2;
+    g.ups = H * d;
+    g.total = N * g.ups;
+    g.ntens = ntens;
+    g.CH = CH;
+    int nst = kStrSmemBudget / (ntens * g.ub);
+    if (nst > kStrMaxStages) nst = kStrMaxStages;
+    if (nst < 2) return false;
+    g.nst = nst;
+    return true;
+}
+template <typename KernelT>
+static int stream_prepare(KernelT kernel, int& done) {
+    if (done) return 0;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStrSmemBudget + 512);
+    if (e != cudaSuccess) return set_error("norm stream: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    done = 1;
+    return 0;
+}
+static inline size_t stream_smem(const StreamGeom& g) { return (size_t)g.nst * g.ntens * g.ub + 512; }
+static inline int stream_grid(const StreamGeom& g) { return g.total < ew_sm_count() ? g.total : ew_sm_count(); }
+
 }  // namespace sscg
 
 using namespace sscg;
@@ -337,8 +400,33 @@ extern "C" int sscg_bias_grad(const float* bstats, int32_t N, int32_t C, int32_t
     return 0;
 }
 
+extern "C" int sscg_set_stream_norm(int32_t on) {
+    g_stream_norm = on < 0 ? 0 : (on > 2 ? 2 : on);
+    return 0;
+}
+
 extern "C" int sscg_in_apply(const SscgApplyArgs* a, void* stream) {
     if (a->C % 8 || a->C > 2048) return set_error("in_apply: C=%d must be a multiple of 8 (<= 2048)", a->C);
+    {
+        // bulk-pipelined fast path: all-bf16, halo (if any) written by reflection
+        ApplyStreamDev sd;
+        const bool plain = !(a->raw_fp32 || a->res_lo || a->dst_lo);
+        const bool halo_ok = a->pad == 0 || a->pad_mode == SSCG_PAD_REFLECT;
+        const bool res_ok = a->res.ptr == nullptr || a->res.sW == a->C;
+        if (plain && halo_ok && res_ok && a->pad < a->H && a->pad < a->W &&
+            stream_geom(a->N, a->H, a->W, a->C, a->res.ptr ? 2 : 1, kStrThreadsLight, sd.g)) {
+            static int prepared = 0;
+            if (int rc = stream_prepare(in_apply_stream_kernel<kStrThreadsLight>, prepared)) return rc;
+            sd.a = *a;
+            {
+                LaunchScope ls_(7, static_cast<cudaStream_t>(stream));
+                in_apply_stream_kernel<kStrThreadsLight><<<stream_grid(sd.g), kStrThreadsLight + 32, stream_smem(sd.g),
+                                         static_cast<cudaStream_t>(stream)>>>(sd);
+            }
+            SSCG_CHECK_LAUNCH("in_apply_stream");
+            return 0;
+        }
+    }
     ApplyDev d;
     d.a = *a;
     int gridx;
@@ -356,6 +444,26 @@ extern "C" int sscg_in_apply(const SscgApplyArgs* a, void* stream) {
 
 extern "C" int sscg_in_bwd_prep(const SscgBwdArgs* a, void* stream) {
     if (a->C % 8 || a->C > 2048) return set_error("in_bwd_prep: C=%d must be a multiple of 8 (<= 2048)", a->C);
+    {
+        BwdStreamDev sd;
+        const bool plain = !(a->raw_fp32 || a->dyp_fp32 || a->skip_fp32 || a->g_fp32 || a->dz_fp32 || a->dz_lo);
+        const bool need_raw = a->stats != nullptr || a->act != SSCG_ACT_NONE;
+        const bool views_ok = a->dyp.ptr != nullptr && a->dyp.sW == a->C && (a->skip.ptr == nullptr || a->skip.sW == a->C);
+        const bool pad_ok = a->pad == 0 || (a->pad < a->H && a->pad < a->W);
+        const int ntens = 1 + (a->skip.ptr ? 1 : 0) + (need_raw ? 1 : 0);
+        if (plain && views_ok && pad_ok && a->dz != nullptr && stream_prep_enabled() && stream_geom(a->N, a->H, a->W, a->C, ntens, kStrThreadsHeavy, sd.g)) {
+            static int prepared = 0;
+            if (int rc = stream_prepare(in_bwd_prep_stream_kernel<kStrThreadsHeavy>, prepared)) return rc;
+            sd.a = *a; sd.draw = nullptr;
+            {
+                LaunchScope ls_(8, static_cast<cudaStream_t>(stream));
+                in_bwd_prep_stream_kernel<kStrThreadsHeavy><<<stream_grid(sd.g), kStrThreadsHeavy + 32, stream_smem(sd.g),
+                                            static_cast<cudaStream_t>(stream)>>>(sd);
+            }
+            SSCG_CHECK_LAUNCH("in_bwd_prep_stream");
+            return 0;
+        }
+    }
     BwdDev d;
     d.a = *a; d.draw = nullptr; d.draw_lo = nullptr; d.sync = nullptr;
     int gridx;
@@ -419,6 +527,21 @@ extern "C" int sscg_in_bwd_fused(const SscgBwdArgs* a, void* draw, void* draw_lo
 extern "C" int sscg_in_bwd_apply(const SscgBwdArgs* a, void* draw, void* draw_lo, void* stream) {
     if (a->C % 8 || a->C > 2048) return set_error("in_bwd_apply: C=%d must be a multiple of 8 (<= 2048)", a->C);
     if (!a->stats || !a->bstats) return set_error("in_bwd_apply: needs stats and bstats");
+    {
+        BwdStreamDev sd;
+        if (!(a->raw_fp32 || a->dz_fp32 || draw_lo) && stream_geom(a->N, a->H, a->W, a->C, 2, kStrThreadsLight, sd.g)) {
+            static int prepared = 0;
+            if (int rc = stream_prepare(in_bwd_apply_stream_kernel<kStrThreadsLight>, prepared)) return rc;
+            sd.a = *a; sd.draw = draw;
+            {
+                LaunchScope ls_(8, static_cast<cudaStream_t>(stream));
+                in_bwd_apply_stream_kernel<kStrThreadsLight><<<stream_grid(sd.g), kStrThreadsLight + 32, stream_smem(sd.g),
+                                             static_cast<cudaStream_t>(stream)>>>(sd);
+            }
+            SSCG_CHECK_LAUNCH("in_bwd_apply_stream");
+            return 0;
+        }
+    }
     BwdDev d;
     d.a = *a; d.draw = draw; d.draw_lo = draw_lo; d.sync = nullptr;
     int gridx;

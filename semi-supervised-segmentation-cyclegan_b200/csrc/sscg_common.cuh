@@ -3,6 +3,7 @@
 #pragma once
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "../../include/sscg_b200.h"

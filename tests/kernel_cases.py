@@ -305,7 +305,7 @@ def case_apply_fwd(N=2, H=12, W=12, Cc=64, pad=1, reflect=True, act=L.ACT_RELU, 
     return _result(got, ref, 2e-2)
 
 
-def case_apply_bwd(N=2, H=12, W=12, Cc=64, pad=1, act=L.ACT_RELU, skip=True, fused=False):
+def case_apply_bwd(N=2, H=12, W=12, Cc=64, pad=1, act=L.ACT_RELU, skip=True, fused=False, dz_bf16=False):
     """Backward of pad(act(IN(raw))) (+ skip gradient): dRaw vs autograd."""
     _setup()
     raw = _bf(torch.randn(N, Cc, H, W, device=DEV) * 2 + 0.5)
@@ -335,11 +335,12 @@ def case_apply_bwd(N=2, H=12, W=12, Cc=64, pad=1, act=L.ACT_RELU, skip=True, fus
         skb = sk.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
         a.skip = L.make_view(skb.data_ptr(), N, H, W, Cc, H * W * Cc, W * Cc, Cc)
         a.skip_fp32 = 0
-    dz = torch.zeros(N, H, W, Cc, device=DEV)
+    dz = torch.zeros(N, H, W, Cc, device=DEV, dtype=torch.bfloat16 if dz_bf16 else torch.float32)
     bst = torch.zeros(N, Cc, 2, device=DEV)
-    a.dz, a.dz_fp32, a.dz_lo = dz.data_ptr(), 1, None
+    a.dz, a.dz_fp32, a.dz_lo = dz.data_ptr(), 0 if dz_bf16 else 1, None
     a.bstats = bst.data_ptr()
     draw = torch.zeros(N, H, W, Cc, device=DEV, dtype=torch.bfloat16)
+    L.lib().sscg_set_stream_norm(2 if dz_bf16 else 1)      # bf16 dZ cases exercise the pipelined first half too
     if fused:
         sync = torch.zeros(N, dtype=torch.int32, device=DEV)
         assert K.run_bwd_fused(a, draw, None, sync)
@@ -347,7 +348,83 @@ def case_apply_bwd(N=2, H=12, W=12, Cc=64, pad=1, act=L.ACT_RELU, skip=True, fus
         K.run_bwd_prep(a)
         K.run_bwd_apply(a, draw)
     torch.cuda.synchronize()
-    return _result(draw.float().permute(0, 3, 1, 2), rr.grad, 2e-2)
+    L.lib().sscg_set_stream_norm(1)
+    # bf16 dZ (the fast-mode layout, served by the bulk-pipelined kernels) adds one bf16 rounding of values up to ~10
+    return _result(draw.float().permute(0, 3, 1, 2), rr.grad, 5e-2 if dz_bf16 else 2e-2)
+
+
+def case_stream_ab(N=3, H=16, W=64, Cc=256, pad=1, act=L.ACT_RELU, skip=True, residual=True, drop=True):
+    """Bulk-pipelined InstanceNorm kernels (norm_stream.cuh) against the register-batched ones on the same
+    inputs, all-bf16 layouts, dropout on: forward output, dZ, folded total gradient and dRaw must be
+    bit-identical (same arithmetic); the plane sums may differ in summation order only."""
+    _setup()
+    lib = L.lib()
+    raw = (torch.randn(N, H, W, Cc, device=DEV) * 2 + 0.5).to(torch.bfloat16)
+    st = torch.stack([raw.float().sum(dim=(1, 2)), (raw.float() ** 2).sum(dim=(1, 2))], dim=-1).contiguous()
+    seed = 0x1234567 if drop else 0
+    worst = 0.0
+    # ---- forward ------------------------------------------------------------------------------
+    outs = []
+    resb = None
+    if residual:
+        resb = K.ActBuf(N, H, W, Cc, 1, DEV)
+        resb.hi.copy_(torch.randn_like(resb.hi.float()).to(torch.bfloat16))
+    for on in (0, 2):
+        lib.sscg_set_stream_norm(on)
+        dst = K.ActBuf(N, H, W, Cc, pad, DEV)
+        a = L.ApplyArgs()
+        a.raw, a.raw_fp32 = raw.data_ptr(), 0
+        a.stats, a.eps = st.data_ptr(), 1e-5
+        a.N, a.H, a.W, a.C = N, H, W, Cc
+        a.act, a.slope, a.drop_seed = act, 0.2, seed
+        if resb is not None:
+            a.res = resb.view(interior=True)
+        a.dst, a.dst_lo = dst.hi.data_ptr(), None
+        a.pad, a.pad_mode = pad, (L.PAD_REFLECT if pad else L.PAD_NONE)
+        K.run_apply(a)
+        torch.cuda.synchronize()
+        outs.append(dst.hi.clone())
+    worst = max(worst, float((outs[0].float() - outs[1].float()).abs().max()))
+    assert float(outs[1].float().abs().max()) > 0
+    # ---- backward -----------------------------------------------------------------------------
+    dypb = K.ActBuf(N, H, W, Cc, pad, DEV)
+    dypb.hi.copy_(torch.randn_like(dypb.hi.float()).to(torch.bfloat16))
+    skb = torch.randn(N, H, W, Cc, device=DEV).to(torch.bfloat16) if skip else None
+    res = []
+    for on in (0, 2):
+        lib.sscg_set_stream_norm(on)
+        a = L.BwdArgs()
+        a.raw, a.raw_fp32 = raw.data_ptr(), 0
+        a.stats, a.eps = st.data_ptr(), 1e-5
+        a.N, a.H, a.W, a.C = N, H, W, Cc
+        a.act, a.slope, a.drop_seed = act, 0.2, seed
+        a.dyp, a.dyp_fp32 = dypb.view(interior=False), 0
+        a.pad, a.pad_mode = pad, L.PAD_REFLECT if pad else L.PAD_NONE
+        if skip:
+            a.skip = L.make_view(skb.data_ptr(), N, H, W, Cc, H * W * Cc, W * Cc, Cc)
+        gout = torch.zeros(N, H, W, Cc, device=DEV, dtype=torch.bfloat16)
+        a.g_out, a.g_fp32 = gout.data_ptr(), 0
+        dz = torch.zeros(N, H, W, Cc, device=DEV, dtype=torch.bfloat16)
+        bst = torch.zeros(N, Cc, 2, device=DEV)
+        a.dz, a.dz_fp32, a.dz_lo = dz.data_ptr(), 0, None
+        a.bstats = bst.data_ptr()
+        K.run_bwd_prep(a)
+        torch.cuda.synchronize()
+        bst_own = bst.clone()
+        if on == 2:
+            bst.copy_(res[0][2])          # same plane sums for the second half, so dRaw can be compared bitwise
+        draw = torch.zeros(N, H, W, Cc, device=DEV, dtype=torch.bfloat16)
+        K.run_bwd_apply(a, draw)
+        torch.cuda.synchronize()
+        res.append((dz.clone(), gout.clone(), bst_own, draw.clone()))
+    lib.sscg_set_stream_norm(1)
+    for i in (0, 1, 3):
+        worst = max(worst, float((res[0][i].float() - res[1][i].float()).abs().max()))
+    assert float(res[1][3].float().abs().max()) > 0
+    # plane sums: same terms, different summation order
+    rel = float((res[1][2] - res[0][2]).abs().max() / res[0][2].abs().max().clamp_min(1e-6))
+    assert rel < 1e-4, rel
+    return worst, 1.0, 0.0
 
 
 def case_pack_unpack(N=2, Cc=21, H=10, W=12, pad=3):
@@ -469,5 +546,18 @@ CASES = {
     "apply_bwd_fused_big": lambda: case_apply_bwd(N=16, H=64, W=64, Cc=256, pad=1, fused=True),
     "apply_bwd_fused_lrelu_nopad": lambda: case_apply_bwd(N=3, H=31, W=31, Cc=512, pad=0, act=L.ACT_LRELU, skip=False,
                                                           fused=True),
+    # bulk-pipelined (cp.async.bulk ring) variants: eligible all-bf16 shapes
+    "apply_fwd_stream_res": lambda: case_apply_fwd(N=3, H=16, W=64, Cc=256, pad=1, act=L.ACT_NONE, residual=True),
+    "apply_fwd_stream_pad3": lambda: case_apply_fwd(N=2, H=20, W=128, Cc=64, pad=3),
+    "apply_fwd_stream_c512": lambda: case_apply_fwd(N=2, H=31, W=31, Cc=512, pad=0, act=L.ACT_LRELU),
+    "apply_bwd_stream_res": lambda: case_apply_bwd(N=3, H=16, W=64, Cc=256, pad=1, dz_bf16=True),
+    "apply_bwd_stream_pad3": lambda: case_apply_bwd(N=2, H=20, W=128, Cc=64, pad=3, skip=False, dz_bf16=True),
+    "apply_bwd_stream_c512": lambda: case_apply_bwd(N=2, H=31, W=31, Cc=512, pad=0, act=L.ACT_LRELU, skip=False,
+                                                    dz_bf16=True),
+    "apply_bwd_stream_many_samples": lambda: case_apply_bwd(N=40, H=8, W=64, Cc=128, pad=1, dz_bf16=True),
+    "stream_ab_res": lambda: case_stream_ab(),
+    "stream_ab_pad3": lambda: case_stream_ab(N=2, H=20, W=128, Cc=64, pad=3, skip=False, residual=False),
+    "stream_ab_nopad_lrelu": lambda: case_stream_ab(N=2, H=31, W=31, Cc=512, pad=0, act=L.ACT_LRELU, skip=False,
+                                                    residual=False, drop=False),
     "pack_unpack": lambda: case_pack_unpack(),
 }
