@@ -232,6 +232,18 @@ int sscg_wprep(const SscgWprepArgs* a, void* stream);
 /* inverse mapping for gradients: fp32 slab [rows][Kc] -> += into the parameter-shaped gradient */
 int sscg_wgrad_unpack(const SscgWprepArgs* a, const float* slab, float* grad, float scale, void* stream);
 
+/* Batched forms: ONE launch over a DEVICE table of descriptors (every slab of a network).  `start` is the
+ * running element offset of the entry (entries sorted by start; total = sum of ntaps * rows_pad * Kc);
+ * slab / grad are used by the gradient form only.  Same arithmetic as the per-slab calls above. */
+typedef struct SscgWbatchEntry {
+    SscgWprepArgs a;
+    const float* slab;
+    float* grad;
+    int64_t start;
+} SscgWbatchEntry;
+int sscg_wprep_batch(const SscgWbatchEntry* table_dev, int32_t count, int64_t total, void* stream);
+int sscg_wgrad_unpack_batch(const SscgWbatchEntry* table_dev, int32_t count, int64_t total, float scale, void* stream);
+
 /* sscg_seg_head_fwd / _bwd: fused segmentation-head loss on NCHW fp32 logits — softmax over classes
  * (nn.Softmax2d, model.py:273,401-402), mean cross-entropy against the label map
  * (nn.CrossEntropyLoss, model.py:272,398,455) and first-max argmax (model.py:435,509) in one pass;
@@ -242,6 +254,21 @@ int sscg_seg_head_fwd(const float* logits, const int64_t* labels, int32_t N, int
                       int64_t* argmax, float* loss_sum, void* stream);
 int sscg_seg_head_bwd(const float* probs, const int64_t* labels, const float* dloss, const float* dprobs, int32_t N,
                       int32_t C, int64_t HW, float* dlogits, void* stream);
+
+/* sscg_lsgan_fwd / _bwd: LSGAN patch loss against a constant target (nn.MSELoss vs all-ones / all-zeros,
+ * model.py:270,445-446,452,521-534): loss_sum += scale * sum (x - target)^2 (scale = 1/n gives the mean);
+ * dx = dloss * 2 (x - target) / n with dloss a device scalar (gradient of the MEAN). */
+int sscg_lsgan_fwd(const float* x, int64_t n, float target, float scale, float* loss_sum, void* stream);
+int sscg_lsgan_bwd(const float* x, int64_t n, float target, const float* dloss, float* dx, void* stream);
+/* sscg_l1_fwd / _bwd: nn.L1Loss (model.py:271,453,461): loss_sum += scale * sum |x - y|; dx = dloss * sign(x - y) / n. */
+int sscg_l1_fwd(const float* x, const float* y, int64_t n, float scale, float* loss_sum, void* stream);
+int sscg_l1_bwd(const float* x, const float* y, int64_t n, const float* dloss, float* dx, void* stream);
+/* sscg_adam_flat: one Adam update (torch.optim.Adam semantics, no weight decay / amsgrad; model.py:286-287,
+ * 474,542) over a flat fp32 bucket: p, g, m (exp_avg), v (exp_avg_sq) of n elements; lr and step are DEVICE
+ * scalars (step already incremented for this update), so the call is CUDA-graph capturable and the
+ * LambdaLR schedule (utils.py:434-441) only rewrites one float. */
+int sscg_adam_flat(float* p, const float* g, float* m, float* v, int64_t n, const float* lr, float beta1, float beta2,
+                   float eps, const float* step, void* stream);
 
 /* utility */
 int sscg_fill_zero(void* ptr, int64_t bytes, void* stream);

@@ -95,6 +95,10 @@ class WprepArgs(C.Structure):
     ]
 
 
+class WbatchEntry(C.Structure):
+    _fields_ = [("a", WprepArgs), ("slab", C.c_void_p), ("grad", C.c_void_p), ("start", C.c_int64)]
+
+
 _SIGNATURES = {
     "sscg_conv_igemm": [C.POINTER(ConvArgs), C.c_void_p],
     "sscg_conv_wgrad": [C.POINTER(WgradArgs), C.c_void_p],
@@ -113,11 +117,19 @@ _SIGNATURES = {
     "sscg_set_stream_norm": [C.c_int32],
     "sscg_wprep": [C.POINTER(WprepArgs), C.c_void_p],
     "sscg_wgrad_unpack": [C.POINTER(WprepArgs), C.c_void_p, C.c_void_p, C.c_float, C.c_void_p],
+    "sscg_wprep_batch": [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p],
+    "sscg_wgrad_unpack_batch": [C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_void_p],
     "sscg_fill_zero": [C.c_void_p, C.c_int64, C.c_void_p],
     "sscg_seg_head_fwd": [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                           C.c_void_p],
     "sscg_seg_head_bwd": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_void_p,
                           C.c_void_p],
+    "sscg_lsgan_fwd": [C.c_void_p, C.c_int64, C.c_float, C.c_float, C.c_void_p, C.c_void_p],
+    "sscg_lsgan_bwd": [C.c_void_p, C.c_int64, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p],
+    "sscg_l1_fwd": [C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_void_p, C.c_void_p],
+    "sscg_l1_bwd": [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p],
+    "sscg_adam_flat": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_float, C.c_float,
+                       C.c_float, C.c_void_p, C.c_void_p],
     "sscg_device_error": [],
     "sscg_version": [],
     "sscg_prof_begin": [C.c_uint32],

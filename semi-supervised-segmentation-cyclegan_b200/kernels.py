@@ -242,7 +242,7 @@ def bias_grad(bstats, N, Cc, Cp, grad, scale=1.0):
             "sscg_bias_grad")
 
 
-TAG_NAMES = {10: "seg_head_loss", 1: "res_conv_fwd", 2: "res_conv_dgrad", 3: "res_conv_wgrad", 4: "other_conv_fwd", 5: "other_conv_dgrad",
+TAG_NAMES = {10: "loss_kernels", 11: "adam", 1: "res_conv_fwd", 2: "res_conv_dgrad", 3: "res_conv_wgrad", 4: "other_conv_fwd", 5: "other_conv_dgrad",
              6: "other_conv_wgrad", 7: "in_apply", 8: "in_bwd", 9: "pack_unpack_wprep"}
 
 

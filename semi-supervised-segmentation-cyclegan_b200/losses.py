@@ -1,7 +1,9 @@
-"""Fused segmentation-head loss (softmax + cross-entropy + argmax) as one autograd node on top of
-libsscg_b200.so — replaces nn.CrossEntropyLoss / nn.Softmax2d / .max(1)[1] of the reference step
-(model.py:272-273,398,401-402,435,455,509).  CUDA tensors only; the step uses the stock torch ops on
-CPU tensors (the reference's own gpu_ids=[] path)."""
+"""Fused loss nodes on top of libsscg_b200.so, each one autograd.Function:
+  * seg_head  — softmax + cross-entropy + argmax: nn.CrossEntropyLoss / nn.Softmax2d / .max(1)[1] of the
+                reference step (model.py:272-273,398,401-402,435,455,509);
+  * lsgan_loss — nn.MSELoss against an all-ones / all-zeros target (model.py:270,445-446,452,521-534);
+  * l1_loss   — nn.L1Loss (model.py:271,453,461).
+CUDA tensors only; the step uses the stock torch ops on CPU tensors (the reference's own gpu_ids=[] path)."""
 import ctypes as C
 
 import torch
@@ -48,3 +50,54 @@ class _SegHead(torch.autograd.Function):
 def seg_head(logits, labels=None):
     """-> (mean cross-entropy (0 if labels is None), softmax probabilities, argmax label map)."""
     return _SegHead.apply(logits, labels, True)
+
+
+class _LsganLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, target):
+        x = x.contiguous()
+        assert x.dtype == torch.float32 and x.is_cuda
+        n = x.numel()
+        loss = torch.zeros((), dtype=torch.float32, device=x.device)
+        L.check(L.lib().sscg_lsgan_fwd(_ptr(x), n, float(target), 1.0 / n, _ptr(loss), _stream()), "sscg_lsgan_fwd")
+        ctx.save_for_backward(x)
+        ctx.target = float(target)
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        (x,) = ctx.saved_tensors
+        dx = torch.empty_like(x)
+        dl = dloss.contiguous().float()
+        L.check(L.lib().sscg_lsgan_bwd(_ptr(x), x.numel(), ctx.target, _ptr(dl), _ptr(dx), _stream()), "sscg_lsgan_bwd")
+        return dx, None
+
+
+def lsgan_loss(x, target):
+    """mean((x - target)^2) for a constant target (1.0 = "real", 0.0 = "fake")."""
+    return _LsganLoss.apply(x, target)
+
+
+class _L1Loss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, y):
+        x, y = x.contiguous(), y.contiguous()
+        assert x.dtype == torch.float32 and y.dtype == torch.float32 and x.shape == y.shape and x.is_cuda
+        n = x.numel()
+        loss = torch.zeros((), dtype=torch.float32, device=x.device)
+        L.check(L.lib().sscg_l1_fwd(_ptr(x), _ptr(y), n, 1.0 / n, _ptr(loss), _stream()), "sscg_l1_fwd")
+        ctx.save_for_backward(x, y)
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        x, y = ctx.saved_tensors
+        dx = torch.empty_like(x)
+        dl = dloss.contiguous().float()
+        L.check(L.lib().sscg_l1_bwd(_ptr(x), _ptr(y), x.numel(), _ptr(dl), _ptr(dx), _stream()), "sscg_l1_bwd")
+        return dx, None       # the second argument is data (model.py:453,461), never a graph tensor
+
+
+def l1_loss(x, y):
+    """mean(|x - y|); gradient flows to x only."""
+    return _L1Loss.apply(x, y.detach())

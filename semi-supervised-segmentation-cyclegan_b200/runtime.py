@@ -48,6 +48,8 @@ class NetRunner:
         # owner calls flush_wgrad() once per optimizer step (one re-layout per stage instead of one per pass)
         self.defer_unpack = False
         self._dw_dirty = False
+        self._prep_table = None       # (key, device table, count, total) of sscg_wprep_batch
+        self._unpack_table = None     # same for sscg_wgrad_unpack_batch
 
     def _setup(self, device, precision):
         if self.specs is not None and self.precision == precision and self.device == device:
@@ -68,6 +70,8 @@ class NetRunner:
             off += n
         self.plans = {}
         self._wkey = None
+        self._prep_table = None
+        self._unpack_table = None
 
     def params(self):
         ps = []
@@ -77,22 +81,67 @@ class NetRunner:
                 ps.append(s.bias)
         return ps
 
+    @staticmethod
+    def _slab_elems(a):
+        return (a.KH if a.mode == 1 else a.KH * a.KW) * a.rows_pad * a.Kc
+
+    def _upload_table(self, entries):
+        """entries: [(WprepArgs, slab ptr, grad ptr)] -> (device byte tensor holding SscgWbatchEntry[], count, total)"""
+        import ctypes as C
+        tab = (L.WbatchEntry * len(entries))()
+        start = 0
+        for i, (a, slab, grad) in enumerate(entries):
+            C.memmove(C.byref(tab[i].a), C.byref(a), C.sizeof(L.WprepArgs))
+            tab[i].slab, tab[i].grad, tab[i].start = slab, grad, start
+            start += self._slab_elems(a)
+        dev = torch.frombuffer(bytearray(bytes(tab)), dtype=torch.uint8).to(self.device)
+        return dev, len(entries), start
+
+    def _prepare_weights(self):
+        """All bf16 operand slabs of the network in ONE launch (sscg_wprep_batch over a device table)."""
+        from . import kernels as K
+        key = tuple(s.weight.data_ptr() for s in self.specs)
+        if self._prep_table is None or self._prep_table[0] != key:
+            entries = []
+            for w in self.weights:
+                w.prep_fwd.w = w.spec.weight.data_ptr()
+                entries.append((w.prep_fwd, None, None))
+                if w.need_dgrad:
+                    w.prep_dg.w = w.spec.weight.data_ptr()
+                    entries.append((w.prep_dg, None, None))
+            self._prep_table = (key,) + self._upload_table(entries)
+        _, dev, count, total = self._prep_table
+        L.check(L.lib().sscg_wprep_batch(dev.data_ptr(), count, total, K._stream()), "sscg_wprep_batch")
+        for w in self.weights:
+            if w.bias_pad is not None:
+                w.bias_pad[: w.spec.Cout].copy_(w.spec.bias.detach())
+
     def ensure_weights(self):
         key = tuple((p.data_ptr(), p._version) for p in self.params())
         if key != self._wkey:
             with torch.no_grad():
-                for w in self.weights:
-                    w.prepare()
+                self._prepare_weights()
             self._wkey = key
+
+    def invalidate_weights(self):
+        """Force the bf16 slabs to be re-derived at the next forward (for updates that bypass autograd's
+        version counters, e.g. optim.FlatAdam)."""
+        self._wkey = None
 
     def flush_wgrad(self, scale=1.0):
         """Fold the accumulated weight-gradient slabs into the parameters' .grad and clear the slabs."""
         if not self._dw_dirty:
             return
         from . import kernels as K
-        for s, wt in zip(self.specs, self.weights):
-            if s.weight.grad is not None:
-                K.run_wgrad_unpack(wt.unpack_wg, wt.dw, s.weight.grad, scale)
+        live = [(s, wt) for s, wt in zip(self.specs, self.weights) if s.weight.grad is not None]
+        key = tuple((wt.dw.data_ptr(), s.weight.grad.data_ptr()) for s, wt in live)
+        if live:
+            if self._unpack_table is None or self._unpack_table[0] != key:
+                entries = [(wt.unpack_wg, wt.dw.data_ptr(), s.weight.grad.data_ptr()) for s, wt in live]
+                self._unpack_table = (key,) + self._upload_table(entries)
+            _, dev, count, total = self._unpack_table
+            L.check(L.lib().sscg_wgrad_unpack_batch(dev.data_ptr(), count, total, float(scale), K._stream()),
+                    "sscg_wgrad_unpack_batch")
         self.dw_flat.zero_()
         self._dw_dirty = False
 

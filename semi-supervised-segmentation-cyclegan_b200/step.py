@@ -24,7 +24,7 @@ import torch
 import torch.nn as nn
 
 from .arch import define_Dis, define_Gen, set_grad
-from .losses import seg_head
+from .losses import l1_loss, lsgan_loss, seg_head
 
 
 @dataclass
@@ -154,18 +154,26 @@ class SemiSupCycleGAN:
         self.softmax = nn.Softmax2d()                                                     # model.py:273
         g_params = list(itertools.chain(self.Gis.parameters(), self.Gsi.parameters()))
         d_params = list(itertools.chain(self.Di.parameters(), self.Ds.parameters()))
-        kw = {"fused": True} if (fused_adam and torch.device(device).type == "cuda") else {}
+        cuda = torch.device(device).type == "cuda"
         self.graph_safe = graph_safe
         if graph_safe:
-            kw["capturable"] = True
             # device-side step counter: mixed into the dropout seeds so that replays draw fresh masks
             self.step_counter = torch.zeros(1, dtype=torch.int64, device=device)
             for n in self.nets.values():
                 if getattr(n, "_runner", None) is not None:
                     n._runner.drop_ctr = self.step_counter
-        self.g_optimizer = torch.optim.Adam(g_params, lr=lr, betas=(0.5, 0.999), **kw)       # model.py:286
-        self.d_optimizer = torch.optim.Adam(d_params, lr=lr, betas=(0.5, 0.999), **kw)       # model.py:287
         self.g_grads, self.d_grads = FlatGrads(g_params), FlatGrads(d_params)
+        if fused_adam and cuda:
+            # one flat-bucket Adam launch per optimizer (optim.FlatAdam, sscg_adam_flat); graph capturable
+            from .optim import FlatAdam
+            self.g_optimizer = FlatAdam(g_params, self.g_grads, lr=lr, betas=(0.5, 0.999),
+                                        post_step=[lambda: self._invalidate_weights((self.Gis, self.Gsi))])   # model.py:286
+            self.d_optimizer = FlatAdam(d_params, self.d_grads, lr=lr, betas=(0.5, 0.999),
+                                        post_step=[lambda: self._invalidate_weights((self.Di, self.Ds))])     # model.py:287
+        else:
+            kw = {"capturable": True} if graph_safe else {}
+            self.g_optimizer = torch.optim.Adam(g_params, lr=lr, betas=(0.5, 0.999), **kw)       # model.py:286
+            self.d_optimizer = torch.optim.Adam(d_params, lr=lr, betas=(0.5, 0.999), **kw)       # model.py:287
         for n in (self.Gis, self.Gsi, self.Di, self.Ds):          # p.grad are persistent views: accumulate in place
             if getattr(n, "_runner", None) is not None:
                 n._runner.direct_grad = True
@@ -179,6 +187,15 @@ class SemiSupCycleGAN:
                 p.dec = self.pool_dec[i]
         self.Gsi.train()
         self.Gis.train()                                                                 # model.py:363-364
+
+    @staticmethod
+    def _invalidate_weights(nets):
+        """The flat Adam kernel writes the parameters behind autograd's back: tell the runners to re-derive
+        their bf16 weight slabs at the next forward."""
+        for n in nets:
+            r = getattr(n, "_runner", None)
+            if r is not None:
+                r.invalidate_weights()
 
     @staticmethod
     def _flush_wgrad(nets):
@@ -241,21 +258,29 @@ class SemiSupCycleGAN:
         fake_img_dis = self.Di(fake_img)                                                 # :431
         fake_gt_disc = make_one_hot(fake_gt_arg.unsqueeze(1), C)                         # :435-437
         fake_gt_dis = self.Ds(fake_gt_disc.float())                                      # :438
-        img_gen_loss = self.MSE(fake_img_dis, self._ones(fake_img_dis))                  # :445
-        gt_gen_loss = self.MSE(fake_gt_dis, self._ones(fake_gt_dis))                     # :446
+        if fused:     # fused LSGAN / L1 kernels (losses.py): scalar target, one pass forward, one backward
+            MSE1 = lambda t: lsgan_loss(t, 1.0)
+            MSE0 = lambda t: lsgan_loss(t, 0.0)
+            L1 = l1_loss
+        else:
+            MSE1 = lambda t: self.MSE(t, torch.ones_like(t))
+            MSE0 = lambda t: self.MSE(t, torch.zeros_like(t))
+            L1 = self.L1
+        img_gen_loss = MSE1(fake_img_dis)                                                # :445
+        gt_gen_loss = MSE1(fake_gt_dis)                                                  # :446
         if fused:
             gt_cycle_loss, _, _ = seg_head(recon_gt, l_gt)                               # :455
         else:
             gt_cycle_loss = self.CE(recon_gt, l_gt.squeeze(1))                           # :455
-        lab_loss_MSE = self.L1(fake_img, l_img)                                          # :461
+        lab_loss_MSE = L1(fake_img, l_img)                                               # :461
         fullsupervisedloss = w.lab_CE_weight * lab_loss_CE + w.lab_MSE_weight * lab_loss_MSE      # :464
         if head:
             resnet_fake_img_dis = self.old_Di(recon_img)                                 # :432
-            img_cycle_loss = self.MSE(resnet_fake_img_dis, self._ones(resnet_fake_img_dis))       # :452
+            img_cycle_loss = MSE1(resnet_fake_img_dis)                                   # :452
             unsupervisedloss = (w.adversarial_weight * (img_gen_loss + gt_gen_loss) + img_cycle_loss
                                 + gt_cycle_loss * w.lamda_gt)                            # :466
         else:
-            img_cycle_loss = self.L1(recon_img, unl_img)                                 # :453
+            img_cycle_loss = L1(recon_img, unl_img)                                      # :453
             unsupervisedloss = (w.adversarial_weight * (img_gen_loss + gt_gen_loss) + img_cycle_loss * w.lamda_img
                                 + gt_cycle_loss * w.lamda_gt)
         gen_loss = fullsupervisedloss + unsupervisedloss                                 # :468
@@ -280,15 +305,12 @@ class SemiSupCycleGAN:
         real_gt_dis = self.Ds(make_one_hot(l_gt, C).float())                             # :506-507
         fake_gt_disc = make_one_hot(fake_gt.data.max(1)[1].unsqueeze(1), C)              # :509-511
         fake_gt_dis = self.Ds(fake_gt_disc.float())                                      # :512
-        img_dis_loss = (self.MSE(unl_img_dis, torch.ones_like(unl_img_dis))
-                        + self.MSE(fake_img_dis, torch.zeros_like(fake_img_dis))) * 0.5  # :521-522,531
-        gt_dis_loss = (self.MSE(real_gt_dis, torch.ones_like(real_gt_dis))
-                       + self.MSE(fake_gt_dis, torch.zeros_like(fake_gt_dis))) * 0.5     # :523-524,532
+        img_dis_loss = (MSE1(unl_img_dis) + MSE0(fake_img_dis)) * 0.5                    # :521-522,531
+        gt_dis_loss = (MSE1(real_gt_dis) + MSE0(fake_gt_dis)) * 0.5                      # :523-524,532
         if head:
             resnet_recon_img_dis = self.old_Di(resnet_recon_img)                         # :501
             resnet_fake_img_dis = self.old_Di(recon_img)                                 # :502
-            cycle_img_dis_loss = (self.MSE(resnet_recon_img_dis, torch.ones_like(resnet_recon_img_dis))
-                                  + self.MSE(resnet_fake_img_dis, torch.zeros_like(resnet_fake_img_dis)))  # :527-534
+            cycle_img_dis_loss = MSE1(resnet_recon_img_dis) + MSE0(resnet_fake_img_dis)   # :527-534
             discriminator_loss = w.discriminator_weight * (img_dis_loss + gt_dis_loss) + cycle_img_dis_loss  # :538
         else:
             cycle_img_dis_loss = torch.zeros((), device=l_img.device)
@@ -383,6 +405,9 @@ class GraphedStep:
         self.l_gt.copy_(l_gt, non_blocking=True)
         self.unl_img.copy_(unl_img, non_blocking=True)
         self.m.feed_pool_decisions()
+        for opt in (self.m.g_optimizer, self.m.d_optimizer):      # LambdaLR rewrites param_groups: push to the device scalar
+            if hasattr(opt, "sync_lr"):
+                opt.sync_lr()
         for i, g in enumerate(self.graphs):
             g.replay()
             if i < len(self.points):

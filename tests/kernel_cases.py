@@ -478,6 +478,74 @@ def case_seg_head(N=2, Cc=21, H=24, W=40):
     return (e if exact else 1.0), 1.0, 2e-5
 
 
+def case_lsgan(shape=(16, 1, 30, 30), target=1.0):
+    """Fused LSGAN loss (forward mean + gradient) vs nn.MSELoss against a constant target."""
+    _setup()
+    from sscg_b200.losses import lsgan_loss
+    x = torch.randn(*shape, device=DEV)
+    xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    la = lsgan_loss(xa, target) * 0.37
+    la.backward()
+    lb = F.mse_loss(xb, torch.full_like(xb, target)) * 0.37
+    lb.backward()
+    torch.cuda.synchronize()
+    e = max(abs(float(la) - float(lb)), float((xa.grad - xb.grad).abs().max()) * x.numel())
+    return e, float(lb), 1e-5 * max(1.0, abs(float(lb)))
+
+
+def case_l1(shape=(2, 3, 33, 35)):
+    """Fused L1 loss vs nn.L1Loss (odd element count: exercises the scalar tail)."""
+    _setup()
+    from sscg_b200.losses import l1_loss
+    x, y = torch.randn(*shape, device=DEV), torch.randn(*shape, device=DEV)
+    x.view(-1)[:7] = y.view(-1)[:7]                        # exact ties: sign(0) = 0
+    xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    la = l1_loss(xa, y) * 1.7
+    la.backward()
+    lb = F.l1_loss(xb, y) * 1.7
+    lb.backward()
+    torch.cuda.synchronize()
+    e = max(abs(float(la) - float(lb)), float((xa.grad - xb.grad).abs().max()) * x.numel())
+    return e, float(lb), 1e-5
+
+
+def case_flat_adam(steps=6):
+    """optim.FlatAdam (one sscg_adam_flat launch over a flat bucket) vs torch.optim.Adam(betas=(0.5, 0.999)) on the
+    same gradients, through a LambdaLR decay and a state_dict round trip."""
+    _setup()
+    from sscg_b200.optim import FlatAdam
+    from sscg_b200.step import FlatGrads
+    shapes = [(7, 3, 3, 3), (7,), (5, 7, 1, 1), (1,), (33, 2)]
+    pa = [torch.nn.Parameter(torch.randn(*sh, device=DEV)) for sh in shapes]
+    pb = [torch.nn.Parameter(p.detach().clone()) for p in pa]
+    fg = FlatGrads(pa)
+    oa = FlatAdam(pa, fg, lr=2e-4, betas=(0.5, 0.999))
+    ob = torch.optim.Adam(pb, lr=2e-4, betas=(0.5, 0.999))
+    lam = lambda ep: 1.0 - max(0, ep - 2) / 6.0               # utils.py:434-441 with epochs=8, decay_epoch=2
+    sa = torch.optim.lr_scheduler.LambdaLR(oa, lr_lambda=lam)
+    sb = torch.optim.lr_scheduler.LambdaLR(ob, lr_lambda=lam)
+    worst = 0.0
+    for it in range(steps):
+        for a, b in zip(pa, pb):
+            g = torch.randn_like(b) * (0.1 + it)
+            a.grad.copy_(g)
+            b.grad = g.clone()
+        oa.step()
+        ob.step()
+        sa.step()
+        sb.step()
+        if it == 2:                                            # checkpoint round trip (model.py:641-655)
+            sd = oa.state_dict()
+            oa.load_state_dict(sd)
+        for a, b in zip(pa, pb):
+            worst = max(worst, float((a.detach() - b.detach()).abs().max()))
+    torch.cuda.synchronize()
+    ma = oa.state[pa[0]]["exp_avg"]
+    mb = ob.state[pb[0]]["exp_avg"]
+    worst = max(worst, float((ma - mb).abs().max()))
+    return worst, 1.0, 2e-6
+
+
 CASES = {
     "seg_head_loss_c21": lambda: case_seg_head(),
     "seg_head_loss_c4": lambda: case_seg_head(N=3, Cc=4, H=17, W=9),
@@ -559,5 +627,10 @@ CASES = {
     "stream_ab_pad3": lambda: case_stream_ab(N=2, H=20, W=128, Cc=64, pad=3, skip=False, residual=False),
     "stream_ab_nopad_lrelu": lambda: case_stream_ab(N=2, H=31, W=31, Cc=512, pad=0, act=L.ACT_LRELU, skip=False,
                                                     residual=False, drop=False),
+    "lsgan_real": lambda: case_lsgan(),
+    "lsgan_fake_odd": lambda: case_lsgan(shape=(3, 1, 7, 5), target=0.0),
+    "l1_loss": lambda: case_l1(),
+    "l1_loss_big": lambda: case_l1(shape=(4, 3, 64, 64)),
+    "flat_adam": lambda: case_flat_adam(),
     "pack_unpack": lambda: case_pack_unpack(),
 }
