@@ -38,6 +38,8 @@ struct ConvDev {
     int tiles_x;    // tiles_h * tiles_w * N
     int n_ntiles;   // Co_pad / BN
     int total_tiles;
+    int tail_from;  // >= 0: schedule entries from this index on are HALF-N tiles (two per output tile): the last,
+                    // partial wave of a persistent grid then costs ~0.6 instead of 1.0 tile times (BN = 256 only)
     void* y;
     int y_fp32;
     long long y_sN, y_sH, y_sW;
@@ -74,11 +76,18 @@ struct IgemmCfg {
 
 struct TileInfo {
     int n, i0, j0, n0, ph, pw, Hph, Wph, tap0, nkb;
+    int bn;         // columns of this tile: BN, or BN / 2 for a tail tile
     bool valid;
 };
 
 __device__ __forceinline__ TileInfo decode_tile(const ConvDev& p, int tile, int BN) {
     TileInfo t;
+    int half = -1;
+    if (p.tail_from >= 0 && tile >= p.tail_from) {
+        const int h = tile - p.tail_from;
+        tile = p.tail_from + (h >> 1);
+        half = h & 1;
+    }
     int x = tile % p.tiles_x;
     int rest = tile / p.tiles_x;
     const int y = rest % p.n_ntiles;
@@ -94,6 +103,11 @@ __device__ __forceinline__ TileInfo decode_tile(const ConvDev& p, int tile, int 
     t.i0 = ti * p.TH;
     t.j0 = tj * p.TW;
     t.n0 = y * BN;
+    t.bn = BN;
+    if (half >= 0) {
+        t.bn = BN >> 1;
+        t.n0 += half * t.bn;
+    }
     t.tap0 = p.phase_start[z];
     t.nkb = (p.phase_start[z + 1] - t.tap0) * p.kcb;
     t.valid = (t.i0 < t.Hph) && (t.j0 < t.Wph);
@@ -159,7 +173,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     const SscgTap tap = p.taps[t.tap0 + tp];
                     mbar_wait(smem_u32(&empty_bar[stage]), par ^ 1, 1);
                     const uint32_t fb = smem_u32(&full_bar[stage]);
-                    mbar_arrive_expect_tx(fb, Cfg::kTxBytes);
+                    const bool half_tile = (SPLIT == 1 && SKW == 0) && t.bn != BN;
+                    mbar_arrive_expect_tx(fb, half_tile ? Cfg::kTxBytes - Cfg::kBBytes / 2 : Cfg::kTxBytes);
                     uint8_t* st = smem + stage * Cfg::kStageBytes;
                     const int cw = t.j0 * p.stride + tap.dw + p.org_w;
                     const int ch = t.i0 * p.stride + tap.dh + p.org_h;
@@ -171,7 +186,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                             tma_load_2d(smem_u32(st + Cfg::kAStage + j * Cfg::kBBytes), &tmB, fb, cb * 64,
                                         (tap.brow + j * p.shift_brow_step) * p.Co_pad + t.n0);
                     } else {
-                        tma_load_2d(smem_u32(st + kPlanes * kABytes), &tmB, fb, cb * 64, brow);
+                        // half tiles read their 128 weight rows through the half-height box (passed in the tmBlo slot)
+                        tma_load_2d(smem_u32(st + kPlanes * kABytes), half_tile ? &tmBlo : &tmB, fb, cb * 64, brow);
                     }
                     if (SPLIT == 3) {
                         tma_load_4d(smem_u32(st + kABytes), &tmAlo, fb, cb * 64, cw, ch, t.n);
@@ -185,7 +201,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     } else if (warp == 1) {
         // ================================ MMA issuer ============================================
         if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_bf16(kTileM, BN < 16 ? 16 : BN, 0, 0);
+            constexpr uint32_t idesc_full = make_idesc_bf16(kTileM, BN < 16 ? 16 : BN, 0, 0);
+            constexpr uint32_t idesc_half = make_idesc_bf16(kTileM, BN < 32 ? 16 : BN / 2, 0, 0);
             int stage = 0; uint32_t par = 0;
             uint32_t it = 0;
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -196,6 +213,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 mbar_wait(smem_u32(&tmem_empty_bar[acc]), acc_par ^ 1, 7);   // epilogue drained this buffer
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * Cfg::kAccCols;
+                const uint32_t idesc = (t.bn != BN) ? idesc_half : idesc_full;
                 uint32_t accum = 0;
                 for (int kb = 0; kb < t.nkb; ++kb) {
                     mbar_wait(smem_u32(&full_bar[stage]), par, 2);
@@ -261,8 +279,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             mbar_wait(smem_u32(&tmem_full_bar[acc]), acc_par, 3);
             tc_fence_after();
             const uint32_t t_acc = tmem_base + acc * Cfg::kAccCols + (static_cast<uint32_t>(quad * 32) << 16);
+            const int nch = (t.bn != BN) ? kChunks / 2 : kChunks;
 #pragma unroll 1
-            for (int c = 0; c < kChunks; ++c) {
+            for (int c = 0; c < nch; ++c) {
                 uint32_t r[32];
                 if (BN >= 32) {
                     tmem_ld_32x32(t_acc + c * 32, r);
@@ -272,7 +291,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     for (int q = 16; q < 32; ++q) r[q] = 0;
                 }
                 tmem_ld_wait();
-                if (c == kChunks - 1) {            // accumulator fully read: hand the TMEM buffer back
+                if (c == nch - 1) {                // accumulator fully read: hand the TMEM buffer back
                     tc_fence_before();
                     mbar_arrive(smem_u32(&tmem_empty_bar[acc]));
                 }
@@ -341,7 +360,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         }
                     }
                     const int col = c * 32 + lane;
-                    if (col < BN) {
+                    if (col < t.bn) {
                         s_stat[(quad * BN + col) * 2 + 0] = s1[0];
                         s_stat[(quad * BN + col) * 2 + 1] = s2[0];
                     }
@@ -350,7 +369,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             if (p.stats != nullptr) {
                 named_bar_sync(1, 128);               // all four quadrants wrote their partials
                 const int e = threadIdx.x - 64;       // 0..127
-                for (int col = e; col < BN; col += 128) {
+                for (int col = e; col < t.bn; col += 128) {
                     float a = 0.f, b = 0.f;
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
@@ -487,6 +506,16 @@ extern "C" int sscg_conv_igemm(const SscgConvArgs* a, void* stream_) {
     d.tiles_x = d.tiles_h * d.tiles_w * d.N;
     d.n_ntiles = a->Co_pad / a->BN;
     d.total_tiles = d.tiles_x * d.n_ntiles * a->n_phases;
+    d.tail_from = -1;
+    if (a->BN == 256 && a->split == 1 && skw == 0 && !getenv("SSCG_NO_TAIL_SPLIT")) {
+        // persistent grid of one CTA per SM: if the last wave is at most half full, run it as half-N tiles
+        const int G = sm_count(), T = d.total_tiles, rem = T % G;
+        if (T > G && rem > 0 && 2 * rem <= G) {
+            d.tail_from = T - rem;
+            d.total_tiles = T + rem;
+            if (int rc = encode_2d(&tmBlo, a->w, a->Kc, a->w_rows, 64, a->BN / 2)) return rc;
+        }
+    }
     d.y = a->y; d.y_fp32 = a->y_fp32;
     d.y_sN = a->y_sN; d.y_sH = a->y_sH; d.y_sW = a->y_sW; d.y_oh = a->y_oh; d.y_ow = a->y_ow;
     d.bias = a->bias; d.act = a->act; d.slope = a->slope; d.stats = a->stats;

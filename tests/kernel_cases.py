@@ -583,6 +583,9 @@ CASES = {
     "convT_fwd": lambda: case_convT_fwd(),
     "convT_fwd_256": lambda: case_convT_fwd(Cin=256, Cout=128),
     "convT_bwd": lambda: case_convT_bwd(),
+    # 160 tiles on 148 SMs: the last, partial wave runs as half-N tiles (tail_from in conv_igemm.cu)
+    "conv_tail_split_stats": lambda: case_conv_fwd(N=5, H=64, W=64, Cin=64, Cout=256, out_fp32=False, stats=True),
+    "conv_tail_split_bias_act": lambda: case_conv_fwd(N=5, H=64, W=64, Cin=64, Cout=256, bias=True, act=L.ACT_LRELU),
     # dgrad
     "dgrad_3x3_s1": lambda: case_conv_dgrad(),
     "dgrad_3x3_s2": lambda: case_conv_dgrad(stride=2),
