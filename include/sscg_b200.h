@@ -206,11 +206,10 @@ int sscg_in_bwd_apply(const SscgBwdArgs* a, void* draw, void* draw_lo, void* str
  * sums are complete, and sweep their pixels a second time out of L2 to write dRaw — no dZ round trip.
  * Returns 3 (no error string) if N exceeds the number of co-resident CTAs: use prep + apply instead. */
 int sscg_in_bwd_fused(const SscgBwdArgs* a, void* draw, void* draw_lo, uint32_t* sync_ctr, void* stream);
-/* sscg_set_stream_norm: 1 (default) lets sscg_in_apply / sscg_in_bwd_apply use their bulk-copy pipelined
- * variants (cp.async.bulk ring in shared memory, one persistent CTA per SM, a producer warp and free-running
- * consumer warps) when every tensor is bf16 and the row geometry suits the ring; 2 also selects the
- * pipelined sscg_in_bwd_prep (same speed as the register-batched kernel on B200, hence opt-in); 0 forces
- * the register-batched kernels everywhere.  Same results in every mode (identical arithmetic; only the
+/* sscg_set_stream_norm: 2 (default) lets sscg_in_apply / sscg_in_bwd_prep / sscg_in_bwd_apply use their
+ * bulk-copy pipelined variants (cp.async.bulk ring in shared memory, one persistent CTA per SM, a producer
+ * warp and free-running consumer warps) when every tensor is bf16 and the row geometry suits the ring; 1
+ * keeps the register-batched sscg_in_bwd_prep; 0 forces the register-batched kernels everywhere.  Same results in every mode (identical arithmetic; only the
  * summation order of the plane sums differs).  SSCG_STREAM_NORM=0|1|2 sets the initial value. */
 int sscg_set_stream_norm(int32_t on);
 

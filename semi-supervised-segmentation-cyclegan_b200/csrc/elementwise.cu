@@ -314,13 +314,12 @@ static int g_stream_norm = -1;     // -1: read SSCG_STREAM_NORM from the environ
 static bool stream_enabled() {
     if (g_stream_norm < 0) {
         const char* e = getenv("SSCG_STREAM_NORM");
-        g_stream_norm = (e && e[0] >= '0' && e[0] <= '2') ? (e[0] - '0') : 1;
+        g_stream_norm = (e && e[0] >= '0' && e[0] <= '2') ? (e[0] - '0') : 2;
     }
     return g_stream_norm != 0;
 }
-// The pipelined first backward half matches the register-batched kernel's speed but does not beat it
-// (both issue-bound at ~240 instructions per 8-channel vector), so it is opt-in: value 2 (or
-// SSCG_STREAM_NORM=2) selects it too.
+// Mode 1 keeps the register-batched first backward half (the pipelined one is 8-20 % faster at production
+// shapes: 39 vs 43 us on 16 x 64 x 64 x 256 with a reflect halo); mode 2, the default, pipelines all three.
 static bool stream_prep_enabled() { return stream_enabled() && g_stream_norm >= 2; }
 static int ew_sm_count() {
     static int n = 0;
@@ -333,12 +332,13 @@ static int ew_sm_count() {
 }
 // Unit = 1/d of an image row (d = smallest divisor of W that brings the unit under kStrUnitMax; a whole
 // row of up to 48 KB when W has no such divisor).  Returns false when the shape does not suit the ring.
-static bool stream_geom(int N, int H, int W, int C, int ntens, int threads, StreamGeom& g) {
+static bool stream_geom(int N, int H, int W, int C, int ntens, int threads, StreamGeom& g, int budget = kStrSmemBudget,
+                        int halo_px = 0) {
     if (!stream_enabled() || C % 8 || N < 1 || H < 1 || W < 1) return false;
     const int CH = C / 8;
     if (CH > 64 || threads % CH) return false;
     const long long row = (long long)W * C * 2;
-    long long unit_max = kStrSmemBudget / (3 * ntens);       // at least three stages in the ring
+    long long unit_max = budget / (3 * ntens);       // at least three stages in the ring
     if (unit_max > kStrUnitMax) unit_max = kStrUnitMax;
     int d = 0;
     for (int t = 1; t <= W; ++t)
@@ -354,7 +354,9 @@ static bool stream_geom(int N, int H, int W, int C, int ntens, int threads, Stre
     g.total = N * g.ups;
     g.ntens = ntens;
     g.CH = CH;
-    int nst = kStrSmemBudget / (ntens * g.ub);
+    g.slot0 = ((g.seg_px + 2 * halo_px) * C * 2 + 127) & ~127;
+    g.stage_bytes = g.slot0 + (ntens - 1) * g.ub;
+    int nst = budget / g.stage_bytes;
     if (nst > kStrMaxStages) nst = kStrMaxStages;
     if (nst < 2) return false;
     g.nst = nst;
@@ -368,7 +370,7 @@ static int stream_prepare(KernelT kernel, int& done) {
     done = 1;
     return 0;
 }
-static inline size_t stream_smem(const StreamGeom& g) { return (size_t)g.nst * g.ntens * g.ub + 512; }
+static inline size_t stream_smem(const StreamGeom& g) { return (size_t)g.nst * g.stage_bytes + 512; }
 static inline int stream_grid(const StreamGeom& g) { return g.total < ew_sm_count() ? g.total : ew_sm_count(); }
 
 }  // namespace sscg
@@ -492,14 +494,26 @@ extern "C" int sscg_in_bwd_prep(const SscgBwdArgs* a, void* stream) {
         const bool views_ok = a->dyp.ptr != nullptr && a->dyp.sW == a->C && (a->skip.ptr == nullptr || a->skip.sW == a->C);
         const bool pad_ok = a->pad == 0 || (a->pad < a->H && a->pad < a->W);
         const int ntens = 1 + (a->skip.ptr ? 1 : 0) + (need_raw ? 1 : 0);
-        if (plain && views_ok && pad_ok && a->dz != nullptr && stream_prep_enabled() && stream_geom(a->N, a->H, a->W, a->C, ntens, kStrThreadsHeavy, sd.g)) {
-            static int prepared = 0;
-            if (int rc = stream_prepare(in_bwd_prep_stream_kernel<kStrThreadsHeavy>, prepared)) return rc;
+        if (plain && views_ok && pad_ok && a->dz != nullptr && stream_prep_enabled() && stream_geom(a->N, a->H, a->W, a->C, ntens, kStrThreadsHeavy, sd.g, kStrSmemBudget - kStrThreadsHeavy * 16 * 4,
+                        (a->pad_mode == SSCG_PAD_REFLECT) ? a->pad : 0)) {
+            static int prepared[3] = {0, 0, 0};
+            if (int rc = stream_prepare(in_bwd_prep_stream_kernel<kStrThreadsHeavy, 0>, prepared[0])) return rc;
+            if (int rc = stream_prepare(in_bwd_prep_stream_kernel<kStrThreadsHeavy, 1>, prepared[1])) return rc;
+            if (int rc = stream_prepare(in_bwd_prep_stream_kernel<kStrThreadsHeavy, 2>, prepared[2])) return rc;
             sd.a = *a; sd.draw = nullptr;
+            int spec = 0;
+            if (a->stats && a->bstats) {
+                if (a->act == SSCG_ACT_RELU && !a->skip.ptr && !a->g_out) spec = 1;
+                else if (a->act == SSCG_ACT_NONE && a->skip.ptr && a->g_out && a->drop_seed == 0) spec = 2;
+            }
             {
                 LaunchScope ls_(8, static_cast<cudaStream_t>(stream));
-                in_bwd_prep_stream_kernel<kStrThreadsHeavy><<<stream_grid(sd.g), kStrThreadsHeavy + 32, stream_smem(sd.g),
-                                            static_cast<cudaStream_t>(stream)>>>(sd);
+                const dim3 grid(stream_grid(sd.g)), block(kStrThreadsHeavy + 32);
+                const size_t smem = stream_smem(sd.g);
+                cudaStream_t st = static_cast<cudaStream_t>(stream);
+                if (spec == 1) in_bwd_prep_stream_kernel<kStrThreadsHeavy, 1><<<grid, block, smem, st>>>(sd);
+                else if (spec == 2) in_bwd_prep_stream_kernel<kStrThreadsHeavy, 2><<<grid, block, smem, st>>>(sd);
+                else in_bwd_prep_stream_kernel<kStrThreadsHeavy, 0><<<grid, block, smem, st>>>(sd);
             }
             SSCG_CHECK_LAUNCH("in_bwd_prep_stream");
             return 0;

@@ -42,6 +42,8 @@ struct StreamGeom {
     int nst;        // ring stages
     int ntens;      // tensors loaded per unit
     int CH;         // 8-channel vectors per pixel
+    int slot0;      // bytes reserved for the first tensor of a stage (>= ub: the backward kernel also stages halo columns)
+    int stage_bytes;
 };
 
 // volatile: the same shared address is re-read after the stage has been refilled; ordered against the
@@ -92,7 +94,7 @@ __device__ __forceinline__ StreamRing stream_ring_init(uint8_t* smem_raw, const 
     r.bars = al;
     r.base = al + 128;
     r.nst = g.nst;
-    r.stage_bytes = g.ntens * g.ub;
+    r.stage_bytes = g.stage_bytes;
     if (threadIdx.x == 0) {
         for (int s = 0; s < g.nst; ++s) {
             mbar_init(r.bars + s * 8, 1);
@@ -256,44 +258,57 @@ struct BwdStreamDev {
     StreamGeom g;
 };
 
-// consumers only (named barrier 1 over kStrThreads threads)
+// consumers only (named barrier 1 over kStrThreads threads).  s_red: kStrThreads * 16 floats.  Thread
+// (row, chunk) parks its 16 partial sums in row `row`; CH * 16 outputs are then summed over the rows.
+// (A first version used shared-memory float atomics: kStrThreads / CH-way contended CAS loops, ~6 us per
+// flush — as much as the whole streaming part of the kernel.)
 template <int kStrThreads>
-__device__ __forceinline__ void stream_flush_stats(float* s_acc, float (&acc1)[8], float (&acc2)[8], float* bstats,
+__device__ __forceinline__ void stream_flush_stats(float* s_red, float (&acc1)[8], float (&acc2)[8], float* bstats,
                                                    int n, int C, int CH, int chunk) {
-    // s_acc: CH * 16 floats, zero on entry and left zero on exit
+    const int row = threadIdx.x / CH, rows = kStrThreads / CH, width = CH * 16;
+    float4* mine = reinterpret_cast<float4*>(s_red + row * width + chunk * 16);
+    mine[0] = make_float4(acc1[0], acc2[0], acc1[1], acc2[1]);
+    mine[1] = make_float4(acc1[2], acc2[2], acc1[3], acc2[3]);
+    mine[2] = make_float4(acc1[4], acc2[4], acc1[5], acc2[5]);
+    mine[3] = make_float4(acc1[6], acc2[6], acc1[7], acc2[7]);
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-        atomicAdd(&s_acc[chunk * 16 + 2 * q], acc1[q]);
-        atomicAdd(&s_acc[chunk * 16 + 2 * q + 1], acc2[q]);
-        acc1[q] = 0.f;
-        acc2[q] = 0.f;
-    }
+    for (int q = 0; q < 8; ++q) acc1[q] = acc2[q] = 0.f;
     named_bar_sync(1, kStrThreads);
-    for (int o = threadIdx.x; o < CH * 16; o += kStrThreads) {
+    for (int o = threadIdx.x; o < width; o += kStrThreads) {
+        float t = 0.f;
+        for (int r = 0; r < rows; ++r) t += s_red[r * width + o];
         // o = ch * 16 + 2 * q + k  ->  bstats[(n * C + ch * 8 + q) * 2 + k]
-        atomicAdd(bstats + (long long)n * C * 2 + o, s_acc[o]);
-        s_acc[o] = 0.f;
+        atomicAdd(bstats + (long long)n * C * 2 + o, t);
     }
     named_bar_sync(1, kStrThreads);
 }
 
-template <int kStrThreads>
+// SPEC: 0 = every flag read at run time; 1 / 2 = the two residual-block shapes with their flags folded at
+// compile time (1: norm + ReLU, no skip / total-gradient output — conv1 of a block; 2: norm, no activation,
+// skip gradient + total-gradient output, no dropout — conv2 of a block).  The generic kernel spends ~70 of its
+// ~240 instructions per 8-channel vector on uniform flag tests and their predication.
+template <int kStrThreads, int SPEC>
 __global__ void __launch_bounds__(kStrThreads + 32, 1) in_bwd_prep_stream_kernel(const __grid_constant__ BwdStreamDev p) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ float s_acc[64 * 16];
+    __shared__ __align__(16) float s_red[kStrThreads * 16];
     const SscgBwdArgs& a = p.a;
     const StreamGeom& g = p.g;
-    for (int o = threadIdx.x; o < 64 * 16; o += kStrThreads + 32) s_acc[o] = 0.f;
     const StreamRing ring = stream_ring_init<kStrThreads>(smem_raw, g);
     const int u0 = (int)((long long)blockIdx.x * g.total / gridDim.x);
     const int u1 = (int)((long long)(blockIdx.x + 1) * g.total / gridDim.x);
     const int cnt = u1 - u0;
     if (cnt <= 0) return;
-    const bool norm = a.stats != nullptr;
-    const bool need_raw = norm || a.act != SSCG_ACT_NONE;
-    const bool has_skip = a.skip.ptr != nullptr;
+    const bool norm = SPEC != 0 ? true : (a.stats != nullptr);
+    const int act = SPEC == 1 ? SSCG_ACT_RELU : (SPEC == 2 ? SSCG_ACT_NONE : a.act);
+    const bool need_raw = norm || act != SSCG_ACT_NONE;
+    const bool has_skip = SPEC == 1 ? false : (SPEC == 2 ? true : (a.skip.ptr != nullptr));
+    const bool has_gout = SPEC == 1 ? false : (SPEC == 2 ? true : (a.g_out != nullptr));
     const bool fold = (a.pad_mode == SSCG_PAD_REFLECT) && a.pad > 0;
-    const int off_skip = g.ub, off_raw = (has_skip ? 2 : 1) * g.ub;
+    const int off_skip = g.slot0, off_raw = g.slot0 + (has_skip ? 1 : 0) * g.ub;
+    // The gradient row is staged WITH the halo columns next to it (first / last unit of a row), so the
+    // mirrored columns of a reflect halo fold out of shared memory; only the 2 * pad rows next to the top /
+    // bottom border still fetch their mirrored rows from global memory.
+    const int last_part_w0 = (g.upr - 1) * g.seg_px;
     if (threadIdx.x >= kStrThreads) {
         if (threadIdx.x == kStrThreads) {
             const __nv_bfloat16* rawp = reinterpret_cast<const __nv_bfloat16*>(a.raw);
@@ -303,9 +318,12 @@ __global__ void __launch_bounds__(kStrThreads + 32, 1) in_bwd_prep_stream_kernel
                 const UnitPos up = unit_pos(g, u0 + k);
                 ring.acquire(k);
                 const uint32_t bar = ring.full(k), dst = ring.stage(k);
-                mbar_arrive_expect_tx(bar, (uint32_t)(g.ntens * g.ub));
+                const int lpad = (fold && up.w0 == 0) ? a.pad : 0;
+                const int rpad = (fold && up.w0 == last_part_w0) ? a.pad : 0;
+                const uint32_t dy_bytes = (uint32_t)((g.seg_px + lpad + rpad) * a.C * 2);
+                mbar_arrive_expect_tx(bar, dy_bytes + (uint32_t)((g.ntens - 1) * g.ub));
                 bulk_load(dst, dyp + (long long)up.n * a.dyp.sN + (long long)(up.h + a.pad) * a.dyp.sH +
-                                   (long long)(up.w0 + a.pad) * a.dyp.sW, g.ub, bar);
+                                   (long long)(up.w0 + a.pad - lpad) * a.dyp.sW, dy_bytes, bar);
                 if (has_skip)
                     bulk_load(dst + off_skip, skp + (long long)up.n * a.skip.sN + (long long)up.h * a.skip.sH +
                                                   (long long)up.w0 * a.skip.sW, g.ub, bar);
@@ -319,8 +337,9 @@ __global__ void __launch_bounds__(kStrThreads + 32, 1) in_bwd_prep_stream_kernel
     const int c0 = chunk * 8;
     const int prow = threadIdx.x / g.CH;
     const int pstep = kStrThreads / g.CH;
-    const uint64_t seed = (a.drop_seed != 0 && a.drop_ctr) ? (a.drop_seed ^ (*a.drop_ctr * 0x9E3779B97F4A7C15ull))
-                                                           : a.drop_seed;
+    const uint64_t seed = SPEC == 2 ? 0ull
+                          : ((a.drop_seed != 0 && a.drop_ctr) ? (a.drop_seed ^ (*a.drop_ctr * 0x9E3779B97F4A7C15ull))
+                                                              : a.drop_seed);
     float mean[8], rstd[8], acc1[8], acc2[8];
 #pragma unroll
     for (int q = 0; q < 8; ++q) acc1[q] = acc2[q] = 0.f;
@@ -329,7 +348,7 @@ __global__ void __launch_bounds__(kStrThreads + 32, 1) in_bwd_prep_stream_kernel
         const UnitPos up = unit_pos(g, u0 + k);
         const int n = up.n, h = up.h, w0 = up.w0;
         if (n != cur_n) {
-            if (cur_n >= 0 && a.bstats != nullptr) stream_flush_stats<kStrThreads>(s_acc, acc1, acc2, a.bstats, cur_n, a.C, g.CH, chunk);
+            if (cur_n >= 0 && a.bstats != nullptr) stream_flush_stats<kStrThreads>(s_red, acc1, acc2, a.bstats, cur_n, a.C, g.CH, chunk);
             cur_n = n;
             if (norm) load_norm(a.stats, a.eps, (long long)n * a.C + c0, 1.f / (float)(a.H * a.W), mean, rstd);
         }
@@ -337,16 +356,24 @@ __global__ void __launch_bounds__(kStrThreads + 32, 1) in_bwd_prep_stream_kernel
         if (fold) mirror_pos(h, a.H, a.pad, hm1, hm2);
         const bool hborder = (hm1 >= 0) || (hm2 >= 0);
         const long long spix0 = ((long long)n * a.H + h) * a.W;
+        const int lpad = (fold && w0 == 0) ? a.pad : 0;
+        const int col0 = w0 + a.pad - lpad;            // padded column held by staged pixel 0 of the gradient row
         mbar_wait(ring.full(k), ring.parity(k), 12);
         const uint32_t st = ring.stage(k);
+        // rows next to the top / bottom border: the gradient of the mirrored halo row (same column) is fetched
+        // from global memory up front, together with the shared-memory loads of the batch
+        const int xf = hm1 >= 0 ? 1 : 2;
+        const __nv_bfloat16* mrow = reinterpret_cast<const __nv_bfloat16*>(a.dyp.ptr) + (long long)n * a.dyp.sN +
+                                    (long long)(hm1 >= 0 ? hm1 : (hm2 >= 0 ? hm2 : 0)) * a.dyp.sH + c0;
         for (int px0 = prow; px0 < g.seg_px; px0 += 2 * pstep) {
-            uint4 rg[2], rs[2], rz[2];
+            uint4 rg[2], rs[2], rz[2], rm[2];
 #pragma unroll
             for (int b = 0; b < 2; ++b) {
                 const int px = px0 + b * pstep;
                 if (px < g.seg_px) {
                     const uint32_t so = st + (px * a.C + c0) * 2;
-                    rg[b] = lds128(so);
+                    if (hborder) rm[b] = *reinterpret_cast<const uint4*>(mrow + (long long)(w0 + px + a.pad) * a.dyp.sW);
+                    rg[b] = lds128(so + lpad * a.C * 2);
                     if (has_skip) rs[b] = lds128(so + off_skip);
                     if (need_raw) rz[b] = lds128(so + off_raw);
                 }
@@ -371,8 +398,13 @@ __global__ void __launch_bounds__(kStrThreads + 32, 1) in_bwd_prep_stream_kernel
                         for (int y = 0; y < 3; ++y) {
                             if (x + y == 0 || hh[x] < 0 || ww[y] < 0) continue;
                             float t[8];
-                            load8(a.dyp.ptr, false,
-                                  (long long)n * a.dyp.sN + (long long)hh[x] * a.dyp.sH + (long long)ww[y] * a.dyp.sW + c0, t);
+                            if (x == 0)       // same row: the mirrored column was staged with the row
+                                cvt8(lds128(st + ((ww[y] - col0) * a.C + c0) * 2), t);
+                            else if (x == xf && y == 0)
+                                cvt8(rm[b], t);
+                            else
+                                load8(a.dyp.ptr, false,
+                                      (long long)n * a.dyp.sN + (long long)hh[x] * a.dyp.sH + (long long)ww[y] * a.dyp.sW + c0, t);
 #pragma unroll
                             for (int q = 0; q < 8; ++q) gv[q] += t[q];
                         }
@@ -383,12 +415,13 @@ __global__ void __launch_bounds__(kStrThreads + 32, 1) in_bwd_prep_stream_kernel
 #pragma unroll
                     for (int q = 0; q < 8; ++q) gv[q] += t[q];
                 }
-                if (a.g_out != nullptr)
+                if (has_gout)
                     *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.g_out) + off) = pack8(gv);
                 if (seed != 0) {
                     const uint32_t bits = drop_bits(seed, (unsigned long long)spix * g.CH + chunk);
+                    // keep -> x2, drop -> x0: bit q moved to the exponent position of 2.0f (0x40000000)
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) gv[q] = ((bits >> q) & 1u) ? 2.f * gv[q] : 0.f;
+                    for (int q = 0; q < 8; ++q) gv[q] *= __uint_as_float(((bits >> q) & 1u) << 30);
                 }
                 if (need_raw) {
                     cvt8(rz[b], z);
@@ -396,13 +429,13 @@ __global__ void __launch_bounds__(kStrThreads + 32, 1) in_bwd_prep_stream_kernel
 #pragma unroll
                         for (int q = 0; q < 8; ++q) z[q] = (z[q] - mean[q]) * rstd[q];
                     }
-                    if (a.act == SSCG_ACT_RELU) {
+                    if (act == SSCG_ACT_RELU) {
 #pragma unroll
                         for (int q = 0; q < 8; ++q) gv[q] = z[q] > 0.f ? gv[q] : 0.f;
-                    } else if (a.act == SSCG_ACT_LRELU) {
+                    } else if (act == SSCG_ACT_LRELU) {
 #pragma unroll
                         for (int q = 0; q < 8; ++q) gv[q] = z[q] > 0.f ? gv[q] : gv[q] * a.slope;
-                    } else if (a.act == SSCG_ACT_TANH) {
+                    } else if (act == SSCG_ACT_TANH) {
 #pragma unroll
                         for (int q = 0; q < 8; ++q) gv[q] = gv[q] * (1.f - z[q] * z[q]);
                     }
@@ -420,7 +453,7 @@ __global__ void __launch_bounds__(kStrThreads + 32, 1) in_bwd_prep_stream_kernel
         }
         ring.release(k);
     }
-    if (a.bstats != nullptr) stream_flush_stats<kStrThreads>(s_acc, acc1, acc2, a.bstats, cur_n, a.C, g.CH, chunk);
+    if (a.bstats != nullptr) stream_flush_stats<kStrThreads>(s_red, acc1, acc2, a.bstats, cur_n, a.C, g.CH, chunk);
 }
 
 // ---------------------------------------------------------------------------------------------
