@@ -198,6 +198,8 @@ typedef struct SscgBwdArgs {
     void* dz; int32_t dz_fp32;        /* [N][H][W][C] */
     void* dz_lo;                      /* lo plane when dZ is the final dRaw in split mode */
     float* bstats;                    /* [N][C][2] */
+    int32_t dz_pad;                   /* > 0: dZ is written into a [N][H+2p][W+2p][C] buffer at offset (p, p); the halo is
+                                         left untouched (kept zero by the caller: input layout of sscg_conv7_nexp's data gradient) */
 } SscgBwdArgs;
 int sscg_in_bwd_prep(const SscgBwdArgs* a, void* stream);
 int sscg_in_bwd_apply(const SscgBwdArgs* a, void* draw, void* draw_lo, void* stream);
@@ -221,8 +223,11 @@ typedef struct SscgWprepArgs {
     int32_t mode;          /* 0: fwd regular  [tap][Co_pad][Kc(ci)]
                               1: fwd window   [kh][Co_pad][Kc(kw*Cp+ci)]
                               2: dgrad regular [tap][Ci_pad][Kc(co)]  (taps indexed as in the source)
+                              3: N-expanded 7x7 forward  [kh][nt][NT: kw * CoW + (co - nt * CoW)][Kc(ci)]
+                              4: N-expanded 7x7 dgrad    [kh][nt][NT: kw * CoW + (ci - nt * CoW)][Kc(co)], taps flipped
+                                 (sscg_conv7_nexp; CoW is passed in Cp, rows_pad = NT = round_up(7 * CoW, 16))
                             */
-    int32_t Cp;            /* channel pitch of the activation in window mode */
+    int32_t Cp;            /* channel pitch of the activation in window mode; CoW in modes 3 / 4 */
     int32_t rows_pad;      /* Co_pad (mode 0,1) or Ci_pad (mode 2) */
     int32_t Kc;
     void* dst; void* dst_lo;
@@ -230,6 +235,28 @@ typedef struct SscgWprepArgs {
 int sscg_wprep(const SscgWprepArgs* a, void* stream);
 /* inverse mapping for gradients: fp32 slab [rows][Kc] -> += into the parameter-shaped gradient */
 int sscg_wgrad_unpack(const SscgWprepArgs* a, const float* slab, float* grad, float scale, void* stream);
+
+/* sscg_conv7_nexp: 7x7 stride-1 convolution with a narrow output (generator head 64 -> 21 / 3 channels,
+ * arch/generators.py:84-85,89-90, and its data gradient) as an N-expanded implicit GEMM: the seven horizontal
+ * taps become GEMM columns (N = 7 * CoW) and are shift-added in the epilogue through shared memory, so a
+ * 128-pixel tile needs 7 * ksteps wide MMAs instead of 196 narrow ones (see csrc/conv_nexp.cu).
+ *   x: bf16 activation [N][Hp][Wp][x_pitch] carrying an explicit halo of 3 (forward: the reflect halo of the
+ *      head's input; data gradient: dRaw in a buffer with a ZERO halo of 6); the first 16 * ksteps channels of
+ *      every pixel enter the contraction.
+ *   w: slab from sscg_wprep mode 3 (forward) or 4 (data gradient): [7][n_ntiles][NT][64] bf16.
+ *   y: output [N][Hp-6][Wp-6] with the given element strides, fp32 (y_fp32) or bf16; N tile nt writes channels
+ *      nt * CoW .. nt * CoW + c_store; bias (fp32, indexed by output channel) and activation are optional. */
+typedef struct SscgConv7Args {
+    const void* x; int32_t x_pitch;
+    int32_t N, Hp, Wp;
+    const void* w;
+    int32_t CoW, n_ntiles, ksteps, c_store;
+    void* y; int32_t y_fp32;
+    int64_t y_sN, y_sH, y_sW;
+    const float* bias; int32_t act;
+    int32_t tag;
+} SscgConv7Args;
+int sscg_conv7_nexp(const SscgConv7Args* a, void* stream);
 
 /* Batched forms: ONE launch over a DEVICE table of descriptors (every slab of a network).  `start` is the
  * running element offset of the entry (entries sorted by start; total = sum of ntaps * rows_pad * Kc);

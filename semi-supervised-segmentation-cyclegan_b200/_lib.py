@@ -83,6 +83,7 @@ class BwdArgs(C.Structure):
         ("dz", C.c_void_p), ("dz_fp32", C.c_int32),
         ("dz_lo", C.c_void_p),
         ("bstats", C.c_void_p),
+        ("dz_pad", C.c_int32),
     ]
 
 
@@ -93,6 +94,13 @@ class WprepArgs(C.Structure):
         ("mode", C.c_int32), ("Cp", C.c_int32), ("rows_pad", C.c_int32), ("Kc", C.c_int32),
         ("dst", C.c_void_p), ("dst_lo", C.c_void_p),
     ]
+
+
+class Conv7Args(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("x_pitch", C.c_int32), ("N", C.c_int32), ("Hp", C.c_int32), ("Wp", C.c_int32),
+                ("w", C.c_void_p), ("CoW", C.c_int32), ("n_ntiles", C.c_int32), ("ksteps", C.c_int32),
+                ("c_store", C.c_int32), ("y", C.c_void_p), ("y_fp32", C.c_int32), ("y_sN", C.c_int64),
+                ("y_sH", C.c_int64), ("y_sW", C.c_int64), ("bias", C.c_void_p), ("act", C.c_int32), ("tag", C.c_int32)]
 
 
 class WbatchEntry(C.Structure):
@@ -117,6 +125,7 @@ _SIGNATURES = {
     "sscg_set_stream_norm": [C.c_int32],
     "sscg_wprep": [C.POINTER(WprepArgs), C.c_void_p],
     "sscg_wgrad_unpack": [C.POINTER(WprepArgs), C.c_void_p, C.c_void_p, C.c_float, C.c_void_p],
+    "sscg_conv7_nexp": [C.POINTER(Conv7Args), C.c_void_p],
     "sscg_wprep_batch": [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p],
     "sscg_wgrad_unpack_batch": [C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_void_p],
     "sscg_fill_zero": [C.c_void_p, C.c_int64, C.c_void_p],

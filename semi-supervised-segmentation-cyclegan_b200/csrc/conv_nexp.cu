@@ -1,0 +1,292 @@
+// conv_nexp.cu — 7x7 stride-1 convolutions with a NARROW output (the generator head, 64 -> 21 / 3 channels,
+// and its data gradient, 21 / 3 -> 64 channels) as an "N-expanded" implicit GEMM on tcgen05.
+//
+// The regular kernel (conv_igemm.cu) runs these layers as M = 128 pixels x N = Cout (16..64) x K = 49 * 64:
+// 196 MMAs per tile whose cost is set by the shared-memory read of the 128 x 16 A slab (~60 cycles each,
+// whatever N is), i.e. the tensor pipe sits at 10-40 %.  Here the seven HORIZONTAL taps move from K to N:
+//
+//     P[p][(kw, co)] = sum_{kh, c} X[row(p) + kh - 3][col(p)][c] * W[kh][kw][c][co]        (GEMM, K = 7 * 64)
+//     Y[o][co]       = sum_{kw}    P[o + kw - 3][(kw, co)]                                   (epilogue)
+//
+// so a tile needs 7 * ksteps MMAs of N = 7 * CoW columns (up to 224) instead of 196 narrow ones, and the
+// operand read per useful MAC drops ~6x.  Pixels are addressed in the FLATTENED padded image (p = row * Wp + col):
+// a shift by kw - 3 is a shift of the flattened index, wrong only across row ends, which are halo columns whose
+// outputs are never stored.  A tile is 128 consecutive flattened pixels and yields 122 outputs; the shift-add
+// runs through a 128 x (N + 1) fp32 staging buffer in shared memory (conflict-free for both the row-wise store
+// and the diagonal read).
+//
+// Roles as in conv_igemm.cu: warp 0 TMA producer, warp 1 MMA issuer (two TMEM accumulators), warps 2..5 epilogue.
+// Replaces (reference): the 7x7 nn.Conv2d head of arch/generators.py:84-85,89-90 (forward and cuDNN dgrad).
+#include "sscg_common.cuh"
+
+namespace sscg {
+
+struct NexpDev {
+    int N;              // samples
+    int Hp, Wp;         // padded input extents (flattened pixel space of one sample: Hp * Wp)
+    int tiles_per_sample, n_ntiles, total_tiles;
+    int NT;             // GEMM N of one tile = round_up(7 * CoW, 16)
+    int CoW;            // output columns per horizontal tap in one N tile
+    int ksteps;         // 16-channel K steps per vertical tap (1, 2 or 4)
+    int stages;
+    void* y;
+    int y_fp32;
+    long long y_sN, y_sH, y_sW;
+    int y_c0_step;      // output channel offset per N tile (= CoW)
+    int c_store;        // channels written per pixel (<= CoW, multiple of 8)
+    const float* bias;
+    int act;
+};
+
+constexpr int kNxTileM = 128;
+constexpr int kNxOut = 122;               // outputs per tile (128 - 6 halo pixels)
+constexpr int kNxABytes = kNxTileM * 128;
+
+__global__ void __launch_bounds__(192, 1)
+conv_nexp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ NexpDev p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int b_bytes = p.NT * 128;
+    const int stage_bytes = kNxABytes + ((b_bytes + 1023) & ~1023);
+    float* S = reinterpret_cast<float*>(smem + p.stages * stage_bytes);
+    const int s_pitch = p.NT + 1;                       // odd: conflict-free row-wise stores and diagonal reads
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(S) + ((kNxTileM * s_pitch * 4 + 15) & ~15));
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + 4;
+    uint64_t* tmem_full_bar = bars + 8;        // [2]
+    uint64_t* tmem_empty_bar = bars + 10;      // [2]
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 12);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int acc_cols = p.NT;                                  // columns per accumulator
+    const uint32_t tmem_cols = 2 * p.NT <= 128 ? 128u : (2 * p.NT <= 256 ? 256u : 512u);
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(smem_u32(&full_bar[s]), 1);
+            mbar_init(smem_u32(&empty_bar[s]), 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(smem_u32(&tmem_full_bar[s]), 1);
+            mbar_init(smem_u32(&tmem_empty_bar[s]), 128);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(smem_u32(tmem_ptr_smem), tmem_cols);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+    const int o_first = 3 * p.Wp;       // flattened index of the first output covered by tile 0 of a sample
+
+    if (warp == 0) {
+        // ================================ TMA producer ==========================================
+        if (lane == 0) {
+            int stage = 0; uint32_t par = 0;
+            const uint32_t tx = (uint32_t)(kNxABytes + b_bytes);
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                const int nt = tile % p.n_ntiles;
+                const int rest = tile / p.n_ntiles;
+                const int t = rest % p.tiles_per_sample, n = rest / p.tiles_per_sample;
+                const int px0 = n * p.Hp * p.Wp + o_first + t * kNxOut - 3;      // input pixel of tile row 0, kh = 3
+                for (int kh = 0; kh < 7; ++kh) {
+                    mbar_wait(smem_u32(&empty_bar[stage]), par ^ 1, 21);
+                    const uint32_t fb = smem_u32(&full_bar[stage]);
+                    mbar_arrive_expect_tx(fb, tx);
+                    uint8_t* st = smem + stage * stage_bytes;
+                    tma_load_2d(smem_u32(st), &tmA, fb, 0, px0 + (kh - 3) * p.Wp);
+                    tma_load_2d(smem_u32(st + kNxABytes), &tmB, fb, 0, (kh * p.n_ntiles + nt) * p.NT);
+                    if (++stage == p.stages) { stage = 0; par ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================ MMA issuer ============================================
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_bf16(kNxTileM, p.NT, 0, 0);
+            int stage = 0; uint32_t par = 0;
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                const uint32_t acc = it & 1, acc_par = (it >> 1) & 1;
+                ++it;
+                mbar_wait(smem_u32(&tmem_empty_bar[acc]), acc_par ^ 1, 22);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * acc_cols;
+                uint32_t accum = 0;
+                for (int kh = 0; kh < 7; ++kh) {
+                    mbar_wait(smem_u32(&full_bar[stage]), par, 23);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * stage_bytes);
+                    const uint64_t da = make_smem_desc_sw128(sa, 0, 1024);
+                    const uint64_t db = make_smem_desc_sw128(sa + kNxABytes, 0, 1024);
+                    for (int k = 0; k < p.ksteps; ++k) {
+                        umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, accum);
+                        accum = 1;
+                    }
+                    umma_commit(smem_u32(&empty_bar[stage]));
+                    if (++stage == p.stages) { stage = 0; par ^= 1; }
+                }
+                umma_commit(smem_u32(&tmem_full_bar[acc]));
+            }
+        }
+    } else {
+        // ================================ epilogue ==============================================
+        const int quad = warp & 3;
+        const int m = quad * 32 + lane;            // TMEM lane = tile pixel
+        float* srow = S + m * s_pitch;
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            const int nt = tile % p.n_ntiles;
+            const int rest = tile / p.n_ntiles;
+            const int t = rest % p.tiles_per_sample, n = rest / p.tiles_per_sample;
+            const uint32_t acc = it & 1, acc_par = (it >> 1) & 1;
+            ++it;
+            mbar_wait(smem_u32(&tmem_full_bar[acc]), acc_par, 24);
+            tc_fence_after();
+            const uint32_t t_acc = tmem_base + acc * acc_cols + (static_cast<uint32_t>(quad * 32) << 16);
+            // ---- accumulator -> staging buffer (row m) --------------------------------------------
+            for (int c0 = 0; c0 < p.NT; c0 += 32) {
+                uint32_t r[32];
+                const int w = p.NT - c0 >= 32 ? 32 : 16;
+                if (w == 32) tmem_ld_32x32(t_acc + c0, r);
+                else tmem_ld_32x16(t_acc + c0, r);
+                tmem_ld_wait();
+#pragma unroll
+                for (int q = 0; q < 32; ++q)
+                    if (q < w) srow[c0 + q] = __uint_as_float(r[q]);
+            }
+            tc_fence_before();
+            mbar_arrive(smem_u32(&tmem_empty_bar[acc]));          // accumulator drained
+            named_bar_sync(1, 128);                                // every row of S is written
+            // ---- shift-add over the seven horizontal taps + bias / activation + store ----------------
+            const int o = o_first + t * kNxOut + m;               // flattened padded position of this thread's output
+            const int orow = o / p.Wp, ocol = o - orow * p.Wp;
+            const bool valid = (m < kNxOut) && orow >= 3 && orow < p.Hp - 3 && ocol >= 3 && ocol < p.Wp - 3;
+            if (valid) {
+                const long long yoff = (long long)n * p.y_sN + (long long)(orow - 3) * p.y_sH +
+                                       (long long)(ocol - 3) * p.y_sW + nt * p.y_c0_step;
+                for (int c0 = 0; c0 < p.c_store; c0 += 8) {
+                    float v[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) v[q] = 0.f;
+#pragma unroll
+                    for (int kw = 0; kw < 7; ++kw) {
+                        const float* src = S + (m + kw) * s_pitch + kw * p.CoW + c0;
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) v[q] += src[q];
+                    }
+                    if (p.bias != nullptr) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) v[q] += __ldg(p.bias + nt * p.y_c0_step + c0 + q);
+                    }
+                    if (p.act == SSCG_ACT_TANH) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) v[q] = tanhf(v[q]);
+                    } else if (p.act == SSCG_ACT_RELU) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) v[q] = fmaxf(v[q], 0.f);
+                    }
+                    if (p.y_fp32) {
+                        float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.y) + yoff + c0);
+                        dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+                        dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+                    } else {
+                        uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.y) + yoff + c0);
+                        *dst = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                                          pack_bf16x2(v[6], v[7]));
+                    }
+                }
+            }
+            named_bar_sync(2, 128);                                // S may be overwritten by the next tile
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, tmem_cols);
+    }
+}
+
+static int encode_2d_pitch(CUtensorMap* tm, const void* ptr, long long rows, long long pitch_elems, int box_cols,
+                           int box_rows) {
+    PFN_encodeTiled enc = get_encode_tiled();
+    if (!enc) return 1;
+    cuuint64_t dims[2] = {(cuuint64_t)box_cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)pitch_elems * 2};
+    cuuint32_t b[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+    cuuint32_t s[2] = {1, 1};
+    if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (strides[0] & 15))
+        return set_error("conv7_nexp: activation pointer/pitch must be 16-byte aligned");
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, b, s,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return set_error("conv7_nexp: cuTensorMapEncodeTiled failed: %d rows=%lld pitch=%lld", (int)r, rows, pitch_elems);
+    return 0;
+}
+
+}  // namespace sscg
+
+using namespace sscg;
+
+extern "C" int sscg_conv7_nexp(const SscgConv7Args* a, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (a->ksteps != 1 && a->ksteps != 2 && a->ksteps != 4) return set_error("conv7_nexp: ksteps must be 1, 2 or 4");
+    if (a->x_pitch < 16 * a->ksteps || a->x_pitch % 8) return set_error("conv7_nexp: bad activation pitch %d", a->x_pitch);
+    if (a->CoW % 8 || a->CoW < 8 || a->CoW > 32) return set_error("conv7_nexp: CoW=%d must be 8, 16, 24 or 32", a->CoW);
+    if (a->c_store % 8 || a->c_store > a->CoW) return set_error("conv7_nexp: c_store=%d", a->c_store);
+    if (a->Hp < 7 || a->Wp < 7 || a->N < 1 || a->n_ntiles < 1) return set_error("conv7_nexp: bad geometry");
+    NexpDev d;
+    d.N = a->N; d.Hp = a->Hp; d.Wp = a->Wp;
+    d.CoW = a->CoW;
+    d.NT = ((7 * a->CoW + 15) / 16) * 16;
+    d.ksteps = a->ksteps;
+    d.n_ntiles = a->n_ntiles;
+    const long long outs = (long long)(a->Hp - 6) * a->Wp;          // flattened output positions, rows 3 .. Hp-4
+    d.tiles_per_sample = (int)((outs + kNxOut - 1) / kNxOut);
+    d.total_tiles = d.N * d.tiles_per_sample * d.n_ntiles;
+    d.y = a->y; d.y_fp32 = a->y_fp32;
+    d.y_sN = a->y_sN; d.y_sH = a->y_sH; d.y_sW = a->y_sW;
+    d.y_c0_step = a->CoW;
+    d.c_store = a->c_store;
+    d.bias = a->bias; d.act = a->act;
+    const int b_bytes = d.NT * 128;
+    const int stage_bytes = kNxABytes + ((b_bytes + 1023) & ~1023);
+    const int s_bytes = ((kNxTileM * (d.NT + 1) * 4 + 15) & ~15) + 256;
+    int stages = (225 * 1024 - 1024 - s_bytes) / stage_bytes;
+    if (stages > 4) stages = 4;
+    if (stages < 2) return set_error("conv7_nexp: tile does not fit shared memory (NT=%d)", d.NT);
+    d.stages = stages;
+    const int smem = 1024 + stages * stage_bytes + s_bytes;
+
+    CUtensorMap tmA, tmB;
+    const long long rows = (long long)a->N * a->Hp * a->Wp;
+    if (int rc = encode_2d_pitch(&tmA, a->x, rows, a->x_pitch, 64, kNxTileM)) return rc;
+    if (int rc = encode_2d(&tmB, a->w, 64, 7 * d.n_ntiles * d.NT, 64, d.NT)) return rc;
+
+    static int max_smem_set = 0;
+    if (smem > max_smem_set) {
+        cudaError_t e = cudaFuncSetAttribute(conv_nexp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return set_error("conv7_nexp: cudaFuncSetAttribute(smem=%d): %s", smem, cudaGetErrorString(e));
+        max_smem_set = smem;
+    }
+    int sms = 148, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int grid = sms < d.total_tiles ? sms : d.total_tiles;
+    {
+        LaunchScope ls(a->tag, stream);
+        conv_nexp_kernel<<<grid, 192, smem, stream>>>(tmA, tmB, d);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error("conv7_nexp launch: %s", cudaGetErrorString(e));
+    return 0;
+}

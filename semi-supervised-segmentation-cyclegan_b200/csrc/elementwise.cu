@@ -205,7 +205,18 @@ __global__ void bias_grad_kernel(const float* __restrict__ bstats, int N, int C,
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ long long wslab_src_index(const SscgWprepArgs& a, int t, int r, int k) {
     int co, ci, kh, kw;
-    if (a.mode == 1) {
+    if (a.mode == 3 || a.mode == 4) {
+        // N-expanded 7x7 slabs (conv_nexp.cu): t = kh * n_ntiles + nt, row r = kw * CoW + local column (CoW = a.Cp)
+        const int cow = a.Cp;
+        const int nn = ((a.mode == 3 ? a.Co : a.Ci) + cow - 1) / cow;
+        const int nt = t % nn;
+        kh = t / nn;
+        kw = r / cow;
+        const int loc = nt * cow + (r - kw * cow);
+        if (kw >= a.KW) return -1;
+        if (a.mode == 3) { co = loc; ci = k; }
+        else { ci = loc; co = k; kh = a.KH - 1 - kh; kw = a.KW - 1 - kw; }     // data gradient: flipped taps
+    } else if (a.mode == 1) {
         kh = t; kw = k / a.Cp; ci = k - kw * a.Cp; co = r;
         if (kw >= a.KW) return -1;
     } else {
@@ -216,7 +227,11 @@ __device__ __forceinline__ long long wslab_src_index(const SscgWprepArgs& a, int
     return a.transposed ? ((((long long)ci * a.Co + co) * a.KH + kh) * a.KW + kw)
                         : ((((long long)co * a.Ci + ci) * a.KH + kh) * a.KW + kw);
 }
-__device__ __forceinline__ int wslab_ntaps(const SscgWprepArgs& a) { return a.mode == 1 ? a.KH : a.KH * a.KW; }
+__host__ __device__ __forceinline__ int wslab_ntaps(const SscgWprepArgs& a) {
+    if (a.mode == 3) return a.KH * ((a.Co + a.Cp - 1) / a.Cp);
+    if (a.mode == 4) return a.KH * ((a.Ci + a.Cp - 1) / a.Cp);
+    return a.mode == 1 ? a.KH : a.KH * a.KW;
+}
 
 __global__ void wprep_kernel(const __grid_constant__ SscgWprepArgs a) {
     const long long total = (long long)wslab_ntaps(a) * a.rows_pad * a.Kc;
@@ -613,7 +628,7 @@ extern "C" int sscg_in_bwd_apply(const SscgBwdArgs* a, void* draw, void* draw_lo
 }
 
 extern "C" int sscg_wprep(const SscgWprepArgs* a, void* stream) {
-    const long long total = (long long)(a->mode == 1 ? a->KH : a->KH * a->KW) * a->rows_pad * a->Kc;
+    const long long total = (long long)wslab_ntaps(*a) * a->rows_pad * a->Kc;
     {
         LaunchScope ls_(9, static_cast<cudaStream_t>(stream));
         wprep_kernel<<<ew_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(*a);
@@ -623,7 +638,7 @@ extern "C" int sscg_wprep(const SscgWprepArgs* a, void* stream) {
 }
 
 extern "C" int sscg_wgrad_unpack(const SscgWprepArgs* a, const float* slab, float* grad, float scale, void* stream) {
-    const long long total = (long long)(a->mode == 1 ? a->KH : a->KH * a->KW) * a->rows_pad * a->Kc;
+    const long long total = (long long)wslab_ntaps(*a) * a->rows_pad * a->Kc;
     {
         LaunchScope ls_(9, static_cast<cudaStream_t>(stream));
         wgrad_unpack_kernel<<<ew_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(*a, slab, grad, scale);

@@ -339,8 +339,11 @@ __global__ void __launch_bounds__(256, SSCG_PREP_MINB) in_bwd_prep_kernel(const 
                     continue;
                 }
                 if (!FUSED) {
-                    if (ANYF32 && a.dz_fp32) store8_f32(a.dz, off, g);
-                    else store8_bf16(a.dz, ANYF32 ? a.dz_lo : nullptr, off, g);
+                    const long long doff = a.dz_pad > 0
+                        ? ((((long long)n * (a.H + 2 * a.dz_pad) + ph[b] + a.dz_pad) * (a.W + 2 * a.dz_pad) + pw[b] + a.dz_pad) * a.C + c0)
+                        : off;
+                    if (ANYF32 && a.dz_fp32) store8_f32(a.dz, doff, g);
+                    else store8_bf16(a.dz, ANYF32 ? a.dz_lo : nullptr, doff, g);
                 }
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {

@@ -443,7 +443,10 @@ __global__ void __launch_bounds__(kStrThreads + 32, 1) in_bwd_prep_stream_kernel
 #pragma unroll
                     for (int q = 0; q < 8; ++q) z[q] = 0.f;
                 }
-                *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.dz) + off) = pack8(gv);
+                const long long doff = a.dz_pad > 0
+                    ? ((((long long)n * (a.H + 2 * a.dz_pad) + h + a.dz_pad) * (a.W + 2 * a.dz_pad) + w + a.dz_pad) * a.C + c0)
+                    : off;
+                *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.dz) + doff) = pack8(gv);
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
                     acc1[q] += gv[q];

@@ -116,14 +116,34 @@ class StageWeights:
         self.bias_pad = None
         if s.bias is not None and not s.norm:
             self.bias_pad = torch.zeros(self.Co_pad, dtype=torch.float32, device=device)
+        # 7x7 head (64 -> <= 32 channels) in bf16 mode: N-expanded kernel (csrc/conv_nexp.cu) for the forward and the
+        # data gradient; the seven horizontal taps are GEMM columns, shift-added in the epilogue
+        self.nexp = (s.kind == "conv" and k == 7 and s.stride == 1 and s.in_halo == 3 and self.Cp_in == 64
+                     and s.Cout <= 32 and not split and not s.norm)
+        if self.nexp:
+            self.nx_CoW = 8 if s.Cout <= 8 else (16 if s.Cout <= 16 else (24 if s.Cout <= 24 else 32))
+            nt_f = G.round_up(7 * self.nx_CoW, 16)
+            self.w_nx = torch.zeros(7 * nt_f * 64, dtype=bf, device=device)
+            self.prep_nx = K.wprep_args(s.weight, False, s.Cout, s.Cin, 7, 7, 3, self.nx_CoW, nt_f, 64, self.w_nx)
+            nt_d = G.round_up(7 * 32, 16)
+            self.nx_dg_tiles = s.Cin // 32
+            self.w_nx_dg = torch.zeros(7 * self.nx_dg_tiles * nt_d * 64, dtype=bf, device=device)
+            self.prep_nx_dg = K.wprep_args(s.weight, False, s.Cout, s.Cin, 7, 7, 4, 32, nt_d, 64, self.w_nx_dg)
+
+    def prep_descs(self):
+        """Slab descriptors of this stage with the source pointer refreshed (parameters may have been re-allocated)."""
+        out = [self.prep_fwd]
+        if self.need_dgrad:
+            out.append(self.prep_dg)
+        if self.nexp:
+            out += [self.prep_nx, self.prep_nx_dg]
+        for d in out:
+            d.w = self.spec.weight.data_ptr()
+        return out
 
     def prepare(self):
-        # parameters may have been re-allocated (e.g. .to()), so refresh the source pointer
-        self.prep_fwd.w = self.spec.weight.data_ptr()
-        K.run_wprep(self.prep_fwd)
-        if self.need_dgrad:
-            self.prep_dg.w = self.spec.weight.data_ptr()
-            K.run_wprep(self.prep_dg)
+        for d in self.prep_descs():
+            K.run_wprep(d)
         if self.bias_pad is not None:
             self.bias_pad[: self.spec.Cout].copy_(self.spec.bias.detach())
 
@@ -238,6 +258,13 @@ class NetPlan:
         self.wstream = torch.cuda.Stream(device=dev) if torch.device(dev).type == "cuda" else None
         self.ev_draw = [torch.cuda.Event() for _ in range(2)] if self.wstream is not None else None
         self.ev_wg = [torch.cuda.Event() for _ in range(2)] if self.wstream is not None else None
+        # dRaw of an N-expanded head stage lives in its own buffer with a zero halo of 6 (input layout of the
+        # data-gradient kernel); nothing else writes it, so the halo stays zero
+        self.draw_nx = {}
+        for i, (s, wt) in enumerate(zip(self.specs, self.weights)):
+            if wt.nexp and not sp and i > 0:
+                _, _, ho, wo = self.geom[i]
+                self.draw_nx[i] = K.ActBuf(N, ho, wo, wt.Co_pitch, 6, dev)
         self.sync_ctr = torch.zeros(max(N, 1), dtype=torch.int32, device=dev)
         self.tbuf = [None, None]   # residual-path total gradients (ping-pong), allocated lazily
         nb = sum(N * wt.Co_pitch * 2 for wt in self.weights)
@@ -315,6 +342,14 @@ class NetPlan:
                     dst = c.out if s.final else c.act[i + 1]
                     assert dst.pad == 0
                     kw = {}
+                    if wt.nexp and self.split == 1 and dst.fp32:
+                        src = c.act[i]
+                        ca = K.conv7_args(src.hi.data_ptr(), src.C, self.N, src.Hp, src.Wp, wt.w_nx, wt.nx_CoW, 1, 4,
+                                          min(wt.nx_CoW, dst.C), dst.hi.data_ptr(), True, (dst.sN, dst.sH, dst.sW),
+                                          bias=wt.bias_pad, act=s.act, tag=4)
+                        self._args_cache[key] = (ca, None)
+                        K.run_conv7(ca)
+                        continue
                     if self._rowshift_ok(s, wt.Co_pad):      # 7x7 head: one row box feeds the 7 horizontal taps
                         table = G.taps_rowshift_fwd(s.k, s.k, 0 if s.in_halo else -s.pad)
                         kw = dict(shift_kw=s.k, shift_brow_step=1, BN=min(wt.Co_pad, 32))
@@ -324,6 +359,9 @@ class NetPlan:
                     args = (ca, None)
                 self._args_cache[key] = args
             ca, aa = args
+            if isinstance(ca, L.Conv7Args):
+                K.run_conv7(ca)
+                continue
             K.run_conv(ca)
             if aa is not None:
                 aa.drop_seed = (c.drop_seed * 1000003 + i + 1) if (s.dropout and c.drop_seed) else 0
@@ -383,7 +421,7 @@ class NetPlan:
             if wa is not None and not overlap:
                 K.run_wgrad(wa)
             if da is not None:
-                K.run_conv(da)
+                (K.run_conv7 if isinstance(da, L.Conv7Args) else K.run_conv)(da)
             if wa is not None and overlap:
                 # fork AFTER the dgrad: the side-stream wgrad then runs next to the memory-bound
                 # prep/apply kernels of stage i-1 (they co-reside with a GEMM CTA on an SM) instead of
@@ -409,6 +447,8 @@ class NetPlan:
     def _draw_view(self, i, lo=False):
         wt = self.weights[i]
         _, _, ho, wo = self.geom[i]
+        if i in self.draw_nx and not lo:
+            return self.draw_nx[i].view(interior=True)
         t = self.draws_lo[i & 1] if lo else self.draws[i & 1]
         cp = wt.Co_pitch
         return L.make_view(t.data_ptr(), self.N, ho, wo, cp, ho * wo * cp, wo * cp, cp)
@@ -458,6 +498,8 @@ class NetPlan:
             ba.stats = None
             ba.dz, ba.dz_fp32 = self.draws[i & 1].data_ptr(), 0
             ba.dz_lo = self.draws_lo[i & 1].data_ptr() if self.draws_lo[i & 1] is not None else None
+            if i in self.draw_nx:
+                ba.dz, ba.dz_pad = self.draw_nx[i].hi.data_ptr(), 6
             use_apply = False
         # ---- 2. wgrad ------------------------------------------------------------------------
         wa = None
@@ -479,7 +521,12 @@ class NetPlan:
         # ---- 3. dgrad ------------------------------------------------------------------------
         da = None
         dkw = {}
-        if (i > 0 or need_dx) and wt.need_dgrad:
+        if i in self.draw_nx and wt.need_dgrad and not self.gact[i].fp32:
+            gin, src = self.gact[i], self.draw_nx[i]
+            assert gin.pad == 3 and gin.C == 32 * wt.nx_dg_tiles
+            da = K.conv7_args(src.hi.data_ptr(), src.C, N, src.Hp, src.Wp, wt.w_nx_dg, 32, wt.nx_dg_tiles, src.C // 16, 32,
+                              gin.hi.data_ptr(), False, (gin.sN, gin.sH, gin.sW), tag=5)
+        elif (i > 0 or need_dx) and wt.need_dgrad:
             gin = self.gact[i]
             dview = self._draw_view(i)
             dlo = self.draws_lo[i & 1].data_ptr() if self.draws_lo[i & 1] is not None else None

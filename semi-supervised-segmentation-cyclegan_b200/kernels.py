@@ -171,6 +171,21 @@ def run_conv(a):
     L.check(L.lib().sscg_conv_igemm(C.byref(a), _stream()), "sscg_conv_igemm")
 
 
+def run_conv7(a):
+    L.check(L.lib().sscg_conv7_nexp(C.byref(a), _stream()), "sscg_conv7_nexp")
+
+
+def conv7_args(x_ptr, x_pitch, N, Hp, Wp, w, CoW, n_ntiles, ksteps, c_store, y_ptr, y_fp32, y_strides, bias=None,
+               act=L.ACT_NONE, tag=4):
+    a = L.Conv7Args()
+    a.x, a.x_pitch, a.N, a.Hp, a.Wp = x_ptr, x_pitch, N, Hp, Wp
+    a.w, a.CoW, a.n_ntiles, a.ksteps, a.c_store = _ptr(w), CoW, n_ntiles, ksteps, c_store
+    a.y, a.y_fp32 = y_ptr, 1 if y_fp32 else 0
+    a.y_sN, a.y_sH, a.y_sW = y_strides
+    a.bias, a.act, a.tag = _ptr(bias), act, tag
+    return a
+
+
 def run_wgrad(a):
     L.check(L.lib().sscg_conv_wgrad(C.byref(a), _stream()), "sscg_conv_wgrad")
 

@@ -83,7 +83,11 @@ class NetRunner:
 
     @staticmethod
     def _slab_elems(a):
-        return (a.KH if a.mode == 1 else a.KH * a.KW) * a.rows_pad * a.Kc
+        if a.mode in (3, 4):      # N-expanded 7x7 slabs: [kh][n tiles][NT][Kc], CoW in a.Cp
+            taps = a.KH * (((a.Co if a.mode == 3 else a.Ci) + a.Cp - 1) // a.Cp)
+        else:
+            taps = a.KH if a.mode == 1 else a.KH * a.KW
+        return taps * a.rows_pad * a.Kc
 
     def _upload_table(self, entries):
         """entries: [(WprepArgs, slab ptr, grad ptr)] -> (device byte tensor holding SscgWbatchEntry[], count, total)"""
@@ -104,11 +108,7 @@ class NetRunner:
         if self._prep_table is None or self._prep_table[0] != key:
             entries = []
             for w in self.weights:
-                w.prep_fwd.w = w.spec.weight.data_ptr()
-                entries.append((w.prep_fwd, None, None))
-                if w.need_dgrad:
-                    w.prep_dg.w = w.spec.weight.data_ptr()
-                    entries.append((w.prep_dg, None, None))
+                entries += [(d, None, None) for d in w.prep_descs()]
             self._prep_table = (key,) + self._upload_table(entries)
         _, dev, count, total = self._prep_table
         L.check(L.lib().sscg_wprep_batch(dev.data_ptr(), count, total, K._stream()), "sscg_wprep_batch")

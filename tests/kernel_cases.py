@@ -477,6 +477,65 @@ def case_seg_head(N=2, Cc=21, H=24, W=40):
     return (e if exact else 1.0), 1.0, 2e-5
 
 
+def _nexp_slab(w, mode, CoW):
+    Co, Ci = w.shape[0], w.shape[1]
+    NT = G.round_up(7 * CoW, 16)
+    nn = ((Co if mode == 3 else Ci) + CoW - 1) // CoW
+    dst = torch.zeros(7 * nn * NT * 64, dtype=torch.bfloat16, device=DEV)
+    a = K.wprep_args(w, False, Co, Ci, 7, 7, mode, CoW, NT, 64, dst)
+    K.run_wprep(a)
+    return dst, nn
+
+
+def case_conv7_nexp_fwd(N=2, H=20, W=40, Cout=21, act=L.ACT_NONE, bias=True):
+    """N-expanded 7x7 head convolution (conv_nexp.cu) vs conv2d on the reflect-padded input."""
+    _setup()
+    Cin = 64
+    x = _bf(torch.randn(N, Cin, H, W, device=DEV))
+    w = _bf(torch.randn(Cout, Cin, 7, 7, device=DEV) * 0.05)
+    b = torch.randn(Cout, device=DEV) if bias else None
+    buf = K.ActBuf(N, H, W, Cin, 3, DEV)
+    _fill_act(buf, x, L.PAD_REFLECT)
+    CoW = 8 if Cout <= 8 else (16 if Cout <= 16 else (24 if Cout <= 24 else 32))
+    slab, nn = _nexp_slab(w, 3, CoW)
+    Cp = G.pad_out_channels(Cout)
+    y = torch.zeros(N, H, W, Cp, device=DEV)
+    bias_pad = None
+    if bias:
+        bias_pad = torch.zeros(max(Cp, CoW), device=DEV)
+        bias_pad[:Cout] = b
+    a = K.conv7_args(buf.hi.data_ptr(), Cin, N, buf.Hp, buf.Wp, slab, CoW, nn, 4, min(CoW, Cp), y.data_ptr(), True,
+                     (H * W * Cp, W * Cp, Cp), bias=bias_pad, act=act)
+    K.run_conv7(a)
+    torch.cuda.synchronize()
+    ref = F.conv2d(F.pad(x, (3,) * 4, mode="reflect"), w, b)
+    if act == L.ACT_TANH:
+        ref = torch.tanh(ref)
+    return _result(y[..., :Cout].permute(0, 3, 1, 2), ref, 3e-4)
+
+
+def case_conv7_nexp_dgrad(N=2, H=20, W=40, Cout=21):
+    """Data gradient of the 7x7 head w.r.t. its halo-padded 64-channel input: N-expanded kernel on dRaw held in a
+    zero-haloed (6) buffer vs conv_transpose2d."""
+    _setup()
+    Cin = 64
+    dy = _bf(torch.randn(N, Cout, H, W, device=DEV))
+    w = _bf(torch.randn(Cout, Cin, 7, 7, device=DEV) * 0.05)
+    Cp = G.pad_out_channels(Cout)
+    buf = K.ActBuf(N, H, W, Cp, 6, DEV)
+    _fill_act(buf, dy, L.PAD_ZERO)
+    slab, nn = _nexp_slab(w, 4, 32)
+    Ho, Wo = H + 6, W + 6
+    gx = torch.zeros(N, Ho, Wo, Cin, device=DEV, dtype=torch.bfloat16)
+    a = K.conv7_args(buf.hi.data_ptr(), Cp, N, buf.Hp, buf.Wp, slab, 32, nn, Cp // 16, 32, gx.data_ptr(), False,
+                     (Ho * Wo * Cin, Wo * Cin, Cin))
+    K.run_conv7(a)
+    torch.cuda.synchronize()
+    ref = F.conv_transpose2d(dy, w)
+    err, scale, _ = _result(gx.float().permute(0, 3, 1, 2), ref, 0)
+    return err, scale, scale * 2.0 ** -8
+
+
 def case_lsgan(shape=(16, 1, 30, 30), target=1.0):
     """Fused LSGAN loss (forward mean + gradient) vs nn.MSELoss against a constant target."""
     _setup()
@@ -629,6 +688,13 @@ CASES = {
     "stream_ab_pad3": lambda: case_stream_ab(N=2, H=20, W=128, Cc=64, pad=3, skip=False, residual=False),
     "stream_ab_nopad_lrelu": lambda: case_stream_ab(N=2, H=31, W=31, Cc=512, pad=0, act=L.ACT_LRELU, skip=False,
                                                     residual=False, drop=False),
+    "conv7_nexp_fwd_c21": lambda: case_conv7_nexp_fwd(),
+    "conv7_nexp_fwd_c3_tanh": lambda: case_conv7_nexp_fwd(Cout=3, act=L.ACT_TANH),
+    "conv7_nexp_fwd_c4_odd": lambda: case_conv7_nexp_fwd(N=3, H=13, W=23, Cout=4, bias=False),
+    "conv7_nexp_fwd_big": lambda: case_conv7_nexp_fwd(N=2, H=128, W=256, Cout=19),
+    "conv7_nexp_dgrad_c21": lambda: case_conv7_nexp_dgrad(),
+    "conv7_nexp_dgrad_c3": lambda: case_conv7_nexp_dgrad(Cout=3),
+    "conv7_nexp_dgrad_big": lambda: case_conv7_nexp_dgrad(N=2, H=128, W=256, Cout=20),
     "lsgan_real": lambda: case_lsgan(),
     "lsgan_fake_odd": lambda: case_lsgan(shape=(3, 1, 7, 5), target=0.0),
     "l1_loss": lambda: case_l1(),

@@ -52,6 +52,15 @@ def key_conv(a):
     return key, flops, byts
 
 
+def key_conv7(a):
+    nt = (7 * a.CoW + 15) // 16 * 16
+    px = a.N * (a.Hp - 6) * (a.Wp - 6)
+    flops = 2.0 * a.N * (a.Hp - 6) * a.Wp * 7 * 16 * a.ksteps * nt * a.n_ntiles
+    key = "%s nexp %dx%d K=%dx7 N=%dx%d" % ({4: "fwd", 5: "dgrad"}.get(a.tag, "conv7"), a.Hp - 6, a.Wp - 6, 16 * a.ksteps, nt,
+                                            a.n_ntiles)
+    return key, flops, px * a.CoW * a.n_ntiles * (4 if a.y_fp32 else 2) + a.N * a.Hp * a.Wp * a.x_pitch * 2
+
+
 def key_wgrad(a):
     px = a.dy.N * a.dy.H * a.dy.W
     flops = 2.0 * px * a.n_taps * a.Kc * a.Co_pad
@@ -85,6 +94,7 @@ def main():
     torch.manual_seed(0)
     K.run_conv = _timed(K.run_conv, key_conv)
     K.run_wgrad = _timed(K.run_wgrad, key_wgrad)
+    K.run_conv7 = _timed(K.run_conv7, key_conv7)
     K.run_apply = _timed(K.run_apply, key_apply)
     K.run_bwd_prep = _timed(K.run_bwd_prep, key_prep)
     K.run_bwd_apply = _timed(K.run_bwd_apply, key_bapply)
