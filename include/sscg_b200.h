@@ -200,6 +200,7 @@ typedef struct SscgBwdArgs {
     float* bstats;                    /* [N][C][2] */
     int32_t dz_pad;                   /* > 0: dZ is written into a [N][H+2p][W+2p][C] buffer at offset (p, p); the halo is
                                          left untouched (kept zero by the caller: input layout of sscg_conv7_nexp's data gradient) */
+    int32_t draw_pad;                 /* same, for the dRaw output of sscg_in_bwd_apply */
 } SscgBwdArgs;
 int sscg_in_bwd_prep(const SscgBwdArgs* a, void* stream);
 int sscg_in_bwd_apply(const SscgBwdArgs* a, void* draw, void* draw_lo, void* stream);

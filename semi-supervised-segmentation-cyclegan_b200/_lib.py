@@ -84,6 +84,7 @@ class BwdArgs(C.Structure):
         ("dz_lo", C.c_void_p),
         ("bstats", C.c_void_p),
         ("dz_pad", C.c_int32),
+        ("draw_pad", C.c_int32),
     ]
 
 

@@ -460,7 +460,12 @@ __global__ void __launch_bounds__(256, SSCG_BAPPLY_MINB) in_bwd_apply_kernel(con
                 const float zz = (z[q] - mean[q]) * rstd[q];
                 g[q] = rstd[q] * (g[q] - m1[q] - zz * m2[q]);
             }
-            store8_bf16(p.draw, ANYF32 ? p.draw_lo : nullptr, off, g);
+            long long doff = off;
+            if (a.draw_pad > 0) {
+                const int h = pix / a.W, w = pix - h * a.W;
+                doff = (((long long)n * (a.H + 2 * a.draw_pad) + h + a.draw_pad) * (a.W + 2 * a.draw_pad) + w + a.draw_pad) * a.C + c0;
+            }
+            store8_bf16(p.draw, ANYF32 ? p.draw_lo : nullptr, doff, g);
         }
     }
 }

@@ -511,6 +511,11 @@ __global__ void __launch_bounds__(kStrThreads + 32, 1) in_bwd_apply_stream_kerne
         mbar_wait(ring.full(k), ring.parity(k), 13);
         const uint32_t st = ring.stage(k);
         __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(p.draw) + (long long)u * (g.ub / 2) + c0;
+        if (a.draw_pad > 0) {          // dRaw goes into a zero-haloed buffer (input of the N-expanded data gradient)
+            const UnitPos up = unit_pos(g, u);
+            obase = reinterpret_cast<__nv_bfloat16*>(p.draw) +
+                    (((long long)n * (a.H + 2 * a.draw_pad) + up.h + a.draw_pad) * (a.W + 2 * a.draw_pad) + up.w0 + a.draw_pad) * a.C + c0;
+        }
         for (int px0 = prow; px0 < g.seg_px; px0 += 2 * pstep) {
             uint4 rz[2], rg[2];
 #pragma unroll

@@ -120,6 +120,15 @@ class StageWeights:
         # data gradient; the seven horizontal taps are GEMM columns, shift-added in the epilogue
         self.nexp = (s.kind == "conv" and k == 7 and s.stride == 1 and s.in_halo == 3 and self.Cp_in == 64
                      and s.Cout <= 32 and not split and not s.norm)
+        # 7x7 stem (small Cin -> 64): only its data gradient (64 -> Cin columns) takes the N-expanded kernel
+        self.nexp_stem = (first and s.kind == "window" and k == 7 and s.stride == 1 and s.in_halo == 3 and s.Cout == 64
+                          and self.Co_pitch == 64 and s.Cin <= 32 and not split and s.norm)
+        if self.nexp_stem:
+            self.nx_CoW = 8 if s.Cin <= 8 else (16 if s.Cin <= 16 else (24 if s.Cin <= 24 else 32))
+            nt_d = G.round_up(7 * self.nx_CoW, 16)
+            self.nx_dg_tiles = 1
+            self.w_nx_dg = torch.zeros(7 * nt_d * 64, dtype=bf, device=device)
+            self.prep_nx_dg = K.wprep_args(s.weight, False, s.Cout, s.Cin, 7, 7, 4, self.nx_CoW, nt_d, 64, self.w_nx_dg)
         if self.nexp:
             self.nx_CoW = 8 if s.Cout <= 8 else (16 if s.Cout <= 16 else (24 if s.Cout <= 24 else 32))
             nt_f = G.round_up(7 * self.nx_CoW, 16)
@@ -137,6 +146,8 @@ class StageWeights:
             out.append(self.prep_dg)
         if self.nexp:
             out += [self.prep_nx, self.prep_nx_dg]
+        if self.nexp_stem:
+            out.append(self.prep_nx_dg)
         for d in out:
             d.w = self.spec.weight.data_ptr()
         return out
@@ -262,7 +273,7 @@ class NetPlan:
         # data-gradient kernel); nothing else writes it, so the halo stays zero
         self.draw_nx = {}
         for i, (s, wt) in enumerate(zip(self.specs, self.weights)):
-            if wt.nexp and not sp and i > 0:
+            if (wt.nexp and not sp and i > 0) or (wt.nexp_stem and not sp and i == 0):
                 _, _, ho, wo = self.geom[i]
                 self.draw_nx[i] = K.ActBuf(N, ho, wo, wt.Co_pitch, 6, dev)
         self.sync_ctr = torch.zeros(max(N, 1), dtype=torch.int32, device=dev)
@@ -412,11 +423,14 @@ class NetPlan:
             if overlap and wg_pending[par]:
                 main.wait_event(self.ev_wg[par])          # the wgrad that last read this dRaw buffer is done
                 wg_pending[par] = False
-            if not (use_apply and self.fused_in_bwd and
+            if not (use_apply and self.fused_in_bwd and i not in self.draw_nx and
                     K.run_bwd_fused(ba, self.draws[par], self.draws_lo[par], self.sync_ctr)):
                 K.run_bwd_prep(ba)
                 if use_apply:
-                    K.run_bwd_apply(ba, self.draws[par], self.draws_lo[par])
+                    if i in self.draw_nx:
+                        K.run_bwd_apply(ba, self.draw_nx[i].hi, None)
+                    else:
+                        K.run_bwd_apply(ba, self.draws[par], self.draws_lo[par])
             self.draw, self.draw_lo = self.draws[par], self.draws_lo[par]
             if wa is not None and not overlap:
                 K.run_wgrad(wa)
@@ -501,6 +515,8 @@ class NetPlan:
             if i in self.draw_nx:
                 ba.dz, ba.dz_pad = self.draw_nx[i].hi.data_ptr(), 6
             use_apply = False
+        if use_apply and i in self.draw_nx:
+            ba.draw_pad = 6
         # ---- 2. wgrad ------------------------------------------------------------------------
         wa = None
         if need_dw:
@@ -521,7 +537,12 @@ class NetPlan:
         # ---- 3. dgrad ------------------------------------------------------------------------
         da = None
         dkw = {}
-        if i in self.draw_nx and wt.need_dgrad and not self.gact[i].fp32:
+        if i == 0 and i in self.draw_nx and need_dx and wt.need_dgrad:
+            gin, src = self.gact[0], self.draw_nx[0]          # fp32 gradient w.r.t. the halo-padded network input
+            assert gin.pad == 3 and gin.fp32 and gin.C >= wt.nx_CoW
+            da = K.conv7_args(src.hi.data_ptr(), src.C, N, src.Hp, src.Wp, wt.w_nx_dg, wt.nx_CoW, 1, 4, wt.nx_CoW,
+                              gin.hi.data_ptr(), True, (gin.sN, gin.sH, gin.sW), tag=5)
+        elif i in self.draw_nx and i > 0 and wt.need_dgrad and not self.gact[i].fp32:
             gin, src = self.gact[i], self.draw_nx[i]
             assert gin.pad == 3 and gin.C == 32 * wt.nx_dg_tiles
             da = K.conv7_args(src.hi.data_ptr(), src.C, N, src.Hp, src.Wp, wt.w_nx_dg, 32, wt.nx_dg_tiles, src.C // 16, 32,
