@@ -28,6 +28,8 @@ struct NexpDev {
     int NT;             // GEMM N of one tile = round_up(7 * CoW, 16)
     int CoW;            // output columns per horizontal tap in one N tile
     int ksteps;         // 16-channel K steps per vertical tap (1, 2 or 4)
+    int row_bytes;      // 32 * ksteps: operand rows are exactly as wide as the channels that enter the contraction,
+                        // with the matching swizzle (128B / 64B / 32B) for TMA and the UMMA descriptors
     int stages;
     void* y;
     int y_fp32;
@@ -40,15 +42,38 @@ struct NexpDev {
 
 constexpr int kNxTileM = 128;
 constexpr int kNxOut = 122;               // outputs per tile (128 - 6 halo pixels)
-constexpr int kNxABytes = kNxTileM * 128;
+
+// K-major operand descriptor for rows of 128 / 64 / 32 bytes (SWIZZLE_128B / 64B / 32B): 8-row atoms, SBO = 8 rows
+__device__ __forceinline__ uint64_t nexp_desc(uint32_t saddr, int row_bytes) {
+    const uint64_t layout = row_bytes == 128 ? 2 : (row_bytes == 64 ? 4 : 6);
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((saddr >> 4) & 0x3fff);
+    d |= static_cast<uint64_t>(((8u * row_bytes) >> 4) & 0x3fff) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= layout << 61;
+    return d;
+}
+
+// explicit shared-space accesses: the staging buffer is carved out of dynamic shared memory through integer
+// arithmetic, which makes the compiler fall back to generic LD / ST (address translation, long scoreboard)
+__device__ __forceinline__ void sts_f32(uint32_t saddr, float v) {
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(saddr), "f"(v) : "memory");
+}
+__device__ __forceinline__ float lds_f32(uint32_t saddr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr));
+    return v;
+}
 
 __global__ void __launch_bounds__(192, 1)
 conv_nexp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ NexpDev p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const int b_bytes = p.NT * 128;
-    const int stage_bytes = kNxABytes + ((b_bytes + 1023) & ~1023);
+    const int a_bytes = kNxTileM * p.row_bytes;
+    const int b_bytes = p.NT * p.row_bytes;
+    const int stage_bytes = ((a_bytes + 1023) & ~1023) + ((b_bytes + 1023) & ~1023);
+    const int b_off = (a_bytes + 1023) & ~1023;
     float* S = reinterpret_cast<float*>(smem + p.stages * stage_bytes);
     const int s_pitch = p.NT + 1;                       // odd: conflict-free row-wise stores and diagonal reads
     uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(S) + ((kNxTileM * s_pitch * 4 + 15) & ~15));
@@ -57,6 +82,7 @@ conv_nexp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint64_t* tmem_full_bar = bars + 8;        // [2]
     uint64_t* tmem_empty_bar = bars + 10;      // [2]
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 12);
+    float* bias_sm = reinterpret_cast<float*>(bars + 14);          // up to 64 output channels
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -80,6 +106,10 @@ conv_nexp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tmem_alloc(smem_u32(tmem_ptr_smem), tmem_cols);
         tmem_relinquish();
     }
+    if (warp >= 2 && p.bias != nullptr) {
+        const int e = threadIdx.x - 64;
+        if (e < p.n_ntiles * p.CoW && e < 64) bias_sm[e] = p.bias[e];
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -90,7 +120,7 @@ conv_nexp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // ================================ TMA producer ==========================================
         if (lane == 0) {
             int stage = 0; uint32_t par = 0;
-            const uint32_t tx = (uint32_t)(kNxABytes + b_bytes);
+            const uint32_t tx = (uint32_t)(a_bytes + b_bytes);
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
                 const int nt = tile % p.n_ntiles;
                 const int rest = tile / p.n_ntiles;
@@ -102,7 +132,7 @@ conv_nexp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     mbar_arrive_expect_tx(fb, tx);
                     uint8_t* st = smem + stage * stage_bytes;
                     tma_load_2d(smem_u32(st), &tmA, fb, 0, px0 + (kh - 3) * p.Wp);
-                    tma_load_2d(smem_u32(st + kNxABytes), &tmB, fb, 0, (kh * p.n_ntiles + nt) * p.NT);
+                    tma_load_2d(smem_u32(st + b_off), &tmB, fb, 0, (kh * p.n_ntiles + nt) * p.NT);
                     if (++stage == p.stages) { stage = 0; par ^= 1; }
                 }
             }
@@ -124,8 +154,8 @@ conv_nexp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     mbar_wait(smem_u32(&full_bar[stage]), par, 23);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + stage * stage_bytes);
-                    const uint64_t da = make_smem_desc_sw128(sa, 0, 1024);
-                    const uint64_t db = make_smem_desc_sw128(sa + kNxABytes, 0, 1024);
+                    const uint64_t da = nexp_desc(sa, p.row_bytes);
+                    const uint64_t db = nexp_desc(sa + b_off, p.row_bytes);
                     for (int k = 0; k < p.ksteps; ++k) {
                         umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, accum);
                         accum = 1;
@@ -140,7 +170,9 @@ conv_nexp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // ================================ epilogue ==============================================
         const int quad = warp & 3;
         const int m = quad * 32 + lane;            // TMEM lane = tile pixel
-        float* srow = S + m * s_pitch;
+        const uint32_t s_base = smem_u32(S);
+        const uint32_t bias_s = smem_u32(bias_sm);
+        const uint32_t srow = s_base + (uint32_t)(m * s_pitch) * 4u;
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
             const int nt = tile % p.n_ntiles;
@@ -151,16 +183,23 @@ conv_nexp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             mbar_wait(smem_u32(&tmem_full_bar[acc]), acc_par, 24);
             tc_fence_after();
             const uint32_t t_acc = tmem_base + acc * acc_cols + (static_cast<uint32_t>(quad * 32) << 16);
-            // ---- accumulator -> staging buffer (row m) --------------------------------------------
-            for (int c0 = 0; c0 < p.NT; c0 += 32) {
-                uint32_t r[32];
-                const int w = p.NT - c0 >= 32 ? 32 : 16;
-                if (w == 32) tmem_ld_32x32(t_acc + c0, r);
-                else tmem_ld_32x16(t_acc + c0, r);
+            // ---- accumulator -> staging buffer (row m), two 32-column TMEM loads in flight ------------------
+            for (int c0 = 0; c0 < p.NT; c0 += 64) {
+                uint32_t r0[32], r1[32];
+                const int w0 = p.NT - c0 >= 32 ? 32 : 16;
+                const int rem = p.NT - c0 - 32;
+                const int w1 = rem >= 32 ? 32 : (rem >= 16 ? 16 : 0);
+                if (w0 == 32) tmem_ld_32x32(t_acc + c0, r0);
+                else tmem_ld_32x16(t_acc + c0, r0);
+                if (w1 == 32) tmem_ld_32x32(t_acc + c0 + 32, r1);
+                else if (w1 == 16) tmem_ld_32x16(t_acc + c0 + 32, r1);
                 tmem_ld_wait();
 #pragma unroll
                 for (int q = 0; q < 32; ++q)
-                    if (q < w) srow[c0 + q] = __uint_as_float(r[q]);
+                    if (q < w0) sts_f32(srow + (uint32_t)(c0 + q) * 4u, __uint_as_float(r0[q]));
+#pragma unroll
+                for (int q = 0; q < 32; ++q)
+                    if (q < w1) sts_f32(srow + (uint32_t)(c0 + 32 + q) * 4u, __uint_as_float(r1[q]));
             }
             tc_fence_before();
             mbar_arrive(smem_u32(&tmem_empty_bar[acc]));          // accumulator drained
@@ -173,18 +212,25 @@ conv_nexp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const long long yoff = (long long)n * p.y_sN + (long long)(orow - 3) * p.y_sH +
                                        (long long)(ocol - 3) * p.y_sW + nt * p.y_c0_step;
                 for (int c0 = 0; c0 < p.c_store; c0 += 8) {
+                    // all 56 staged values first (the loads are ordered volatile asm: adding as they arrive would
+                    // expose one shared-memory latency per value), then the sums in tap order
+                    float tv[7][8];
+#pragma unroll
+                    for (int kw = 0; kw < 7; ++kw) {
+                        const uint32_t src = s_base + (uint32_t)((m + kw) * s_pitch + kw * p.CoW + c0) * 4u;
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) tv[kw][q] = lds_f32(src + 4u * q);
+                    }
                     float v[8];
 #pragma unroll
                     for (int q = 0; q < 8; ++q) v[q] = 0.f;
 #pragma unroll
-                    for (int kw = 0; kw < 7; ++kw) {
-                        const float* src = S + (m + kw) * s_pitch + kw * p.CoW + c0;
+                    for (int kw = 0; kw < 7; ++kw)
 #pragma unroll
-                        for (int q = 0; q < 8; ++q) v[q] += src[q];
-                    }
+                        for (int q = 0; q < 8; ++q) v[q] += tv[kw][q];
                     if (p.bias != nullptr) {
 #pragma unroll
-                        for (int q = 0; q < 8; ++q) v[q] += __ldg(p.bias + nt * p.y_c0_step + c0 + q);
+                        for (int q = 0; q < 8; ++q) v[q] += lds_f32(bias_s + 4u * (uint32_t)(nt * p.y_c0_step + c0 + q));
                     }
                     if (p.act == SSCG_ACT_TANH) {
 #pragma unroll
@@ -216,17 +262,19 @@ conv_nexp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 }
 
 static int encode_2d_pitch(CUtensorMap* tm, const void* ptr, long long rows, long long pitch_elems, int box_cols,
-                           int box_rows) {
+                           int box_rows, long long dim0 = 0) {
     PFN_encodeTiled enc = get_encode_tiled();
     if (!enc) return 1;
-    cuuint64_t dims[2] = {(cuuint64_t)box_cols, (cuuint64_t)rows};
+    cuuint64_t dims[2] = {(cuuint64_t)(dim0 > 0 ? dim0 : box_cols), (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)pitch_elems * 2};
+    const CUtensorMapSwizzle sw = box_cols == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                 : (box_cols == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
     cuuint32_t b[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     cuuint32_t s[2] = {1, 1};
     if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (strides[0] & 15))
         return set_error("conv7_nexp: activation pointer/pitch must be 16-byte aligned");
     CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, b, s,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS)
         return set_error("conv7_nexp: cuTensorMapEncodeTiled failed: %d rows=%lld pitch=%lld", (int)r, rows, pitch_elems);
@@ -244,6 +292,7 @@ extern "C" int sscg_conv7_nexp(const SscgConv7Args* a, void* stream_) {
     if (a->CoW % 8 || a->CoW < 8 || a->CoW > 32) return set_error("conv7_nexp: CoW=%d must be 8, 16, 24 or 32", a->CoW);
     if (a->c_store % 8 || a->c_store > a->CoW) return set_error("conv7_nexp: c_store=%d", a->c_store);
     if (a->Hp < 7 || a->Wp < 7 || a->N < 1 || a->n_ntiles < 1) return set_error("conv7_nexp: bad geometry");
+    if (a->bias && a->n_ntiles * a->CoW > 64) return set_error("conv7_nexp: bias supports up to 64 output channels");
     NexpDev d;
     d.N = a->N; d.Hp = a->Hp; d.Wp = a->Wp;
     d.CoW = a->CoW;
@@ -258,9 +307,10 @@ extern "C" int sscg_conv7_nexp(const SscgConv7Args* a, void* stream_) {
     d.y_c0_step = a->CoW;
     d.c_store = a->c_store;
     d.bias = a->bias; d.act = a->act;
-    const int b_bytes = d.NT * 128;
-    const int stage_bytes = kNxABytes + ((b_bytes + 1023) & ~1023);
-    const int s_bytes = ((kNxTileM * (d.NT + 1) * 4 + 15) & ~15) + 256;
+    d.row_bytes = 32 * a->ksteps;
+    const int a_bytes = kNxTileM * d.row_bytes, b_bytes = d.NT * d.row_bytes;
+    const int stage_bytes = ((a_bytes + 1023) & ~1023) + ((b_bytes + 1023) & ~1023);
+    const int s_bytes = ((kNxTileM * (d.NT + 1) * 4 + 15) & ~15) + 512;
     int stages = (225 * 1024 - 1024 - s_bytes) / stage_bytes;
     if (stages > 4) stages = 4;
     if (stages < 2) return set_error("conv7_nexp: tile does not fit shared memory (NT=%d)", d.NT);
@@ -269,8 +319,9 @@ extern "C" int sscg_conv7_nexp(const SscgConv7Args* a, void* stream_) {
 
     CUtensorMap tmA, tmB;
     const long long rows = (long long)a->N * a->Hp * a->Wp;
-    if (int rc = encode_2d_pitch(&tmA, a->x, rows, a->x_pitch, 64, kNxTileM)) return rc;
-    if (int rc = encode_2d(&tmB, a->w, 64, 7 * d.n_ntiles * d.NT, 64, d.NT)) return rc;
+    const int kcols = 16 * a->ksteps;
+    if (int rc = encode_2d_pitch(&tmA, a->x, rows, a->x_pitch, kcols, kNxTileM)) return rc;
+    if (int rc = encode_2d_pitch(&tmB, a->w, 7LL * d.n_ntiles * d.NT, 64, kcols, d.NT, 64)) return rc;
 
     static int max_smem_set = 0;
     if (smem > max_smem_set) {
