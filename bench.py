@@ -336,12 +336,19 @@ def run_ours(args):
     tf_step = (fwd + bwd) * args.batch / 1e12
     res_ms, res_n = prof.get("res_conv_fwd", (0.0, 0))
     roof = None
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")     # dram bytes of the same kernel from `ncu --set full`
+    if os.path.exists(tpath) and args.batch == BATCH:
+        with open(tpath) as f:
+            tj = json.load(f)
+        traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source")
     if res_n:
         achieved = res_conv_flops(args.batch) / 1e12 / (res_ms / res_n / 1e3)
         peak = peaks["bf16_tflops_sustained"]
         roof = {"bound": "tensor", "kernel": "conv_igemm_kernel<256,1>: 3x3 256->256 @64x64 residual-block conv, forward "
                                              "(108 launches per step)",
-                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+                "traffic_source": traffic_src,
                 "peak_source": peak_src + " (sustained cuBLAS bf16: kernel timed inside a long step)",
                 "avg_launch_ms": res_ms / res_n, "launches_timed": res_n,
                 "algorithmic_flops_per_launch": res_conv_flops(args.batch),

@@ -1,0 +1,73 @@
+"""Turn `ncu --set full` reports into the markdown summary committed under profiles/ (and the traffic record
+bench.py reads).  Usage: python tools/summarize_ncu_full.py out.md a.ncu-rep [b.ncu-rep ...]"""
+import csv
+import json
+import os
+import re
+import subprocess
+import sys
+
+KEYS = ["gpu__time_duration.sum", "sm__cycles_elapsed.max", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__pipe_tc_cycles_active.avg.pct_of_peak_sustained_active", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+        "l1tex__m_xbar2l1tex_read_bytes.sum", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__grid_size",
+        "launch__block_size", "launch__shared_mem_per_block_dynamic", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"]
+
+
+def to_bytes(v, unit):
+    f = float(v.replace(",", ""))
+    return f * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
+
+
+def main(out, reps):
+    lines = ["# ncu --set full captures (--clock-control none), one training step of configs[1] (bs 16, 256x256, bf16)\n",
+             "Per kernel: the first captured launch of every distinct (name, grid) and how many launches of it were captured.\n"]
+    traffic = None
+    for rep in reps:
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        rows = list(csv.reader([l for l in raw.splitlines() if not l.startswith("==")]))
+        if len(rows) < 3:
+            continue
+        hdr, units = rows[0], rows[1]
+        seen = {}
+        for r in rows[2:]:
+            name = r[hdr.index("Kernel Name")]
+            m = re.search(r"(\w+_kernel(<[^>]*>)?)", name)
+            short = m.group(1) if m else name[:60]
+            key = (short, r[hdr.index("launch__grid_size")] if "launch__grid_size" in hdr else "")
+            seen.setdefault(key, [r, 0])[1] += 1
+            if short.startswith("conv_igemm_kernel<256, 1, 0>") and "full_fwd" in rep:
+                # launch order of a generator forward: ... down2 (first <256> launch), then the residual-block convs:
+                # keep the LAST captured one = a 3x3 256->256 @64x64 residual conv, the kernel bench.py's roofline names
+                i, j = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+                traffic = {"kernel": short + " (3x3 256->256 @64x64 residual-block conv, forward)",
+                           "dram_bytes_read": to_bytes(r[i], units[i]), "dram_bytes_write": to_bytes(r[j], units[j]),
+                           "gpu_time_us": r[hdr.index("gpu__time_duration.sum")],
+                           "tensor_pipe_pct": r[hdr.index("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active")]}
+                traffic["dram_bytes_per_launch"] = traffic["dram_bytes_read"] + traffic["dram_bytes_write"]
+                traffic["source"] = "profiles/%s (%s): last captured launch of %s" % (os.path.basename(out), os.path.basename(rep), short)
+        lines.append("\n## %s\n" % os.path.basename(rep))
+        for (short, grid), (r, cnt) in seen.items():
+            lines.append("### `%s` (captured launches: %d)\n" % (short, cnt))
+            for k in KEYS:
+                if k in hdr:
+                    i = hdr.index(k)
+                    lines.append("- %s = %s %s" % (k, r[i], units[i]))
+            lines.append("")
+    if traffic:
+        lines.append("\n## dominant kernel (bench.py `roofline`)\n")
+        lines.append("`%s`: %s us, tensor pipe active %s %%, DRAM read %.1f MB + write %.1f MB per launch "
+                     "(algorithmic: 35.7 MB halo-padded input + 1.2 MB weights read once; the 33.5 MB bf16 output stays in "
+                     "the 126 MB L2 for the normalisation pass that follows)." %
+                     (traffic["kernel"], traffic["gpu_time_us"], traffic["tensor_pipe_pct"], traffic["dram_bytes_read"] / 1e6,
+                      traffic["dram_bytes_write"] / 1e6))
+    with open(out, "w") as f:
+        f.write("\n".join(lines) + "\n")
+    if traffic:
+        with open(os.path.join(os.path.dirname(out), "r01_ncu_traffic.json"), "w") as f:
+            json.dump(traffic, f, indent=1)
+
+
+if __name__ == "__main__":
+    main(sys.argv[1], sys.argv[2:])
