@@ -235,7 +235,18 @@ def run_ours(args):
         # NCCL prints its version banner to STDOUT at debug levels VERSION and WARN, in front of the JSON line
         if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
             os.environ.pop("NCCL_DEBUG")
-        dist.init_process_group("nccl", device_id=dev)
+        # ... and whatever the environment says, keep fd 1 clean while the communicator comes up (created eagerly here)
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.all_reduce(torch.zeros(1, device=dev))
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     import sscg_b200  # noqa: F401
     from sscg_b200 import kernels as K
     from sscg_b200.step import GraphedStep, SemiSupCycleGAN
