@@ -297,6 +297,11 @@ int sscg_l1_bwd(const float* x, const float* y, int64_t n, const float* dloss, f
 int sscg_adam_flat(float* p, const float* g, float* m, float* v, int64_t n, const float* lr, float beta1, float beta2,
                    float eps, const float* step, void* stream);
 
+/* sscg_confusion: hist[t * n_class + p] += #{i : label_true[i] == t, label_pred[i] == p, 0 <= t, p < n_class} —
+ * the device form of runningScore._fast_hist (utils.py:363-369) used by the validation loop (model.py:555-572). */
+int sscg_confusion(const int64_t* label_true, const int64_t* label_pred, int64_t n, int32_t n_class, uint64_t* hist,
+                   void* stream);
+
 /* utility */
 int sscg_fill_zero(void* ptr, int64_t bytes, void* stream);
 const char* sscg_last_error(void);

@@ -3,6 +3,7 @@ NLayerDiscriminator (reference arch/discriminators.py:42-63) and the define_Dis 
 (reference arch/discriminators.py:84-101).  `pixel` (discriminators.py:66-80) is kept routable as a
 small stock-torch module because HEAD's training loop instantiates it (model.py:220-222,229).
 """
+import torch
 import torch.nn as nn
 
 from .. import _lib as L
@@ -58,6 +59,15 @@ class NLayerDiscriminator(nn.Module):
         if input.is_cuda and self.fusable:
             return self._runner(input, self.training, False, self.precision)
         return self.dis_model(input)
+
+    def forward_onehot(self, labels):
+        """forward(make_one_hot(labels, input_nc)) for an int64 label map N x 1 x H x W (model.py:435-438,506-512)
+        without materialising the one-hot tensor on the fused path."""
+        if labels.is_cuda and self.fusable:
+            return self._runner(labels.long(), self.training, False, self.precision)
+        one_hot = torch.zeros(labels.size(0), self.input_nc, labels.size(2), labels.size(3), dtype=torch.float32,
+                              device=labels.device).scatter_(1, labels.long(), 1)
+        return self.forward(one_hot)
 
 
 class PixelDiscriminator(nn.Module):

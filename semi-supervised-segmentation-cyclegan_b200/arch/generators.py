@@ -77,6 +77,15 @@ class ResnetGenerator(nn.Module):
             return self._runner(x, self.training, self.use_dropout, self.precision)
         return self.res_model(x)
 
+    def forward_onehot(self, labels):
+        """forward(make_one_hot(labels, input_nc)) for an int64 label map N x 1 x H x W (model.py:385) without
+        materialising the one-hot tensor on the fused path."""
+        if labels.is_cuda and self.fusable:
+            return self._runner(labels.long(), self.training, self.use_dropout, self.precision)
+        one_hot = torch.zeros(labels.size(0), self.input_nc, labels.size(2), labels.size(3), dtype=torch.float32,
+                              device=labels.device).scatter_(1, labels.long(), 1)
+        return self.forward(one_hot)
+
 
 def _residual_plan(specs):
     """Backward routing of the residual skip connections (x + block(x), reference ops.py:73-74).

@@ -212,6 +212,25 @@ __global__ void __launch_bounds__(256) adam_flat_kernel(float* __restrict__ p, c
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Confusion matrix of a label map against its prediction (utils.py:357-372, runningScore._fast_hist:
+// np.bincount(n_class * true[mask] + pred[mask]) with mask = 0 <= true < n_class), accumulated on the device:
+// per-block histogram in shared memory, one 64-bit atomic per non-empty bin and block.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) confusion_kernel(const long long* __restrict__ lt, const long long* __restrict__ lp,
+                                                        long long n, int C, unsigned long long* __restrict__ hist) {
+    __shared__ unsigned int s_hist[kMaxClasses * kMaxClasses];
+    for (int i = threadIdx.x; i < C * C; i += blockDim.x) s_hist[i] = 0u;
+    __syncthreads();
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const long long t = lt[i], p = lp[i];
+        if (t >= 0 && t < C && p >= 0 && p < C) atomicAdd(&s_hist[(int)t * C + (int)p], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < C * C; i += blockDim.x)
+        if (s_hist[i]) atomicAdd(&hist[i], (unsigned long long)s_hist[i]);
+}
 }  // namespace sscg
 
 using namespace sscg;
@@ -310,5 +329,19 @@ extern "C" int sscg_adam_flat(float* p, const float* g, float* m, float* v, int6
                                                                                          eps, step);
     }
     SSCG_LOSS_LAUNCH_CHECK("adam_flat");
+    return 0;
+}
+
+extern "C" int sscg_confusion(const int64_t* label_true, const int64_t* label_pred, int64_t n, int32_t n_class,
+                              uint64_t* hist, void* stream) {
+    if (!label_true || !label_pred || !hist || n < 1) return set_error("confusion: bad arguments");
+    if (n_class < 1 || n_class > kMaxClasses) return set_error("confusion: n_class=%d must be in [1, %d]", n_class, kMaxClasses);
+    {
+        LaunchScope ls_(10, static_cast<cudaStream_t>(stream));
+        confusion_kernel<<<loss_grid(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+            reinterpret_cast<const long long*>(label_true), reinterpret_cast<const long long*>(label_pred), n, n_class,
+            reinterpret_cast<unsigned long long*>(hist));
+    }
+    SSCG_LOSS_LAUNCH_CHECK("confusion");
     return 0;
 }

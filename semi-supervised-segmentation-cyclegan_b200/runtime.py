@@ -158,6 +158,9 @@ class NetRunner:
         return p
 
     def __call__(self, x, training, use_dropout, precision=None):
+        """x: NCHW fp32, or an int64 label map N x 1 x H x W that stands for its one-hot encoding over the
+        network's input channels (make_one_hot, utils.py:314-350): the first stage's operand buffer is then written
+        straight from the labels (sscg_onehot_pack) and no N x C x H x W fp32 tensor is materialised."""
         if not x.is_cuda:
             raise RuntimeError("fused path needs CUDA tensors")
         self._setup(x.device, precision or _DEFAULT_PRECISION)
@@ -185,7 +188,8 @@ class _FusedNet(torch.autograd.Function):
     @staticmethod
     def forward(ctx, runner: NetRunner, dropout_on, x, *params):
         x = x.detach()
-        if x.dtype != torch.float32:
+        labels = x.dtype == torch.int64
+        if not labels and x.dtype != torch.float32:
             x = x.float()
         x = x.contiguous()
         N, _, H, W = x.shape
@@ -195,7 +199,11 @@ class _FusedNet(torch.autograd.Function):
         seed = 0
         if dropout_on:
             seed = int(torch.randint(1, 2 ** 31 - 1, (1,)).item())   # CPU generator: follows torch.manual_seed
-        plan.forward(c, x, training=dropout_on, drop_seed=seed)
+        if labels:
+            assert x.shape[1] == 1, "label maps are N x 1 x H x W"
+            plan.forward(c, labels=x, n_classes=runner.specs[0].Cin, training=dropout_on, drop_seed=seed)
+        else:
+            plan.forward(c, x, training=dropout_on, drop_seed=seed)
         y = plan.output_nchw(c)
         # (grad mode is always off inside Function.forward; needs_input_grad already reflects no_grad())
         need_grad = any(ctx.needs_input_grad[2:])

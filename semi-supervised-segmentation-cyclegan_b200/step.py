@@ -231,7 +231,9 @@ class SemiSupCycleGAN:
         if head:
             set_grad([self.old_Gsi, self.old_Gis], False)                                # :380
         self.g_grads.zero()                                                              # :381
-        fake_img = self.Gis(make_one_hot(l_gt, C).float())                               # :385
+        onehot_in = l_img.is_cuda     # label glue: one-hot inputs go in as label maps (arch.*.forward_onehot)
+        fake_img = (self.Gis.forward_onehot(l_gt) if onehot_in
+                    else self.Gis(make_one_hot(l_gt, C).float()))                        # :385
         fake_gt = self.Gsi(unl_img.float())                                              # :386
         lab_gt = self.Gsi(l_img)                                                         # :387
         assert fake_img.shape[2:] == l_img.shape[2:] and fake_gt.shape[2:] == l_img.shape[2:]   # interp == identity
@@ -256,8 +258,11 @@ class SemiSupCycleGAN:
                 resnet_recon_img = self.old_Gis(resnet_fake_gt.float())
                 self.old_Gis(resnet_lab_gt.float())                                      # resnet_recon_lab_img: unused
         fake_img_dis = self.Di(fake_img)                                                 # :431
-        fake_gt_disc = make_one_hot(fake_gt_arg.unsqueeze(1), C)                         # :435-437
-        fake_gt_dis = self.Ds(fake_gt_disc.float())                                      # :438
+        if onehot_in:
+            fake_gt_dis = self.Ds.forward_onehot(fake_gt_arg.unsqueeze(1))               # :435-438
+        else:
+            fake_gt_disc = make_one_hot(fake_gt_arg.unsqueeze(1), C)                     # :435-437
+            fake_gt_dis = self.Ds(fake_gt_disc.float())                                  # :438
         if fused:     # fused LSGAN / L1 kernels (losses.py): scalar target, one pass forward, one backward
             MSE1 = lambda t: lsgan_loss(t, 1.0)
             MSE0 = lambda t: lsgan_loss(t, 0.0)
@@ -302,9 +307,13 @@ class SemiSupCycleGAN:
             fake_gt = self.pool_fake_gt([fake_gt.detach()])[0]                           # :493
         unl_img_dis = self.Di(unl_img)                                                   # :499
         fake_img_dis = self.Di(fake_img)                                                 # :500
-        real_gt_dis = self.Ds(make_one_hot(l_gt, C).float())                             # :506-507
-        fake_gt_disc = make_one_hot(fake_gt.data.max(1)[1].unsqueeze(1), C)              # :509-511
-        fake_gt_dis = self.Ds(fake_gt_disc.float())                                      # :512
+        if onehot_in:
+            real_gt_dis = self.Ds.forward_onehot(l_gt)                                   # :506-507
+            fake_gt_dis = self.Ds.forward_onehot(fake_gt.data.max(1)[1].unsqueeze(1))    # :509-512
+        else:
+            real_gt_dis = self.Ds(make_one_hot(l_gt, C).float())                         # :506-507
+            fake_gt_disc = make_one_hot(fake_gt.data.max(1)[1].unsqueeze(1), C)          # :509-511
+            fake_gt_dis = self.Ds(fake_gt_disc.float())                                  # :512
         img_dis_loss = (MSE1(unl_img_dis) + MSE0(fake_img_dis)) * 0.5                    # :521-522,531
         gt_dis_loss = (MSE1(real_gt_dis) + MSE0(fake_gt_dis)) * 0.5                      # :523-524,532
         if head:
