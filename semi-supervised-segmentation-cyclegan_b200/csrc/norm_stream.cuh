@@ -219,8 +219,9 @@ __global__ void __launch_bounds__(kStrThreads + 32, 1) in_apply_stream_kernel(co
                 }
                 if (seed != 0) {
                     const uint32_t bits = drop_bits(seed, (unsigned long long)(spix0 + w) * g.CH + chunk);
+                    // keep -> x2, drop -> x0: bit q moved to the exponent position of 2.0f (0x40000000)
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) v[q] = ((bits >> q) & 1u) ? 2.f * v[q] : 0.f;
+                    for (int q = 0; q < 8; ++q) v[q] *= __uint_as_float(((bits >> q) & 1u) << 30);
                 }
                 if (has_res) {
                     float r8[8];

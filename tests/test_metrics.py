@@ -95,7 +95,9 @@ def test_forward_onehot_gpu_equals_one_hot_forward():
     for net in (g, d):
         ya = net.forward_onehot(lab)
         yb = net(oh)
-        assert float((ya - yb).abs().max()) == 0.0          # the packed operand is bit-identical
+        # the packed operand is bit-identical; the InstanceNorm sums are accumulated with atomics, so two runs of the
+        # same network differ in the last bits of the statistics (and by an occasional bf16 rounding downstream)
+        assert float((ya - yb).abs().max()) <= 2e-2 * float(yb.abs().max())
         ya.square().mean().backward()                        # weight gradients flow with a label-map input
         w = next(net.parameters())
         assert w.grad is not None and bool(torch.isfinite(w.grad).all()) and float(w.grad.abs().max()) > 0
