@@ -260,7 +260,8 @@ typedef struct SscgConv7Args {
 int sscg_conv7_nexp(const SscgConv7Args* a, void* stream);
 
 /* Batched forms: ONE launch over a DEVICE table of descriptors (every slab of a network).  `start` is the
- * running element offset of the entry (entries sorted by start; total = sum of ntaps * rows_pad * Kc);
+ * running (row, k) offset of the entry (entries sorted by start; total = sum of rows_pad * Kc — a thread owns one
+ * (row, k) position and walks the taps);
  * slab / grad are used by the gradient form only.  Same arithmetic as the per-slab calls above. */
 typedef struct SscgWbatchEntry {
     SscgWprepArgs a;

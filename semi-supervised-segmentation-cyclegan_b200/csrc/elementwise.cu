@@ -272,6 +272,10 @@ __device__ __forceinline__ int wbatch_find(const SscgWbatchEntry* __restrict__ t
     }
     return lo;
 }
+// A thread owns one (row, k) position of a slab and walks the taps: for the fixed (co, ci) pair the taps are
+// adjacent in the PyTorch weight layout, so the strided 4-byte gathers of a warp hit the same sectors on every
+// tap (L1) instead of touching 9-49x the useful bytes, and every store of a warp is one contiguous run.
+// `start` / `total` count (row, k) positions: rows_pad * Kc per entry.
 __global__ void wprep_batch_kernel(const SscgWbatchEntry* __restrict__ tab, int count, long long total) {
     for (long long gidx = blockIdx.x * (long long)blockDim.x + threadIdx.x; gidx < total;
          gidx += (long long)gridDim.x * blockDim.x) {
@@ -279,14 +283,17 @@ __global__ void wprep_batch_kernel(const SscgWbatchEntry* __restrict__ tab, int 
         const SscgWprepArgs& a = e.a;
         const long long idx = gidx - e.start;
         const int k = idx % a.Kc;
-        const int r = (idx / a.Kc) % a.rows_pad;
-        const int t = idx / ((long long)a.Kc * a.rows_pad);
-        const long long s = wslab_src_index(a, t, r, k);
-        const float v = s >= 0 ? a.w[s] : 0.f;
-        const __nv_bfloat16 h = __float2bfloat16_rn(v);
-        reinterpret_cast<__nv_bfloat16*>(a.dst)[idx] = h;
-        if (a.dst_lo != nullptr)
-            reinterpret_cast<__nv_bfloat16*>(a.dst_lo)[idx] = __float2bfloat16_rn(v - __bfloat162float(h));
+        const int r = idx / a.Kc;
+        const int nt = wslab_ntaps(a);
+        const long long plane = (long long)a.rows_pad * a.Kc;
+        for (int t = 0; t < nt; ++t) {
+            const long long s = wslab_src_index(a, t, r, k);
+            const float v = s >= 0 ? a.w[s] : 0.f;
+            const __nv_bfloat16 h = __float2bfloat16_rn(v);
+            reinterpret_cast<__nv_bfloat16*>(a.dst)[t * plane + idx] = h;
+            if (a.dst_lo != nullptr)
+                reinterpret_cast<__nv_bfloat16*>(a.dst_lo)[t * plane + idx] = __float2bfloat16_rn(v - __bfloat162float(h));
+        }
     }
 }
 __global__ void wgrad_unpack_batch_kernel(const SscgWbatchEntry* __restrict__ tab, int count, long long total, float scale) {
@@ -296,10 +303,13 @@ __global__ void wgrad_unpack_batch_kernel(const SscgWbatchEntry* __restrict__ ta
         const SscgWprepArgs& a = e.a;
         const long long idx = gidx - e.start;
         const int k = idx % a.Kc;
-        const int r = (idx / a.Kc) % a.rows_pad;
-        const int t = idx / ((long long)a.Kc * a.rows_pad);
-        const long long s = wslab_src_index(a, t, r, k);
-        if (s >= 0) e.grad[s] += scale * e.slab[idx];
+        const int r = idx / a.Kc;
+        const int nt = wslab_ntaps(a);
+        const long long plane = (long long)a.rows_pad * a.Kc;
+        for (int t = 0; t < nt; ++t) {
+            const long long s = wslab_src_index(a, t, r, k);
+            if (s >= 0) e.grad[s] += scale * e.slab[t * plane + idx];
+        }
     }
 }
 

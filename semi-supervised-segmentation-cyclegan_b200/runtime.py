@@ -83,11 +83,8 @@ class NetRunner:
 
     @staticmethod
     def _slab_elems(a):
-        if a.mode in (3, 4):      # N-expanded 7x7 slabs: [kh][n tiles][NT][Kc], CoW in a.Cp
-            taps = a.KH * (((a.Co if a.mode == 3 else a.Ci) + a.Cp - 1) // a.Cp)
-        else:
-            taps = a.KH if a.mode == 1 else a.KH * a.KW
-        return taps * a.rows_pad * a.Kc
+        """Work items of one slab in the batched kernels: one per (row, k) position (the kernel walks the taps)."""
+        return a.rows_pad * a.Kc
 
     def _upload_table(self, entries):
         """entries: [(WprepArgs, slab ptr, grad ptr)] -> (device byte tensor holding SscgWbatchEntry[], count, total)"""

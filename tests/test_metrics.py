@@ -89,6 +89,8 @@ def test_forward_onehot_gpu_equals_one_hot_forward():
     with contextlib.redirect_stdout(io.StringIO()):
         g = define_Gen(21, 3, 8, "resnet_9blocks", norm="instance", use_dropout=False, gpu_ids=[0])
         d = define_Dis(21, 8, "n_layers", norm="instance", gpu_ids=[0])
+    for net in (g, d):
+        net.precision = "bf16x3"      # parity mode: run-to-run noise of the atomically accumulated sums stays ~1e-5
     lab = torch.randint(0, 21, (2, 1, 64, 64)).cuda()
     oh = torch.zeros(2, 21, 64, 64, device="cuda").scatter_(1, lab, 1)
     w = None
@@ -96,8 +98,8 @@ def test_forward_onehot_gpu_equals_one_hot_forward():
         ya = net.forward_onehot(lab)
         yb = net(oh)
         # the packed operand is bit-identical; the InstanceNorm sums are accumulated with atomics, so two runs of the
-        # same network differ in the last bits of the statistics (and by an occasional bf16 rounding downstream)
-        assert float((ya - yb).abs().max()) <= 2e-2 * float(yb.abs().max())
+        # same network differ in the last bits of the statistics (in bf16 mode that flips roundings downstream: ~2e-2)
+        assert float((ya - yb).abs().max()) <= 1e-3 * float(yb.abs().max())
         ya.square().mean().backward()                        # weight gradients flow with a label-map input
         w = next(net.parameters())
         assert w.grad is not None and bool(torch.isfinite(w.grad).all()) and float(w.grad.abs().max()) > 0
