@@ -29,6 +29,38 @@ def test_library_exports_every_declared_symbol():
     assert lib.sscg_version() >= 100
 
 
+def test_ctypes_structs_match_the_header_layout(tmp_path):
+    """The ctypes mirrors in sscg_b200/_lib.py have the size and field offsets a C compiler gives the structs of
+    include/sscg_b200.h (an argument block that drifts from the header corrupts kernel arguments silently)."""
+    import ctypes as C
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no C compiler")
+    pairs = [("SscgTap", _lib.Tap), ("SscgView", _lib.View), ("SscgConvArgs", _lib.ConvArgs),
+             ("SscgWgradArgs", _lib.WgradArgs), ("SscgApplyArgs", _lib.ApplyArgs), ("SscgBwdArgs", _lib.BwdArgs),
+             ("SscgWprepArgs", _lib.WprepArgs), ("SscgWbatchEntry", _lib.WbatchEntry), ("SscgConv7Args", _lib.Conv7Args)]
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "sscg_b200.h"', "int main(void) {"]
+    for cname, ct in pairs:
+        lines.append('printf("%s sizeof %%zu\\n", sizeof(%s));' % (cname, cname))
+        for fname, _ in ct._fields_:
+            lines.append('printf("%s %s %%zu\\n", offsetof(%s, %s));' % (cname, fname, cname, fname))
+    lines += ["return 0; }"]
+    src = tmp_path / "abi.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "abi"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    want = {}
+    for line in out.splitlines():
+        c, f, v = line.split()
+        want[(c, f)] = int(v)
+    for cname, ct in pairs:
+        assert C.sizeof(ct) == want[(cname, "sizeof")], cname
+        for fname, _ in ct._fields_:
+            assert getattr(ct, fname).offset == want[(cname, fname)], (cname, fname)
+
+
 def test_define_errors_match_reference_strings():
     with pytest.raises(NotImplementedError, match=r"Generator model name \[foo\] is not recognized"):
         define_Gen(3, 3, 8, "foo", norm="instance", gpu_ids=[])
