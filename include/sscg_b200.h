@@ -98,6 +98,12 @@ typedef struct SscgConvArgs {
     int32_t shift_base_mode;   /* 2 (use this): descriptor base_offset 0 — the 128B swizzle is a pure function of the
                                 * shared-memory address (verified on B200, tools/shift_probe.py); 1: base_offset = row
                                 * phase (diagnostic only: produces wrong results) */
+    /* Flattened tiling (stride-1 gathers over a buffer that carries its zero halo explicitly): x is the 1-D pixel
+     * view (N = H = 1, W = samples * flat_hw) of a [flat_n][rows][flat_pitch][C] buffer, a tile is 128 consecutive
+     * positions f = row * flat_pitch + col of one sample, tap (dh, dw) reads position f + dh * flat_pitch + dw, and
+     * positions with col >= Wo or row >= Ho are computed but not stored.  66 x 66 outputs then take 36 tiles per
+     * sample instead of 45 (8 x 16 tiles).  0 = off.  Requires stride 1, one phase, TH = 1, TW = 128. */
+    int32_t flat_pitch, flat_hw, flat_n;
 } SscgConvArgs;
 
 int sscg_conv_igemm(const SscgConvArgs* a, void* stream);

@@ -38,6 +38,7 @@ struct ConvDev {
     int tiles_x;    // tiles_h * tiles_w * N
     int n_ntiles;   // Co_pad / BN
     int total_tiles;
+    int flat_pitch, flat_hw;   // flattened tiling (see SscgConvArgs): input row pitch / positions per sample; 0 = off
     int tail_from;  // >= 0: schedule entries from this index on are HALF-N tiles (two per output tile): the last,
                     // partial wave of a persistent grid then costs ~0.6 instead of 1.0 tile times (BN = 256 only)
     void* y;
@@ -110,7 +111,7 @@ __device__ __forceinline__ TileInfo decode_tile(const ConvDev& p, int tile, int 
     }
     t.tap0 = p.phase_start[z];
     t.nkb = (p.phase_start[z + 1] - t.tap0) * p.kcb;
-    t.valid = (t.i0 < t.Hph) && (t.j0 < t.Wph);
+    t.valid = p.flat_pitch > 0 ? true : ((t.i0 < t.Hph) && (t.j0 < t.Wph));
     return t;
 }
 
@@ -176,10 +177,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     const bool half_tile = (SPLIT == 1 && SKW == 0) && t.bn != BN;
                     mbar_arrive_expect_tx(fb, half_tile ? Cfg::kTxBytes - Cfg::kBBytes / 2 : Cfg::kTxBytes);
                     uint8_t* st = smem + stage * Cfg::kStageBytes;
-                    const int cw = t.j0 * p.stride + tap.dw + p.org_w;
-                    const int ch = t.i0 * p.stride + tap.dh + p.org_h;
+                    int cw = t.j0 * p.stride + tap.dw + p.org_w;
+                    int ch = t.i0 * p.stride + tap.dh + p.org_h;
+                    int cn = t.n;
+                    if (p.flat_pitch > 0) {      // 1-D pixel view: tile start + tap offset in flattened positions
+                        cw = t.n * p.flat_hw + t.j0 + tap.dh * p.flat_pitch + tap.dw;
+                        ch = 0;
+                        cn = 0;
+                    }
                     const int brow = tap.brow * p.Co_pad + t.n0;
-                    tma_load_4d(smem_u32(st), &tmA, fb, cb * 64, cw, ch, t.n);
+                    tma_load_4d(smem_u32(st), &tmA, fb, cb * 64, cw, ch, cn);
                     if (SKW > 0) {   // one weight box per horizontal tap of this filter row
 #pragma unroll
                         for (int j = 0; j < (SKW > 0 ? SKW : 1); ++j)
@@ -190,7 +197,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         tma_load_2d(smem_u32(st + kPlanes * kABytes), half_tile ? &tmBlo : &tmB, fb, cb * 64, brow);
                     }
                     if (SPLIT == 3) {
-                        tma_load_4d(smem_u32(st + kABytes), &tmAlo, fb, cb * 64, cw, ch, t.n);
+                        tma_load_4d(smem_u32(st + kABytes), &tmAlo, fb, cb * 64, cw, ch, cn);
                         tma_load_2d(smem_u32(st + kPlanes * kABytes + Cfg::kBBytes), &tmBlo, fb, cb * 64, brow);
                     }
                     if (++stage == kStages) { stage = 0; par ^= 1; }
@@ -271,7 +278,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             if (!t.valid) continue;
             const uint32_t acc = it & 1, acc_par = (it >> 1) & 1;
             ++it;
-            const int i = t.i0 + pi, j = t.j0 + pj;
+            int i = t.i0 + pi, j = t.j0 + pj;
+            if (p.flat_pitch > 0) {            // position f of the flattened sample -> (row, col); halo columns are dropped
+                const int f = t.j0 + m;
+                i = f / p.flat_pitch;
+                j = f - i * p.flat_pitch;
+            }
             const bool valid = (i < t.Hph) && (j < t.Wph);
             const int ho = i * os + t.ph, wo = j * os + t.pw;
             const long long yoff = (long long)t.n * p.y_sN + (long long)(ho + p.y_oh) * p.y_sH +
@@ -501,6 +513,16 @@ extern "C" int sscg_conv_igemm(const SscgConvArgs* a, void* stream_) {
     const int Hph = (a->Ho + os - 1) / os, Wph = (a->Wo + os - 1) / os;
     d.tiles_h = (Hph + a->TH - 1) / a->TH;
     d.tiles_w = (Wph + a->TW - 1) / a->TW;
+    d.flat_pitch = a->flat_pitch;
+    d.flat_hw = a->flat_hw;
+    if (a->flat_pitch > 0) {
+        if (a->stride != 1 || a->n_phases != 1 || skw != 0 || a->TH != 1 || a->TW != 128 || a->flat_n < 1 ||
+            a->flat_pitch < a->Wo || a->stats != nullptr)
+            return set_error("conv_igemm: flattened tiling needs stride 1, one phase, 1x128 tiles, pitch >= Wo, no statistics");
+        d.N = a->flat_n;
+        d.tiles_h = 1;
+        d.tiles_w = (a->Ho * a->flat_pitch + 127) / 128;     // positions of rows 0 .. Ho-1, halo columns included
+    }
     d.shift_brow_step = a->shift_brow_step;
     d.shift_base_mode = a->shift_base_mode;
     d.tiles_x = d.tiles_h * d.tiles_w * d.N;

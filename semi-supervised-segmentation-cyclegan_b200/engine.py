@@ -17,6 +17,7 @@ Precision modes: "bf16" (fast; bf16 operands and storage, fp32 accumulate/statis
 "bf16x3" (parity; operands carried as hi+lo bf16 planes, raw outputs and gradients in fp32).
 """
 import ctypes as C
+import os
 from dataclasses import dataclass
 from typing import List, Optional
 
@@ -276,6 +277,20 @@ class NetPlan:
             if (wt.nexp and not sp and i > 0) or (wt.nexp_stem and not sp and i == 0):
                 _, _, ho, wo = self.geom[i]
                 self.draw_nx[i] = K.ActBuf(N, ho, wo, wt.Co_pitch, 6, dev)
+        # 3x3 stride-1 stages behind an explicit halo (the residual-block convs): dRaw goes into a zero-haloed
+        # (k - 1 = 2) ping-pong buffer so that the data gradient can tile the FLATTENED padded output: 36 tiles per
+        # 66 x 66 sample instead of 45, i.e. 4 waves of the persistent grid instead of 5 at bs 16
+        self.draw_flat = {}
+        self._flat_bufs = {}
+        if not sp and os.environ.get("SSCG_FLAT_DGRAD", "1") != "0":
+            for i, (s, wt) in enumerate(zip(self.specs, self.weights)):
+                if (s.kind == "conv" and s.k == 3 and s.stride == 1 and s.in_halo == 1 and s.pad == 1 and s.norm and i > 0
+                        and wt.need_dgrad and i not in self.draw_nx):
+                    _, _, ho, wo = self.geom[i]
+                    key = (ho, wo, wt.Co_pitch)
+                    if key not in self._flat_bufs:
+                        self._flat_bufs[key] = [K.ActBuf(N, ho, wo, wt.Co_pitch, 2, dev) for _ in range(2)]
+                    self.draw_flat[i] = self._flat_bufs[key][i & 1]
         self.sync_ctr = torch.zeros(max(N, 1), dtype=torch.int32, device=dev)
         self.tbuf = [None, None]   # residual-path total gradients (ping-pong), allocated lazily
         nb = sum(N * wt.Co_pitch * 2 for wt in self.weights)
@@ -423,12 +438,14 @@ class NetPlan:
             if overlap and wg_pending[par]:
                 main.wait_event(self.ev_wg[par])          # the wgrad that last read this dRaw buffer is done
                 wg_pending[par] = False
-            if not (use_apply and self.fused_in_bwd and i not in self.draw_nx and
+            if not (use_apply and self.fused_in_bwd and i not in self.draw_nx and i not in self.draw_flat and
                     K.run_bwd_fused(ba, self.draws[par], self.draws_lo[par], self.sync_ctr)):
                 K.run_bwd_prep(ba)
                 if use_apply:
                     if i in self.draw_nx:
                         K.run_bwd_apply(ba, self.draw_nx[i].hi, None)
+                    elif i in self.draw_flat:
+                        K.run_bwd_apply(ba, self.draw_flat[i].hi, None)
                     else:
                         K.run_bwd_apply(ba, self.draws[par], self.draws_lo[par])
             self.draw, self.draw_lo = self.draws[par], self.draws_lo[par]
@@ -463,6 +480,8 @@ class NetPlan:
         _, _, ho, wo = self.geom[i]
         if i in self.draw_nx and not lo:
             return self.draw_nx[i].view(interior=True)
+        if i in self.draw_flat and not lo:
+            return self.draw_flat[i].view(interior=True)
         t = self.draws_lo[i & 1] if lo else self.draws[i & 1]
         cp = wt.Co_pitch
         return L.make_view(t.data_ptr(), self.N, ho, wo, cp, ho * wo * cp, wo * cp, cp)
@@ -517,6 +536,8 @@ class NetPlan:
             use_apply = False
         if use_apply and i in self.draw_nx:
             ba.draw_pad = 6
+        if use_apply and i in self.draw_flat:
+            ba.draw_pad = 2
         # ---- 2. wgrad ------------------------------------------------------------------------
         wa = None
         if need_dw:
@@ -547,6 +568,15 @@ class NetPlan:
             assert gin.pad == 3 and gin.C == 32 * wt.nx_dg_tiles
             da = K.conv7_args(src.hi.data_ptr(), src.C, N, src.Hp, src.Wp, wt.w_nx_dg, 32, wt.nx_dg_tiles, src.C // 16, 32,
                               gin.hi.data_ptr(), False, (gin.sN, gin.sH, gin.sW), tag=5)
+        elif i in self.draw_flat:
+            gin, src = self.gact[i], self.draw_flat[i]
+            assert gin.pad == 1 and gin.Hp == src.Hp - 2 and gin.Wp == src.Wp - 2
+            npx = N * src.Hp * src.Wp
+            fview = L.make_view(src.hi.data_ptr(), 1, 1, npx, src.C, npx * src.C, npx * src.C, src.C)
+            table = G.taps_conv_dgrad(s.k, s.k, 1, -(s.k - 1))        # taps (k-1-a, k-1-b) >= 0 into the zero-haloed dRaw
+            da = K.conv_args(fview, None, table, wt.Kc_d, wt.w_dg, None, s.k * s.k * wt.Ci_pad, wt.Ci_pad,
+                             gin.hi.data_ptr(), gin.fp32, (gin.sN, gin.sH, gin.sW), (0, 0), gin.Hp, gin.Wp, split=sp,
+                             tag=2 if s.name.startswith("res") else 5, flat=(src.Wp, src.Hp * src.Wp, N))
         elif (i > 0 or need_dx) and wt.need_dgrad:
             gin = self.gact[i]
             dview = self._draw_view(i)

@@ -91,7 +91,7 @@ def fill_taps(dst_taps, table: TapTable):
 
 def conv_args(xview, x_lo, table: TapTable, Kc, w, w_lo, w_rows, Co_pad, y_ptr, y_fp32, y_strides, y_off, Ho, Wo,
               bias=None, act=L.ACT_NONE, slope=0.2, stats=None, BN=None, tile=None, split=1, tag=4,
-              shift_kw=0, shift_brow_step=1, shift_base_mode=2):
+              shift_kw=0, shift_brow_step=1, shift_base_mode=2, flat=None):
     a = L.ConvArgs()
     a.x = xview
     a.x_lo = x_lo
@@ -118,6 +118,9 @@ def conv_args(xview, x_lo, table: TapTable, Kc, w, w_lo, w_rows, Co_pad, y_ptr, 
     a.tag = tag
     a.shift_kw, a.shift_brow_step, a.shift_base_mode = shift_kw, shift_brow_step, shift_base_mode
     if shift_kw:
+        a.TH, a.TW = 1, 128
+    if flat is not None:          # (row pitch, positions per sample, samples) of the flattened zero-haloed input
+        a.flat_pitch, a.flat_hw, a.flat_n = flat
         a.TH, a.TW = 1, 128
     return a
 

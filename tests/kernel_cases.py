@@ -183,6 +183,32 @@ def case_conv_dgrad(N=2, H=16, W=16, Cin=64, Cout=128, k=3, stride=1, pad=1, shi
     return _result(dx[..., :Cin].permute(0, 3, 1, 2), ref, 2e-4)
 
 
+def case_conv_dgrad_flat(N=3, H=30, W=30, Cin=256, Cout=256, k=3):
+    """Flattened tiling (SscgConvArgs.flat_*): gradient w.r.t. the halo-padded input of a stride-1 conv that reads an
+    explicit halo (the residual-block convs) — dRaw sits in a buffer with a zero halo of k - 1, tiles are 128
+    consecutive positions of the flattened padded output; vs conv_transpose2d (full correlation)."""
+    _setup()
+    dy = _bf(torch.randn(N, Cout, H, W, device=DEV))
+    w = _bf(torch.randn(Cout, Cin, k, k, device=DEV) * 0.05)
+    Kc = G.round_up(Cout, 64)
+    Ci_pad = G.pad_out_channels(Cin)
+    buf = K.ActBuf(N, H, W, G.pad_out_channels(Cout), k - 1, DEV)
+    _fill_act(buf, dy, L.PAD_ZERO)
+    slab, _, _ = _wslab(w, False, 2, 0, Ci_pad, Kc, k, k, Cout, Cin)
+    Ho, Wo = H + k - 1, W + k - 1
+    dx = torch.zeros(N, Ho, Wo, Ci_pad, device=DEV, dtype=torch.bfloat16)
+    npx = N * buf.Hp * buf.Wp
+    fview = L.make_view(buf.hi.data_ptr(), 1, 1, npx, buf.C, npx * buf.C, npx * buf.C, buf.C)
+    table = G.taps_conv_dgrad(k, k, 1, -(k - 1))
+    a = K.conv_args(fview, None, table, Kc, slab, None, k * k * Ci_pad, Ci_pad, dx.data_ptr(), False,
+                    (Ho * Wo * Ci_pad, Wo * Ci_pad, Ci_pad), (0, 0), Ho, Wo, flat=(buf.Wp, buf.Hp * buf.Wp, N))
+    K.run_conv(a)
+    torch.cuda.synchronize()
+    ref = F.conv_transpose2d(dy, w)
+    err, scale, _ = _result(dx.float()[..., :Cin].permute(0, 3, 1, 2), ref, 0)
+    return err, scale, scale * 2.0 ** -8
+
+
 def case_conv_wgrad(N=2, H=16, W=16, Cin=64, Cout=128, k=3, stride=1, pad=1, ksplit=None):
     _setup()
     Ho, Wo = G.conv_out(H, k, stride, pad), G.conv_out(W, k, stride, pad)
@@ -651,6 +677,9 @@ CASES = {
     "dgrad_4x4_s1_odd": lambda: case_conv_dgrad(H=10, W=10, k=4, stride=1),
     "dgrad_7x7_small_cout": lambda: case_conv_dgrad(Cin=64, Cout=21, k=7, pad=3),
     "dgrad_to_c3": lambda: case_conv_dgrad(Cin=3, Cout=64, k=7, pad=3),
+    "dgrad_flat_3x3_c256": lambda: case_conv_dgrad_flat(),
+    "dgrad_flat_3x3_c64_odd": lambda: case_conv_dgrad_flat(N=2, H=13, W=21, Cin=64, Cout=128),
+    "dgrad_flat_res_shape": lambda: case_conv_dgrad_flat(N=16, H=64, W=64),     # 576 tiles: four full waves
     # wgrad
     "wgrad_3x3_s1": lambda: case_conv_wgrad(),
     "wgrad_3x3_s1_256": lambda: case_conv_wgrad(Cin=256, Cout=256),
