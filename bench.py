@@ -200,7 +200,12 @@ def run_reference(args):
     if rank != 0:
         return
     n = args.ref_batch
-    step, threads = cpu_reference_step_factory(n, args.variant)
+    # all host threads the process may use (torchrun exports OMP_NUM_THREADS=1 for N > 1: override it)
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except AttributeError:
+        avail = os.cpu_count() or 1
+    step, threads = cpu_reference_step_factory(n, args.variant, threads=avail)
     for _ in range(args.warmup):
         step()
     t0 = time.perf_counter()
