@@ -29,6 +29,13 @@ extern "C" {
 #define SSCG_ACT_LRELU 2
 #define SSCG_ACT_TANH 3
 
+/* Plane sums (InstanceNorm statistics and their backward counterparts) are kept as BINNED FIXED-POINT accumulators:
+ * a value v is the pair of int64 words (hi, lo) with v = hi * 2^-8 + lo * 2^-56.  Kernels add float partial sums with
+ * 64-bit integer atomics (exact split of the float into the two words), so the total does not depend on the order in
+ * which thread blocks arrive: results are reproducible bit for bit, with no fence, counter or extra launch.  A buffer
+ * of plane sums is int64 [N][C][2][SSCG_STAT_WORDS] and must be zeroed before the launch that accumulates into it. */
+#define SSCG_STAT_WORDS 2
+
 /* halo modes */
 #define SSCG_PAD_NONE 0
 #define SSCG_PAD_ZERO 1
@@ -84,7 +91,9 @@ typedef struct SscgConvArgs {
     const float* bias;     /* [Co_pad] or NULL */
     int32_t act;           /* SSCG_ACT_* applied in the epilogue */
     float slope;
-    float* stats;          /* [N][Co_pad][2] fp32 (sum, sum of squares), accumulated atomically; or NULL */
+    void* stats;           /* int64 [N][Co_pad][2][SSCG_STAT_WORDS]: binned accumulators of (sum, sum of squares) per
+                            * (sample, channel) plane, ADDED to by the launch (zero them first); or NULL.  See
+                            * "Plane sums" below. */
     int32_t TH, TW;        /* output tile, TH*TW == 128 */
     int32_t BN;            /* N tile: 16, 32, 64, 128 or 256 */
     int32_t tag;           /* profiling class (0..15), see sscg_prof_begin */
@@ -112,7 +121,9 @@ int sscg_conv_igemm(const SscgConvArgs* a, void* stream);
  * sscg_conv_wgrad — weight gradient as a pixel-contraction GEMM on tcgen05 (both operands MN-major).
  * Replaces: cuDNN wgrad of the same convolutions (K17).
  *   dWt[tap.brow*Co_pad + co, k] += sum_{n, ho, wo} dY[n, ho, wo, co] * X[n, ho*stride+tap.dh+org_h, ..., k]
- * dWt is fp32 [w_rows][Kc], accumulated with red.global.add (split-K over samples / pixel tiles).
+ * dWt is fp32 [w_rows][Kc].  Split-K over samples / pixel tiles: the ksplit partial tiles of an output tile go to
+ * the workspace and are summed in split order by the CTA that arrives last, which alone adds the sum to dWt
+ * (no floating-point atomics: results do not depend on CTA scheduling).
  * ------------------------------------------------------------------------------------------- */
 typedef struct SscgWgradArgs {
     SscgView dy;           /* output-gradient view [N][Ho][Wo][Co_pad] (hi plane); zero outside */
@@ -130,9 +141,12 @@ typedef struct SscgWgradArgs {
     int32_t BN;            /* K-column tile of dWt: 64, 128 or 256 (divides Kc) */
     int32_t ksplit;        /* number of CTAs sharing one (tap, co-tile, k-tile) */
     int32_t tag;           /* profiling class (0..15) */
+    void* ws;              /* ksplit > 1: workspace of sscg_conv_wgrad_ws_bytes() bytes (arrival counters, zero before
+                            * the first launch and left zero by every launch, + partial tiles) */
 } SscgWgradArgs;
 
 int sscg_conv_wgrad(const SscgWgradArgs* a, void* stream);
+int64_t sscg_conv_wgrad_ws_bytes(const SscgWgradArgs* a);
 
 /* ---------------------------------------------------------------------------------------------
  * Elementwise / reduction kernels around the GEMMs.
@@ -160,20 +174,21 @@ int sscg_unpack_fold(const void* src, int32_t src_fp32, int32_t N, int32_t C, in
                      int32_t pad, int32_t pad_mode, float* dst, void* stream);
 
 /* sscg_bias_grad: grad[c] += scale * sum_n bstats[n][c][0] (bias gradient of a conv that is not
- * followed by InstanceNorm: head conv generators.py:85,90; PatchGAN stem/tail discriminators.py:45,58). */
-int sscg_bias_grad(const float* bstats, int32_t N, int32_t C, int32_t Cp, float* grad, float scale, void* stream);
+ * followed by InstanceNorm: head conv generators.py:85,90; PatchGAN stem/tail discriminators.py:45,58);
+ * bstats in the plane-sum format. */
+int sscg_bias_grad(const void* bstats, int32_t N, int32_t C, int32_t Cp, float* grad, float scale, void* stream);
 
 /* sscg_in_apply: y = dropout(act(instance_norm(raw))) (+ residual), written with a halo for the next
  * convolution.  Replaces nn.InstanceNorm2d + ReLU/LeakyReLU + Dropout + residual add + the next
  * layer's ReflectionPad2d (ops.py:11,44,50,57,62-74).
  *   raw:   [N][H][W][C] bf16 (raw_fp32 == 0) or fp32
- *   stats: [N][C][2] (sum, sumsq) from the conv epilogue, or NULL for "no norm"
+ *   stats: plane sums [N][C][2][SSCG_STAT_WORDS] (sum, sumsq) from the conv epilogue, or NULL for "no norm"
  *   res:   optional residual view (bf16 hi/lo), added after norm/act
  *   dst:   bf16 [N][H+2p][W+2p][C] (+ lo plane when dst_lo != NULL)
  *   dropout: p = 0.5 when drop_seed != 0 (keep mask = hash(seed, element index); scale 2). */
 typedef struct SscgApplyArgs {
     const void* raw; int32_t raw_fp32;
-    const float* stats; float eps;
+    const void* stats; float eps;
     int32_t N, H, W, C;
     int32_t act; float slope;
     uint64_t drop_seed;
@@ -187,12 +202,12 @@ int sscg_in_apply(const SscgApplyArgs* a, void* stream);
 /* sscg_in_bwd_prep / sscg_in_bwd_apply: backward of the same chain.
  * prep:  dZ = act'(Z) * dropmask * ( fold_halo(dYp) + skip ), Z = instance_norm(raw) recomputed;
  *        writes dZ (and optionally the folded sum G for the residual skip path), accumulates
- *        bstats[n][c] = (sum dZ, sum dZ*Z).  With stats == NULL (no norm) dZ is the final dRaw and
+ *        bstats[n][c] = (sum dZ, sum dZ*Z) (plane-sum format).  With stats == NULL (no norm) dZ is the final dRaw and
  *        bstats[.][c][0] is the bias gradient contribution.
  * apply: dRaw = rstd * (dZ - mean(dZ) - Z * mean(dZ*Z)). */
 typedef struct SscgBwdArgs {
     const void* raw; int32_t raw_fp32;
-    const float* stats; float eps;
+    const void* stats; float eps;
     int32_t N, H, W, C;
     int32_t act; float slope;
     uint64_t drop_seed;
@@ -203,23 +218,18 @@ typedef struct SscgBwdArgs {
     void* g_out; int32_t g_fp32;      /* optional: folded dYp + skip, [N][H][W][C] */
     void* dz; int32_t dz_fp32;        /* [N][H][W][C] */
     void* dz_lo;                      /* lo plane when dZ is the final dRaw in split mode */
-    float* bstats;                    /* [N][C][2] */
+    void* bstats;                     /* plane sums [N][C][2][SSCG_STAT_WORDS] of (dZ, dZ*Z), ADDED to (zero them first) */
     int32_t dz_pad;                   /* > 0: dZ is written into a [N][H+2p][W+2p][C] buffer at offset (p, p); the halo is
                                          left untouched (kept zero by the caller: input layout of sscg_conv7_nexp's data gradient) */
     int32_t draw_pad;                 /* same, for the dRaw output of sscg_in_bwd_apply */
 } SscgBwdArgs;
 int sscg_in_bwd_prep(const SscgBwdArgs* a, void* stream);
 int sscg_in_bwd_apply(const SscgBwdArgs* a, void* draw, void* draw_lo, void* stream);
-/* sscg_in_bwd_fused: prep + apply in ONE launch (normalised stages only).  All CTAs of a sample stay
- * resident, meet at a per-sample arrival counter (sync_ctr: uint32[N], zeroed by the call) once the plane
- * sums are complete, and sweep their pixels a second time out of L2 to write dRaw — no dZ round trip.
- * Returns 3 (no error string) if N exceeds the number of co-resident CTAs: use prep + apply instead. */
-int sscg_in_bwd_fused(const SscgBwdArgs* a, void* draw, void* draw_lo, uint32_t* sync_ctr, void* stream);
 /* sscg_set_stream_norm: 2 (default) lets sscg_in_apply / sscg_in_bwd_prep / sscg_in_bwd_apply use their
  * bulk-copy pipelined variants (cp.async.bulk ring in shared memory, one persistent CTA per SM, a producer
  * warp and free-running consumer warps) when every tensor is bf16 and the row geometry suits the ring; 1
- * keeps the register-batched sscg_in_bwd_prep; 0 forces the register-batched kernels everywhere.  Same results in every mode (identical arithmetic; only the
- * summation order of the plane sums differs).  SSCG_STREAM_NORM=0|1|2 sets the initial value. */
+ * keeps the register-batched sscg_in_bwd_prep; 0 forces the register-batched kernels everywhere.  Same arithmetic in every mode; the
+ * summation order of the plane sums is fixed within a mode and differs between modes.  SSCG_STREAM_NORM=0|1|2 sets the initial value. */
 int sscg_set_stream_norm(int32_t on);
 
 /* weight preparation: fp32 master weights -> bf16 GEMM operand slabs (see DESIGN.md "weight slabs") */
@@ -278,24 +288,36 @@ typedef struct SscgWbatchEntry {
 int sscg_wprep_batch(const SscgWbatchEntry* table_dev, int32_t count, int64_t total, void* stream);
 int sscg_wgrad_unpack_batch(const SscgWbatchEntry* table_dev, int32_t count, int64_t total, float scale, void* stream);
 
+/* Loss reductions are grid-wide sums WITHOUT floating-point atomics: every block stores its partial sums to a slot
+ * of a caller-provided workspace of SSCG_LOSS_WS_BYTES bytes (zero before the first use; every launch leaves its
+ * arrival counter zero) and the block that arrives last adds the slots in a fixed order, so results are
+ * reproducible bit for bit.  One workspace must not be shared by launches that may run concurrently. */
+#define SSCG_LOSS_WS_BYTES 16384
+
 /* sscg_seg_head_fwd / _bwd: fused segmentation-head loss on NCHW fp32 logits — softmax over classes
- * (nn.Softmax2d, model.py:273,401-402), mean cross-entropy against the label map
- * (nn.CrossEntropyLoss, model.py:272,398,455) and first-max argmax (model.py:435,509) in one pass;
- * backward = cross-entropy gradient + softmax Jacobian of an incoming probability gradient.
- *   labels [N][H][W] int64 or NULL; probs / argmax / loss_sum (fp32 accumulator of sum -log p[label]) or NULL.
- *   dloss: device scalar, gradient of the MEAN cross-entropy (or NULL); dprobs or NULL. */
-int sscg_seg_head_fwd(const float* logits, const int64_t* labels, int32_t N, int32_t C, int64_t HW, float* probs,
-                      int64_t* argmax, float* loss_sum, void* stream);
-int sscg_seg_head_bwd(const float* probs, const int64_t* labels, const float* dloss, const float* dprobs, int32_t N,
-                      int32_t C, int64_t HW, float* dlogits, void* stream);
+ * (nn.Softmax2d, model.py:273,401-402), cross-entropy against the label map (nn.CrossEntropyLoss, model.py:272,
+ * 398,455; log-sum-exp form) and first-max argmax (model.py:435,509) in one pass; backward = cross-entropy
+ * gradient + softmax Jacobian of an incoming probability gradient.
+ *   labels [N][H][W] int64 or NULL.  Pixels labelled ignore_index (torch default -100) are left out of the loss and
+ *   of its gradient; any other label outside [0, C) raises the device error flag (sscg_device_error, code 31) —
+ *   torch device-asserts on those — and is left out as well.
+ *   probs / argmax may be NULL.  loss_out[2] (or NULL) = (sum of -log p[label] over the counted pixels, their
+ *   number): the mean cross-entropy is loss_out[0] / loss_out[1].
+ *   backward: dloss = device scalar, gradient of the MEAN cross-entropy (or NULL), count = device scalar holding
+ *   loss_out[1]; dprobs or NULL. */
+int sscg_seg_head_fwd(const float* logits, const int64_t* labels, int32_t N, int32_t C, int64_t HW,
+                      int64_t ignore_index, float* probs, int64_t* argmax, float* loss_out, void* ws, void* stream);
+int sscg_seg_head_bwd(const float* probs, const int64_t* labels, const float* dloss, const float* count,
+                      const float* dprobs, int32_t N, int32_t C, int64_t HW, float* dlogits, void* stream);
 
 /* sscg_lsgan_fwd / _bwd: LSGAN patch loss against a constant target (nn.MSELoss vs all-ones / all-zeros,
- * model.py:270,445-446,452,521-534): loss_sum += scale * sum (x - target)^2 (scale = 1/n gives the mean);
+ * model.py:270,445-446,452,521-534): *loss_out = scale * sum (x - target)^2 (scale = 1/n gives the mean);
  * dx = dloss * 2 (x - target) / n with dloss a device scalar (gradient of the MEAN). */
-int sscg_lsgan_fwd(const float* x, int64_t n, float target, float scale, float* loss_sum, void* stream);
+int sscg_lsgan_fwd(const float* x, int64_t n, float target, float scale, float* loss_out, void* ws, void* stream);
 int sscg_lsgan_bwd(const float* x, int64_t n, float target, const float* dloss, float* dx, void* stream);
-/* sscg_l1_fwd / _bwd: nn.L1Loss (model.py:271,453,461): loss_sum += scale * sum |x - y|; dx = dloss * sign(x - y) / n. */
-int sscg_l1_fwd(const float* x, const float* y, int64_t n, float scale, float* loss_sum, void* stream);
+/* sscg_l1_fwd / _bwd: nn.L1Loss (model.py:271,453,461): *loss_out = scale * sum |x - y|; dx = dloss * sign(x - y) / n.
+ * Any alignment of x / y is accepted (128-bit loads when both are 16-byte aligned). */
+int sscg_l1_fwd(const float* x, const float* y, int64_t n, float scale, float* loss_out, void* ws, void* stream);
 int sscg_l1_bwd(const float* x, const float* y, int64_t n, const float* dloss, float* dx, void* stream);
 /* sscg_adam_flat: one Adam update (torch.optim.Adam semantics, no weight decay / amsgrad; model.py:286-287,
  * 474,542) over a flat fp32 bucket: p, g, m (exp_avg), v (exp_avg_sq) of n elements; lr and step are DEVICE

@@ -11,6 +11,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SSCG_LIB", os.path.join(_HERE, "libsscg_b200.so"))   # SSCG_LIB: tuning builds only
 
 SSCG_MAX_TAPS = 64
+SSCG_LOSS_WS_BYTES = 16384
+SSCG_STAT_WORDS = 2          # int64 words per plane-sum value (binned fixed-point accumulators, see the header)
 ACT_NONE, ACT_RELU, ACT_LRELU, ACT_TANH = 0, 1, 2, 3
 PAD_NONE, PAD_ZERO, PAD_REFLECT = 0, 1, 2
 
@@ -54,6 +56,7 @@ class WgradArgs(C.Structure):
         ("Co_pad", C.c_int32), ("split", C.c_int32),
         ("dw", C.c_void_p), ("w_rows", C.c_int32),
         ("TH", C.c_int32), ("TW", C.c_int32), ("BN", C.c_int32), ("ksplit", C.c_int32), ("tag", C.c_int32),
+        ("ws", C.c_void_p),
     ]
 
 
@@ -112,6 +115,7 @@ class WbatchEntry(C.Structure):
 _SIGNATURES = {
     "sscg_conv_igemm": [C.POINTER(ConvArgs), C.c_void_p],
     "sscg_conv_wgrad": [C.POINTER(WgradArgs), C.c_void_p],
+    "sscg_conv_wgrad_ws_bytes": [C.POINTER(WgradArgs)],
     "sscg_pack_nchw": [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
                        C.c_int32, C.c_int32, C.c_int32, C.c_void_p],
     "sscg_unpack_fold": [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
@@ -123,7 +127,6 @@ _SIGNATURES = {
     "sscg_in_apply": [C.POINTER(ApplyArgs), C.c_void_p],
     "sscg_in_bwd_prep": [C.POINTER(BwdArgs), C.c_void_p],
     "sscg_in_bwd_apply": [C.POINTER(BwdArgs), C.c_void_p, C.c_void_p, C.c_void_p],
-    "sscg_in_bwd_fused": [C.POINTER(BwdArgs), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
     "sscg_set_stream_norm": [C.c_int32],
     "sscg_wprep": [C.POINTER(WprepArgs), C.c_void_p],
     "sscg_wgrad_unpack": [C.POINTER(WprepArgs), C.c_void_p, C.c_void_p, C.c_float, C.c_void_p],
@@ -131,13 +134,13 @@ _SIGNATURES = {
     "sscg_wprep_batch": [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p],
     "sscg_wgrad_unpack_batch": [C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_void_p],
     "sscg_fill_zero": [C.c_void_p, C.c_int64, C.c_void_p],
-    "sscg_seg_head_fwd": [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
-                          C.c_void_p],
-    "sscg_seg_head_bwd": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_void_p,
-                          C.c_void_p],
-    "sscg_lsgan_fwd": [C.c_void_p, C.c_int64, C.c_float, C.c_float, C.c_void_p, C.c_void_p],
+    "sscg_seg_head_fwd": [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
+                          C.c_void_p, C.c_void_p, C.c_void_p],
+    "sscg_seg_head_bwd": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64,
+                          C.c_void_p, C.c_void_p],
+    "sscg_lsgan_fwd": [C.c_void_p, C.c_int64, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p],
     "sscg_lsgan_bwd": [C.c_void_p, C.c_int64, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p],
-    "sscg_l1_fwd": [C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_void_p, C.c_void_p],
+    "sscg_l1_fwd": [C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p],
     "sscg_l1_bwd": [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p],
     "sscg_adam_flat": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_float, C.c_float,
                        C.c_float, C.c_void_p, C.c_void_p],
@@ -170,7 +173,7 @@ def lib():
     for name, argtypes in _SIGNATURES.items():
         fn = getattr(l, name)
         fn.argtypes = argtypes
-        fn.restype = C.c_int
+        fn.restype = C.c_int64 if name.endswith("_ws_bytes") else C.c_int
     l.sscg_last_error.restype = C.c_char_p
     l.sscg_last_error.argtypes = []
     l.sscg_launch_count.restype = C.c_uint64

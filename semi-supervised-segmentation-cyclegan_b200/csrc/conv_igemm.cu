@@ -12,8 +12,8 @@
 //                 accumulator to the epilogue while the next tile accumulates into the other one.
 //   warps 2..5  : epilogue — tcgen05.ld the accumulator (then immediately give the TMEM buffer back),
 //                 optional bias/activation, InstanceNorm partial statistics (warp-shuffle
-//                 transpose-reduce per channel, one atomicAdd per channel per tile), vectorised NHWC
-//                 store.
+//                 transpose-reduce per channel, then one order-independent integer accumulation per channel
+//                 and tile: binned fixed-point sums, sscg_ptx.cuh), vectorised NHWC store.
 //
 // Replaces (reference): nn.Conv2d / nn.ConvTranspose2d forward + cuDNN dgrad at
 // arch/ops.py:40-57,63,68; arch/generators.py:74-90; arch/discriminators.py:45-58, with
@@ -48,9 +48,12 @@ struct ConvDev {
     const float* bias;
     int act;
     float slope;
-    float* stats;
+    unsigned long long* stats;   // [N][Co_pad][2][kDetWords] binned accumulators of (sum, sum of squares)
 };
 
+#ifndef SSCG_IGEMM_BN128_KB
+#define SSCG_IGEMM_BN128_KB 200
+#endif
 constexpr int kTileM = 128;
 constexpr int kABytes = kTileM * 128;   // 128 pixels x 64 bf16
 
@@ -67,7 +70,9 @@ struct IgemmCfg {
     static constexpr int kStageBytes = kPlanes * (kAStage + kBStage);
     static constexpr int kTxBytes = kPlanes * (kARows * 128 + kBStage);
     // wide tiles: as deep a ring as fits one CTA per SM; narrow tiles: 4 stages so that 2+ CTAs fit
-    static constexpr int kMaxStages = ((BN >= 128 || SKW > 0) ? 200 * 1024 : 100 * 1024) / kStageBytes;
+    // SSCG_IGEMM_BN128_KB: ring budget of the BN = 128 tile (200: one CTA per SM with 6 stages; 100: 3 stages, two CTAs)
+    static constexpr int kMaxStages = ((BN > 128 || SKW > 0) ? 200 * 1024
+                                       : (BN == 128 ? SSCG_IGEMM_BN128_KB * 1024 : 100 * 1024)) / kStageBytes;
     static constexpr int kStages = kMaxStages > 6 ? 6 : (kMaxStages < 2 ? 2 : kMaxStages);
     static constexpr int kAccCols = BN < 32 ? 32 : BN;          // columns per accumulator
     static constexpr int kTmemCols = 2 * kAccCols < 32 ? 32 : 2 * kAccCols;
@@ -388,9 +393,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         a += s_stat[(q * BN + col) * 2 + 0];
                         b += s_stat[(q * BN + col) * 2 + 1];
                     }
-                    float* dst = p.stats + ((long long)t.n * p.Co_pad + t.n0 + col) * 2;
-                    atomicAdd(dst, a);
-                    atomicAdd(dst + 1, b);
+                    // binned integer accumulators (sscg_ptx.cuh): order-independent, hence reproducible, plane sums
+                    unsigned long long* dst = p.stats + ((long long)t.n * p.Co_pad + t.n0 + col) * (2 * kDetWords);
+                    det_red_add(dst, a);
+                    det_red_add(dst + kDetWords, b);
                 }
                 named_bar_sync(2, 128);               // s_stat may be overwritten by the next tile
             }
@@ -540,7 +546,7 @@ extern "C" int sscg_conv_igemm(const SscgConvArgs* a, void* stream_) {
     }
     d.y = a->y; d.y_fp32 = a->y_fp32;
     d.y_sN = a->y_sN; d.y_sH = a->y_sH; d.y_sW = a->y_sW; d.y_oh = a->y_oh; d.y_ow = a->y_ow;
-    d.bias = a->bias; d.act = a->act; d.slope = a->slope; d.stats = a->stats;
+    d.bias = a->bias; d.act = a->act; d.slope = a->slope; d.stats = reinterpret_cast<unsigned long long*>(a->stats);
     if (d.total_tiles <= 0) return 0;
     if (skw == 7) {
         if (a->BN == 16) return launch_igemm<16, 1, 7>(tmA, tmAlo, tmB, tmBlo, d, stream, a->tag);

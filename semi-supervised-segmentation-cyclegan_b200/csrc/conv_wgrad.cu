@@ -6,7 +6,9 @@
 // contraction over pixels in blocks of 64.  Both operands are "MN-major" for the tensor core: a TMA
 // box of TH x TW pixels x 64 channels lands as 64 rows (pixels = GEMM-K) of 128 B (64 channels =
 // GEMM-M or -N), 128B-swizzled, which is exactly the canonical MN-major SWIZZLE_128B atom.
-// Split-K over (sample, pixel tile) ranges; partial sums are combined with red.global.add.f32.
+// Split-K over (sample, pixel tile) ranges.  The partial tiles of an output tile are combined in split order — every
+// split CTA reduces its own slice of the tile once all partials are published (fixed-order reduction, sscg_ptx.cuh) —
+// so the result does not depend on CTA scheduling (the earlier red.global.add.f32 version did).
 //
 // Replaces (reference): the cuDNN wgrad that autograd runs for every nn.Conv2d / ConvTranspose2d of
 // arch/ops.py:40-57,63,68, arch/generators.py:74-90, arch/discriminators.py:45-58 during
@@ -24,6 +26,8 @@ struct WgradDev {
     int Co_pad, Kc, n_ktiles;
     int ksplit;
     float* dw;
+    float* part;            // [tile][ksplit][128][BN] fp32 partial tiles (ksplit > 1)
+    unsigned int* ctr;      // [tile][2] arrival / departure counters (zero between launches)
 };
 
 constexpr int kWgAtomBytes = 64 * 128;   // 64 pixels x 64 channels bf16
@@ -44,10 +48,7 @@ struct WgradCfg {
     static_assert(SPLIT == 1 || kN1 == 0, "wide wgrad tiles are bf16-mode only");
 };
 
-__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
-    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
-                 : "memory");
-}
+constexpr int kWgCtrs = 1024;           // arrival counters at the head of the workspace
 
 template <int BN, int SPLIT>
 __global__ void __launch_bounds__(192, 1)
@@ -180,19 +181,98 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
         mbar_wait(smem_u32(tmem_full_bar), 0, 6);
         tc_fence_after();
         float* drow = p.dw + ((long long)tap.brow * p.Co_pad + co) * p.Kc + kt * BN;
+        const int nsplit = (total_blocks + per - 1) / per;          // splits that own at least one pixel block
+        const int tile_id = blockIdx.z * gridDim.y + blockIdx.y;
+        float* prow = p.part + (((long long)tile_id * p.ksplit + split) * 128 + m) * BN;
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
             uint32_t r[32];
             tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + c * 32, r);
             tmem_ld_wait();
             if (valid) {
+                float4* dst = reinterpret_cast<float4*>((nsplit == 1 ? drow : prow) + c * 32);
 #pragma unroll
-                for (int q = 0; q < 8; ++q)
-                    red_add_v4(drow + c * 32 + 4 * q, __uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
-                               __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+                for (int q = 0; q < 8; ++q) {
+                    float4 v = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
+                                           __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+                    if (nsplit == 1) {          // sole owner of the tile: plain read-modify-write
+                        const float4 o = dst[q];
+                        v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+                    }
+                    dst[q] = v;
+                }
             }
         }
         tc_fence_before();
+        if (nsplit > 1) {
+            // All splits of a tile are consecutive blocks (blockIdx.x fastest), hence co-resident or next in line for
+            // an SM: each one publishes its partial tile, waits until all nsplit are there, and then reduces ITS slice
+            // of the tile over the splits in split order — a fixed-order sum whose cost is spread over the nsplit SMs
+            // (one CTA reducing the whole tile reads nsplit x 128 KB through a single SM: +60 us on the 3x3 layers).
+            const int e = threadIdx.x - 64;
+            unsigned int* ctr_a = p.ctr + 2 * tile_id;       // arrivals
+            unsigned int* ctr_d = ctr_a + 1;                 // departures (the last one re-arms both counters)
+            named_bar_sync(1, 128);                          // the CTA's partial tile is stored
+            if (e == 0) {
+                atom_add_acq_rel_gpu(ctr_a, 1u);
+                spin_until_ge(ctr_a, (unsigned int)nsplit, 8);
+            }
+            named_bar_sync(2, 128);
+            const float* pt = p.part + (long long)tile_id * p.ksplit * 128 * BN;
+            const int rows = a_atoms * 64;
+            float* dbase = p.dw + ((long long)tap.brow * p.Co_pad + m0) * p.Kc + kt * BN;
+            const int total4 = rows * BN / 4;
+            const int per4 = (total4 + nsplit - 1) / nsplit;
+            const int j0 = split * per4, j1 = min(total4, j0 + per4);
+            // two positions per thread and pass, all their partials (up to 8 splits each) in flight together: the loads
+            // come from L2 (~1 us round trip), so memory-level parallelism is what bounds this loop
+            for (int j = j0 + e; j < j1; j += 256) {
+                int idx[2];
+                bool on[2];
+                float4 acc[2], old[2];
+#pragma unroll
+                for (int w = 0; w < 2; ++w) {
+                    const int jw = j + w * 128;
+                    on[w] = jw < j1;
+                    idx[w] = (on[w] ? jw : j) * 4;
+                    acc[w] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                float4* d4[2];
+#pragma unroll
+                for (int w = 0; w < 2; ++w) {
+                    const int row = idx[w] / BN, col = idx[w] - row * BN;
+                    d4[w] = reinterpret_cast<float4*>(dbase + (long long)row * p.Kc + col);
+                    old[w] = *d4[w];
+                }
+                for (int s0 = 0; s0 < nsplit; s0 += 8) {
+                    float4 v[2][8];
+#pragma unroll
+                    for (int w = 0; w < 2; ++w)
+#pragma unroll
+                        for (int u = 0; u < 8; ++u)
+                            v[w][u] = (s0 + u < nsplit) ? ld_cg_f4(pt + (long long)(s0 + u) * 128 * BN + idx[w])
+                                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int w = 0; w < 2; ++w)
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            acc[w].x += v[w][u].x; acc[w].y += v[w][u].y; acc[w].z += v[w][u].z; acc[w].w += v[w][u].w;
+                        }
+                }
+#pragma unroll
+                for (int w = 0; w < 2; ++w)
+                    if (on[w])
+                        *d4[w] = make_float4(old[w].x + acc[w].x, old[w].y + acc[w].y, old[w].z + acc[w].z, old[w].w + acc[w].w);
+            }
+            named_bar_sync(1, 128);                          // this CTA no longer reads the partial tiles
+            if (e == 0) {
+                const unsigned int old = atom_add_acq_rel_gpu(ctr_d, 1u);
+                if (old + 1u == (unsigned int)nsplit) {      // everyone is past the wait: counters back to zero
+                    *ctr_a = 0u;
+                    *ctr_d = 0u;
+                }
+            }
+        }
     }
     __syncthreads();
     if (warp == 1) {
@@ -224,6 +304,13 @@ static int launch_wgrad(const CUtensorMap& tmDy, const CUtensorMap& tmDyLo, cons
 }  // namespace sscg
 
 using namespace sscg;
+
+extern "C" int64_t sscg_conv_wgrad_ws_bytes(const SscgWgradArgs* a) {
+    if (a->BN <= 0 || a->Kc % a->BN) return -1;
+    if (a->ksplit <= 1) return 0;
+    const long long tiles = (long long)((a->Co_pad + 127) / 128) * (a->Kc / a->BN) * a->n_taps;
+    return (int64_t)kWgCtrs * 4 + tiles * a->ksplit * 128 * a->BN * 4;
+}
 
 extern "C" int sscg_conv_wgrad(const SscgWgradArgs* a, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -258,6 +345,13 @@ extern "C" int sscg_conv_wgrad(const SscgWgradArgs* a, void* stream_) {
     d.ksplit = a->ksplit; d.dw = a->dw;
     const int m_tiles = (a->Co_pad + 127) / 128;
     dim3 grid((unsigned)a->ksplit, (unsigned)(m_tiles * d.n_ktiles), (unsigned)a->n_taps);
+    d.part = nullptr; d.ctr = nullptr;
+    if (a->ksplit > 1) {
+        if (a->ws == nullptr) return set_error("conv_wgrad: ksplit > 1 needs the workspace (sscg_conv_wgrad_ws_bytes)");
+        if ((long long)grid.y * grid.z * 2 > kWgCtrs) return set_error("conv_wgrad: too many output tiles for the arrival counters");
+        d.ctr = reinterpret_cast<unsigned int*>(a->ws);
+        d.part = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(a->ws) + kWgCtrs * 4);
+    }
 #define SSCG_WG(BN_)                                                                          \
     case BN_:                                                                                  \
         return a->split == 3 ? launch_wgrad<BN_, 3>(tmDy, tmDyLo, tmX, tmXLo, d, grid, stream, a->tag) \

@@ -79,19 +79,44 @@ __device__ __forceinline__ void store8_f32(void* dst, long long off, const float
     p[0] = make_float4(v[0], v[1], v[2], v[3]);
     p[1] = make_float4(v[4], v[5], v[6], v[7]);
 }
-__device__ __forceinline__ void load_norm(const float* stats, float eps, long long sidx, float inv_cnt, float (&mean)[8],
-                                          float (&rstd)[8]) {
-    const float4* sp = reinterpret_cast<const float4*>(stats + sidx * 2);
+// Plane sums -> per-channel constants of one sample, decoded ONCE per CTA into shared memory (coalesced 32-byte reads,
+// one channel per thread and pass) and then picked up by every thread for its 8 channels.  (Per-thread decoding reads
+// 256 strided bytes per thread: 8x the L1 wavefronts of the old float statistics, +5 us per launch.)
+//   BMEANS = false: accumulators of (sum x, sum x^2)  -> (mean, rstd)
+//   BMEANS = true : accumulators of (sum dZ, sum dZ*Z) -> (mean dZ, mean dZ*Z)
+// `bar` synchronises the participating threads (all of them call this function); s_pairs holds C float2.
+template <bool BMEANS, typename Bar>
+__device__ __forceinline__ void cta_load_sums(const void* acc, long long n, int C, float inv_cnt, float eps,
+                                              float2* s_pairs, int tid, int nthreads, int c0, bool active, Bar bar,
+                                              float (&o1)[8], float (&o2)[8]) {
+    bar();                                             // earlier readers are done with s_pairs
+    const longlong2* sp = reinterpret_cast<const longlong2*>(reinterpret_cast<const long long*>(acc) + n * C * (2 * kDetWords));
+    for (int c = tid; c < C; c += nthreads) {
+        const longlong2 s1 = sp[2 * c], s2 = sp[2 * c + 1];
+        const float v1 = det_decode(s1.x, s1.y) * inv_cnt;
+        float v2 = det_decode(s2.x, s2.y) * inv_cnt;
+        if (!BMEANS) v2 = rsqrtf(fmaxf(v2 - v1 * v1, 0.f) + eps);
+        s_pairs[c] = make_float2(v1, v2);
+    }
+    bar();
+    if (active) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const float4 s = sp[q];
-        const float m0 = s.x * inv_cnt, m1 = s.z * inv_cnt;
-        mean[2 * q] = m0;
-        mean[2 * q + 1] = m1;
-        rstd[2 * q] = rsqrtf(fmaxf(s.y * inv_cnt - m0 * m0, 0.f) + eps);
-        rstd[2 * q + 1] = rsqrtf(fmaxf(s.w * inv_cnt - m1 * m1, 0.f) + eps);
+        for (int q = 0; q < 8; ++q) {
+            const float2 t = s_pairs[c0 + q];
+            o1[q] = t.x;
+            o2[q] = t.y;
+        }
     }
 }
+struct BarBlock {
+    __device__ __forceinline__ void operator()() const { __syncthreads(); }
+};
+template <int kThreads>
+struct BarNamed1 {
+    __device__ __forceinline__ void operator()() const { named_bar_sync(1, kThreads); }
+};
+constexpr int kMaxNormC = 2048;        // channel bound of the register-batched kernels (checked by the launchers)
+constexpr int kMaxStreamC = 512;       // ... of the bulk-pipelined ones (stream_geom: C / 8 <= 64)
 
 // ---------------------------------------------------------------------------------------------
 // pack: NCHW fp32 (or int64 labels -> one-hot) -> NHWC bf16 with halo
@@ -191,12 +216,15 @@ __global__ void unpack_fold_kernel(const void* __restrict__ src, int src_fp32, i
 }
 
 // bias gradient of a conv without normalisation: grad[c] += scale * sum_n bstats[n][c][0]
-__global__ void bias_grad_kernel(const float* __restrict__ bstats, int N, int C, int Cp, float* __restrict__ grad,
+__global__ void bias_grad_kernel(const long long* __restrict__ bstats, int N, int C, int Cp, float* __restrict__ grad,
                                  float scale) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     float s = 0.f;
-    for (int n = 0; n < N; ++n) s += bstats[((long long)n * Cp + c) * 2];
+    for (int n = 0; n < N; ++n) {
+        const long long* b = bstats + ((long long)n * Cp + c) * (2 * kDetWords);
+        s += det_decode(b[0], b[1]);
+    }
     grad[c] += scale * s;
 }
 
@@ -458,11 +486,12 @@ extern "C" int sscg_unpack_fold(const void* src, int32_t src_fp32, int32_t N, in
     return 0;
 }
 
-extern "C" int sscg_bias_grad(const float* bstats, int32_t N, int32_t C, int32_t Cp, float* grad, float scale,
+extern "C" int sscg_bias_grad(const void* bstats, int32_t N, int32_t C, int32_t Cp, float* grad, float scale,
                               void* stream) {
     {
         LaunchScope ls_(9, static_cast<cudaStream_t>(stream));
-        bias_grad_kernel<<<(C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(bstats, N, C, Cp, grad, scale);
+        bias_grad_kernel<<<(C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+            reinterpret_cast<const long long*>(bstats), N, C, Cp, grad, scale);
     }
     SSCG_CHECK_LAUNCH("bias_grad");
     return 0;
@@ -545,62 +574,17 @@ extern "C" int sscg_in_bwd_prep(const SscgBwdArgs* a, void* stream) {
         }
     }
     BwdDev d;
-    d.a = *a; d.draw = nullptr; d.draw_lo = nullptr; d.sync = nullptr;
+    d.a = *a; d.draw = nullptr; d.draw_lo = nullptr;
     int gridx;
     vec_layout(a->C, (long long)a->H * a->W, d.CH, d.rows, d.iters, gridx);
     {
         LaunchScope ls_(8, static_cast<cudaStream_t>(stream));
         if (a->raw_fp32 || a->dyp_fp32 || a->skip_fp32 || a->g_fp32 || a->dz_fp32 || a->dz_lo)
-            in_bwd_prep_kernel<true, false><<<dim3(gridx, a->N), 256, 0, static_cast<cudaStream_t>(stream)>>>(d);
+            in_bwd_prep_kernel<true><<<dim3(gridx, a->N), 256, 0, static_cast<cudaStream_t>(stream)>>>(d);
         else
-            in_bwd_prep_kernel<false, false><<<dim3(gridx, a->N), 256, 0, static_cast<cudaStream_t>(stream)>>>(d);
+            in_bwd_prep_kernel<false><<<dim3(gridx, a->N), 256, 0, static_cast<cudaStream_t>(stream)>>>(d);
     }
     SSCG_CHECK_LAUNCH("in_bwd_prep");
-    return 0;
-}
-
-// One-launch InstanceNorm backward (see in_bwd_prep_kernel<., true>).  Returns 3 when the samples' CTAs
-// cannot all be resident (caller falls back to prep + apply).
-extern "C" int sscg_in_bwd_fused(const SscgBwdArgs* a, void* draw, void* draw_lo, uint32_t* sync_ctr, void* stream_) {
-    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    if (a->C % 8 || a->C > 2048) return set_error("in_bwd_fused: C=%d must be a multiple of 8 (<= 2048)", a->C);
-    if (!a->stats || !a->bstats || !sync_ctr) return set_error("in_bwd_fused: needs stats, bstats and sync counters");
-    const bool any = a->raw_fp32 || a->dyp_fp32 || a->skip_fp32 || a->g_fp32 || draw_lo;
-    static int occ[2] = {0, 0};
-    if (occ[any] == 0) {
-        int o = 0;
-        cudaError_t e = any ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, in_bwd_prep_kernel<true, true>, 256, 0)
-                            : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, in_bwd_prep_kernel<false, true>, 256, 0);
-        if (e != cudaSuccess || o < 1) o = 1;
-        occ[any] = o;
-    }
-    int sms = 148, dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int capacity = sms * occ[any];
-    if (a->N > capacity) return 3;
-    BwdDev d;
-    d.a = *a; d.draw = draw; d.draw_lo = draw_lo; d.sync = sync_ctr;
-    d.CH = a->C / 8;
-    d.rows = 256 / d.CH; if (d.rows < 1) d.rows = 1;
-    const long long npix = (long long)a->H * a->W;
-    int cps = capacity / a->N;                                   // CTAs per sample, all co-resident
-    const long long min_pix = (long long)d.rows * 8;             // at least 8 pixels per thread
-    if ((long long)cps * min_pix > npix) cps = (int)((npix + min_pix - 1) / min_pix);
-    if (cps < 1) cps = 1;
-    long long per = (npix + cps - 1) / cps;                      // pixels per CTA
-    int iters = (int)((per + d.rows - 1) / d.rows);
-    iters = ((iters + kPrepBatch - 1) / kPrepBatch) * kPrepBatch;
-    d.iters = iters;
-    cps = (int)((npix + (long long)d.rows * iters - 1) / ((long long)d.rows * iters));
-    cudaError_t e = cudaMemsetAsync(sync_ctr, 0, sizeof(uint32_t) * a->N, stream);
-    if (e != cudaSuccess) return set_error("in_bwd_fused: memset: %s", cudaGetErrorString(e));
-    {
-        LaunchScope ls_(8, stream);
-        if (any) in_bwd_prep_kernel<true, true><<<dim3(cps, a->N), 256, 0, stream>>>(d);
-        else in_bwd_prep_kernel<false, true><<<dim3(cps, a->N), 256, 0, stream>>>(d);
-    }
-    SSCG_CHECK_LAUNCH("in_bwd_fused");
     return 0;
 }
 
@@ -623,7 +607,7 @@ extern "C" int sscg_in_bwd_apply(const SscgBwdArgs* a, void* draw, void* draw_lo
         }
     }
     BwdDev d;
-    d.a = *a; d.draw = draw; d.draw_lo = draw_lo; d.sync = nullptr;
+    d.a = *a; d.draw = draw; d.draw_lo = draw_lo;
     int gridx;
     vec_layout(a->C, (long long)a->H * a->W, d.CH, d.rows, d.iters, gridx);
     {

@@ -12,15 +12,69 @@ namespace sscg {
 
 constexpr int kMaxClasses = 32;
 
+// ---------------------------------------------------------------------------------------------
+// Grid-wide sums without floating-point atomics: every block stores its (up to two) partial sums to
+// its own slot of the workspace, the block that arrives last (sscg_ptx.cuh) adds the slots in a fixed
+// pattern — thread t takes slots t, t + 256, ... in order, then a fixed shuffle / shared-memory tree —
+// and writes the results.  ws: [0] arrival counter (zero between launches), [4..) float2 slots.
+// ---------------------------------------------------------------------------------------------
+constexpr int kLossWsHeader = 4;        // floats reserved in front of the slots (counter + padding)
+__device__ __forceinline__ float2 block_sum2(float a, float b, float2* s_w) {
+    for (int off = 16; off >= 1; off >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, off);
+        b += __shfl_xor_sync(0xffffffffu, b, off);
+    }
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = make_float2(a, b);
+    __syncthreads();
+    float2 t = make_float2(0.f, 0.f);
+    if (threadIdx.x == 0)
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { t.x += s_w[i].x; t.y += s_w[i].y; }
+    return t;                            // valid in thread 0
+}
+// out[0] = scale * sum of a over the grid, out[1] = sum of b (when out1 is set)
+__device__ __forceinline__ void grid_sum2_store(float a, float b, float* ws, float* out, float scale, bool out1) {
+    __shared__ float2 s_w[8];
+    __shared__ unsigned int s_last;
+    const float2 t = block_sum2(a, b, s_w);
+    float2* slots = reinterpret_cast<float2*>(ws + kLossWsHeader);
+    if (threadIdx.x == 0) {
+        slots[blockIdx.x] = t;
+        unsigned int* ctr = reinterpret_cast<unsigned int*>(ws);
+        const unsigned int old = atom_add_acq_rel_gpu(ctr, 1u);
+        const bool last = (old + 1u == gridDim.x);
+        if (last) {
+            *ctr = 0u;
+            __threadfence();
+        }
+        s_last = last ? 1u : 0u;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    float sa = 0.f, sb = 0.f;
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) {
+        const float2 v = ld_cg_f2(reinterpret_cast<const float*>(slots + i));
+        sa += v.x;
+        sb += v.y;
+    }
+    __syncthreads();                     // s_w is reused
+    const float2 r = block_sum2(sa, sb, s_w);
+    if (threadIdx.x == 0) {
+        out[0] = r.x * scale;
+        if (out1) out[1] = r.y;
+    }
+}
+
 // logits [N][C][H][W] fp32; labels [N][H][W] int64 (or null); probs [N][C][H][W] (or null);
-// argmax [N][H][W] int64 (or null); loss_sum: fp32 accumulator of -log p[label] (or null)
+// argmax [N][H][W] int64 (or null); loss_out[2] = (sum of -log p[label] over the counted pixels, their number).
+// nn.CrossEntropyLoss semantics (model.py:272): pixels whose label equals ignore_index are not counted; any other label
+// outside [0, C) raises the device error flag (torch device-asserts there) and is not counted either.
 __global__ void __launch_bounds__(256) seg_head_fwd_kernel(const float* __restrict__ logits,
                                                            const long long* __restrict__ labels, int N, int C,
-                                                           long long HW, float* __restrict__ probs,
-                                                           long long* __restrict__ argmax,
-                                                           float* __restrict__ loss_sum) {
+                                                           long long HW, long long ignore_index,
+                                                           float* __restrict__ probs, long long* __restrict__ argmax,
+                                                           float* __restrict__ loss_out, float* __restrict__ ws) {
     const long long total = (long long)N * HW;
-    float local = 0.f;
+    float local = 0.f, counted = 0.f;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
         const long long n = idx / HW, pix = idx - n * HW;
@@ -33,6 +87,19 @@ __global__ void __launch_bounds__(256) seg_head_fwd_kernel(const float* __restri
             if (c < C) {
                 v[c] = src[c * HW];
                 if (v[c] > mx) { mx = v[c]; am = c; }      // strict '>' keeps the FIRST maximum (torch.max rule)
+            }
+        }
+        float vl = 0.f;
+        bool count_it = false;
+        if (labels != nullptr && loss_out != nullptr) {
+            const long long lab = labels[idx];
+            if (lab >= 0 && lab < C) {
+                count_it = true;
+#pragma unroll
+                for (int c = 0; c < kMaxClasses; ++c)
+                    if (c == (int)lab) vl = v[c];
+            } else if (lab != ignore_index) {
+                atomicCAS(&g_sscg_dev_error, 0u, (31u << 16) | 0x80000000u);     // label outside [0, C)
             }
         }
         float sum = 0.f;
@@ -51,38 +118,25 @@ __global__ void __launch_bounds__(256) seg_head_fwd_kernel(const float* __restri
                 if (c < C) dst[c * HW] = v[c] * inv;
         }
         if (argmax != nullptr) argmax[idx] = am;
-        if (labels != nullptr && loss_sum != nullptr) {
-            const int lab = (int)labels[idx];
-            float pl = 0.f;
-#pragma unroll
-            for (int c = 0; c < kMaxClasses; ++c)
-                if (c == lab) pl = v[c];
-            local += -__logf(fmaxf(pl * inv, 1e-38f));
+        if (count_it) {
+            local += logf(sum) + mx - vl;                  // -log softmax(label) from the logits (log-sum-exp form)
+            counted += 1.f;
         }
     }
-    if (loss_sum != nullptr) {
-        for (int off = 16; off >= 1; off >>= 1) local += __shfl_xor_sync(0xffffffffu, local, off);
-        __shared__ float s[8];
-        if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = local;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            float t = 0.f;
-            for (int i = 0; i < (blockDim.x >> 5); ++i) t += s[i];
-            atomicAdd(loss_sum, t);
-        }
-    }
+    if (loss_out != nullptr) grid_sum2_store(local, counted, ws, loss_out, 1.f, true);
 }
 
 // dlogits = ce_scale * (p - onehot(label)) + p * (dp - sum_c p*dp)
-//   ce_scale: device scalar pointer (upstream gradient of the MEAN cross-entropy) times 1/(N*HW), or null
-//   dprobs:   upstream gradient w.r.t. the probabilities, or null
+//   dloss: device scalar (upstream gradient of the MEAN cross-entropy), count: device scalar (number of counted
+//          pixels, loss_out[1] of the forward), or null;   dprobs: upstream gradient w.r.t. the probabilities, or null
 __global__ void __launch_bounds__(256) seg_head_bwd_kernel(const float* __restrict__ probs,
                                                            const long long* __restrict__ labels,
                                                            const float* __restrict__ dloss,
+                                                           const float* __restrict__ count,
                                                            const float* __restrict__ dprobs, int N, int C,
                                                            long long HW, float* __restrict__ dlogits) {
     const long long total = (long long)N * HW;
-    const float ce = (dloss != nullptr && labels != nullptr) ? (*dloss) / (float)total : 0.f;
+    const float ce = (dloss != nullptr && labels != nullptr) ? (*dloss) / (*count) : 0.f;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
         const long long n = idx / HW, pix = idx - n * HW;
@@ -97,12 +151,13 @@ __global__ void __launch_bounds__(256) seg_head_bwd_kernel(const float* __restri
                 dot += p[c] * dp[c];
             }
         }
-        const int lab = labels != nullptr ? (int)labels[idx] : -1;
+        const long long lab = labels != nullptr ? labels[idx] : -1;
+        const float cew = (lab >= 0 && lab < C) ? ce : 0.f;        // ignored pixels carry no cross-entropy gradient
 #pragma unroll
         for (int c = 0; c < kMaxClasses; ++c) {
             if (c < C) {
                 float g = p[c] * (dp[c] - dot);
-                g += ce * (p[c] - (c == lab ? 1.f : 0.f));
+                g += cew * (p[c] - (c == (int)lab ? 1.f : 0.f));
                 dlogits[base + c * HW] = g;
             }
         }
@@ -116,27 +171,15 @@ __global__ void __launch_bounds__(256) seg_head_bwd_kernel(const float* __restri
 // elementwise pass each.  The reference materialises the target tensor, the difference, its square
 // (or abs) and a mean: 4-5 ATen kernels forward and 3 backward per loss; here the target is a scalar.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void block_sum_atomic(float local, float* dst, float scale) {
-    for (int off = 16; off >= 1; off >>= 1) local += __shfl_xor_sync(0xffffffffu, local, off);
-    __shared__ float s[8];
-    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = local;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        float t = 0.f;
-        for (int i = 0; i < (blockDim.x >> 5); ++i) t += s[i];
-        atomicAdd(dst, t * scale);
-    }
-}
-
-// loss_sum += scale * sum (x - target)^2
+// loss_out = scale * sum (x - target)^2
 __global__ void __launch_bounds__(256) lsgan_fwd_kernel(const float* __restrict__ x, long long n, float target,
-                                                        float scale, float* __restrict__ loss_sum) {
+                                                        float scale, float* __restrict__ loss_sum, float* __restrict__ ws) {
     float local = 0.f;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const float d = x[i] - target;
         local += d * d;
     }
-    block_sum_atomic(local, loss_sum, scale);
+    grid_sum2_store(local, 0.f, ws, loss_sum, scale, false);
 }
 // dx = dloss * 2 (x - target) / n      (dloss: device scalar, gradient of the MEAN)
 __global__ void __launch_bounds__(256) lsgan_bwd_kernel(const float* __restrict__ x, long long n, float target,
@@ -145,19 +188,27 @@ __global__ void __launch_bounds__(256) lsgan_bwd_kernel(const float* __restrict_
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         dx[i] = sc * (x[i] - target);
 }
-// loss_sum += scale * sum |x - y|
+// loss_out = scale * sum |x - y|.  VEC: both pointers are 16-byte aligned (128-bit loads); otherwise scalar loads
+// (nn.L1Loss takes any contiguous slice, e.g. l_img[rank * per : (rank + 1) * per]).
+template <bool VEC>
 __global__ void __launch_bounds__(256) l1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ y,
-                                                     long long n, float scale, float* __restrict__ loss_sum) {
+                                                     long long n, float scale, float* __restrict__ loss_sum,
+                                                     float* __restrict__ ws) {
     float local = 0.f;
-    const long long n4 = n >> 2;
-    const float4* x4 = reinterpret_cast<const float4*>(x);
-    const float4* y4 = reinterpret_cast<const float4*>(y);
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-        const float4 a = x4[i], b = y4[i];
-        local += fabsf(a.x - b.x) + fabsf(a.y - b.y) + fabsf(a.z - b.z) + fabsf(a.w - b.w);
+    if (VEC) {
+        const long long n4 = n >> 2;
+        const float4* x4 = reinterpret_cast<const float4*>(x);
+        const float4* y4 = reinterpret_cast<const float4*>(y);
+        for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+            const float4 a = x4[i], b = y4[i];
+            local += fabsf(a.x - b.x) + fabsf(a.y - b.y) + fabsf(a.z - b.z) + fabsf(a.w - b.w);
+        }
+        if (blockIdx.x == 0 && threadIdx.x < (n & 3)) local += fabsf(x[n4 * 4 + threadIdx.x] - y[n4 * 4 + threadIdx.x]);
+    } else {
+        for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+            local += fabsf(x[i] - y[i]);
     }
-    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) local += fabsf(x[n4 * 4 + threadIdx.x] - y[n4 * 4 + threadIdx.x]);
-    block_sum_atomic(local, loss_sum, scale);
+    grid_sum2_store(local, 0.f, ws, loss_sum, scale, false);
 }
 // dx = dloss * sign(x - y) / n   (sign(0) = 0, as torch)
 __global__ void __launch_bounds__(256) l1_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y,
@@ -236,32 +287,35 @@ __global__ void __launch_bounds__(256) confusion_kernel(const long long* __restr
 using namespace sscg;
 
 extern "C" int sscg_seg_head_fwd(const float* logits, const int64_t* labels, int32_t N, int32_t C, int64_t HW,
-                                 float* probs, int64_t* argmax, float* loss_sum, void* stream) {
+                                 int64_t ignore_index, float* probs, int64_t* argmax, float* loss_out, void* ws,
+                                 void* stream) {
     if (C < 1 || C > kMaxClasses) return set_error("seg_head_fwd: C=%d must be in [1, %d]", C, kMaxClasses);
+    if (loss_out != nullptr && ws == nullptr) return set_error("seg_head_fwd: the loss needs a workspace of SSCG_LOSS_WS_BYTES");
     const long long total = (long long)N * HW;
     long long g = (total + 255) / 256;
     if (g > 148 * 8) g = 148 * 8;
     {
         LaunchScope ls_(10, static_cast<cudaStream_t>(stream));
         seg_head_fwd_kernel<<<(int)g, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-            logits, reinterpret_cast<const long long*>(labels), N, C, HW, probs, reinterpret_cast<long long*>(argmax),
-            loss_sum);
+            logits, reinterpret_cast<const long long*>(labels), N, C, HW, (long long)ignore_index, probs,
+            reinterpret_cast<long long*>(argmax), loss_out, reinterpret_cast<float*>(ws));
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_error("seg_head_fwd launch: %s", cudaGetErrorString(e));
     return 0;
 }
 
-extern "C" int sscg_seg_head_bwd(const float* probs, const int64_t* labels, const float* dloss, const float* dprobs,
-                                 int32_t N, int32_t C, int64_t HW, float* dlogits, void* stream) {
+extern "C" int sscg_seg_head_bwd(const float* probs, const int64_t* labels, const float* dloss, const float* count,
+                                 const float* dprobs, int32_t N, int32_t C, int64_t HW, float* dlogits, void* stream) {
     if (C < 1 || C > kMaxClasses) return set_error("seg_head_bwd: C=%d must be in [1, %d]", C, kMaxClasses);
+    if (dloss != nullptr && labels != nullptr && count == nullptr) return set_error("seg_head_bwd: dloss needs the pixel count");
     const long long total = (long long)N * HW;
     long long g = (total + 255) / 256;
     if (g > 148 * 8) g = 148 * 8;
     {
         LaunchScope ls_(10, static_cast<cudaStream_t>(stream));
         seg_head_bwd_kernel<<<(int)g, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-            probs, reinterpret_cast<const long long*>(labels), dloss, dprobs, N, C, HW, dlogits);
+            probs, reinterpret_cast<const long long*>(labels), dloss, count, dprobs, N, C, HW, dlogits);
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_error("seg_head_bwd launch: %s", cudaGetErrorString(e));
@@ -280,11 +334,13 @@ static inline int loss_grid(long long n) {
         if (e_ != cudaSuccess) return set_error(name " launch: %s", cudaGetErrorString(e_)); \
     } while (0)
 
-extern "C" int sscg_lsgan_fwd(const float* x, int64_t n, float target, float scale, float* loss_sum, void* stream) {
-    if (!x || !loss_sum || n < 1) return set_error("lsgan_fwd: bad arguments");
+extern "C" int sscg_lsgan_fwd(const float* x, int64_t n, float target, float scale, float* loss_sum, void* ws,
+                              void* stream) {
+    if (!x || !loss_sum || !ws || n < 1) return set_error("lsgan_fwd: bad arguments");
     {
         LaunchScope ls_(10, static_cast<cudaStream_t>(stream));
-        lsgan_fwd_kernel<<<loss_grid(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, n, target, scale, loss_sum);
+        lsgan_fwd_kernel<<<loss_grid(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, n, target, scale, loss_sum,
+                                                                                     reinterpret_cast<float*>(ws));
     }
     SSCG_LOSS_LAUNCH_CHECK("lsgan_fwd");
     return 0;
@@ -298,12 +354,18 @@ extern "C" int sscg_lsgan_bwd(const float* x, int64_t n, float target, const flo
     SSCG_LOSS_LAUNCH_CHECK("lsgan_bwd");
     return 0;
 }
-extern "C" int sscg_l1_fwd(const float* x, const float* y, int64_t n, float scale, float* loss_sum, void* stream) {
-    if (!x || !y || !loss_sum || n < 1) return set_error("l1_fwd: bad arguments");
-    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) return set_error("l1_fwd: pointers must be 16-byte aligned");
+extern "C" int sscg_l1_fwd(const float* x, const float* y, int64_t n, float scale, float* loss_sum, void* ws,
+                           void* stream) {
+    if (!x || !y || !loss_sum || !ws || n < 1) return set_error("l1_fwd: bad arguments");
+    const bool vec = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
     {
         LaunchScope ls_(10, static_cast<cudaStream_t>(stream));
-        l1_fwd_kernel<<<loss_grid(n >> 2), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, y, n, scale, loss_sum);
+        if (vec)
+            l1_fwd_kernel<true><<<loss_grid(n >> 2), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+                x, y, n, scale, loss_sum, reinterpret_cast<float*>(ws));
+        else
+            l1_fwd_kernel<false><<<loss_grid(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+                x, y, n, scale, loss_sum, reinterpret_cast<float*>(ws));
     }
     SSCG_LOSS_LAUNCH_CHECK("l1_fwd");
     return 0;

@@ -89,12 +89,14 @@ __global__ void __launch_bounds__(256, SSCG_APPLY_MINB) in_apply_kernel(const __
     const int n = blockIdx.y;
     const int chunk = threadIdx.x % p.CH;
     const int row = threadIdx.x / p.CH;
-    if (row >= p.rows) return;
     const int Hp = a.H + 2 * a.pad, Wp = a.W + 2 * a.pad;
     const int c0 = chunk * 8;
     float mean[8], rstd[8];
     const bool norm = a.stats != nullptr;
-    if (norm) load_norm(a.stats, a.eps, (long long)n * a.C + c0, 1.f / (float)(a.H * a.W), mean, rstd);
+    __shared__ float2 s_pairs[kMaxNormC];
+    if (norm) cta_load_sums<false>(a.stats, n, a.C, 1.f / (float)(a.H * a.W), a.eps, s_pairs, threadIdx.x, 256, c0,
+                                   row < p.rows, BarBlock(), mean, rstd);
+    if (row >= p.rows) return;
     const bool has_res = a.res.ptr != nullptr;
     const bool res_lo = ANYF32 && a.res_lo != nullptr;
     const bool raw_f32 = ANYF32 && a.raw_fp32 != 0;
@@ -190,8 +192,8 @@ struct BwdDev {
     SscgBwdArgs a;
     void* draw; void* draw_lo;
     int CH, rows, iters;
-    unsigned int* sync;      // fused mode: one arrival counter per sample (zeroed before the launch)
 };
+
 
 // positions of the padded gradient buffer that fold onto source index s (reflect) — at most 3
 __device__ __forceinline__ int fold_positions(int s, int n, int pad, int mode, int (&q)[3]) {
@@ -212,13 +214,8 @@ __device__ __forceinline__ int fold_positions(int s, int n, int pad, int mode, i
 #endif
 constexpr int kPrepBatch = SSCG_PREP_BATCH;
 
-// FUSED = false: first half of the two-kernel backward (writes dZ, accumulates the plane sums).
-// FUSED = true : whole InstanceNorm backward in one launch.  All CTAs of a sample are co-resident
-//   (grid.x <= resident capacity / N, checked by the host); after the sums are accumulated they meet at a
-//   per-sample arrival counter, then sweep their pixels a second time — the operands were just read by
-//   the same SM partition and largely come from L2 — and write dRaw directly.  Saves the dZ write + read
-//   and one launch per stage.
-template <bool ANYF32, bool FUSED>
+// First half of the backward: writes dZ (and the folded total gradient), produces the plane sums.
+template <bool ANYF32>
 __global__ void __launch_bounds__(256, SSCG_PREP_MINB) in_bwd_prep_kernel(const __grid_constant__ BwdDev p) {
     const SscgBwdArgs& a = p.a;
     __shared__ float s_red[256 * 16];
@@ -234,15 +231,16 @@ __global__ void __launch_bounds__(256, SSCG_PREP_MINB) in_bwd_prep_kernel(const 
     const bool has_dyp = a.dyp.ptr != nullptr, has_skip = a.skip.ptr != nullptr;
     const bool dyp_f32 = ANYF32 && a.dyp_fp32 != 0, skip_f32 = ANYF32 && a.skip_fp32 != 0;
     const bool raw_f32 = ANYF32 && a.raw_fp32 != 0;
-    if (norm && active) load_norm(a.stats, a.eps, (long long)n * a.C + c0, 1.f / (float)(a.H * a.W), mean, rstd);
+    __shared__ float2 s_pairs[kMaxNormC];
+    if (norm) cta_load_sums<false>(a.stats, n, a.C, 1.f / (float)(a.H * a.W), a.eps, s_pairs, threadIdx.x, 256, c0, active,
+                                   BarBlock(), mean, rstd);
     const uint64_t seed = (a.drop_seed != 0 && a.drop_ctr) ? (a.drop_seed ^ (*a.drop_ctr * 0x9E3779B97F4A7C15ull))
                                                            : a.drop_seed;
     float acc1[8], acc2[8];
 #pragma unroll
     for (int q = 0; q < 8; ++q) acc1[q] = acc2[q] = 0.f;
     const int npix = a.H * a.W;
-    float m1[8], m2[8];      // plane means of dZ and dZ*Z (second sweep of the fused mode)
-    auto sweep = [&](const int pass) {
+    auto sweep = [&]() {
         PixWalk walk(blockIdx.x * p.rows * p.iters + row, a.W);
         const long long obase = (long long)n * npix * a.C + c0;                 // raw / dz / g_out (unpadded NHWC)
         const long long ybase = (long long)n * a.dyp.sN + (long long)a.pad * a.dyp.sH + (long long)a.pad * a.dyp.sW + c0;
@@ -303,7 +301,7 @@ __global__ void __launch_bounds__(256, SSCG_PREP_MINB) in_bwd_prep_kernel(const 
 #pragma unroll
                     for (int q = 0; q < 8; ++q) g[q] += t[q];
                 }
-                if (a.g_out != nullptr && pass == 1) {
+                if (a.g_out != nullptr) {
                     if (ANYF32 && a.g_fp32) store8_f32(a.g_out, off, g);
                     else store8_bf16(a.g_out, nullptr, off, g);
                 }
@@ -332,13 +330,7 @@ __global__ void __launch_bounds__(256, SSCG_PREP_MINB) in_bwd_prep_kernel(const 
 #pragma unroll
                     for (int q = 0; q < 8; ++q) z[q] = 0.f;
                 }
-                if (FUSED && pass == 2) {
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) g[q] = rstd[q] * (g[q] - m1[q] - z[q] * m2[q]);
-                    store8_bf16(p.draw, ANYF32 ? p.draw_lo : nullptr, off, g);
-                    continue;
-                }
-                if (!FUSED) {
+                {
                     const long long doff = a.dz_pad > 0
                         ? ((((long long)n * (a.H + 2 * a.dz_pad) + ph[b] + a.dz_pad) * (a.W + 2 * a.dz_pad) + pw[b] + a.dz_pad) * a.C + c0)
                         : off;
@@ -353,7 +345,7 @@ __global__ void __launch_bounds__(256, SSCG_PREP_MINB) in_bwd_prep_kernel(const 
             }
         }
     };
-    if (active) sweep(1);
+    if (active) sweep();
     if (a.bstats == nullptr) return;
     // block reduction over the pixel rows that share a channel vector: one smem pass, one sync
     {
@@ -366,42 +358,14 @@ __global__ void __launch_bounds__(256, SSCG_PREP_MINB) in_bwd_prep_kernel(const 
     }
     __syncthreads();
     const int nout = p.CH * 16;    // (chunk, q, {sum, sum*z}) values of this block
+    unsigned long long* bacc = reinterpret_cast<unsigned long long*>(a.bstats) + (long long)n * a.C * 2 * kDetWords;
     for (int o = threadIdx.x; o < nout; o += 256) {
         const int ch = o >> 4, e = o & 15;
         float s = 0.f;
         for (int r = 0; r < p.rows; ++r) s += s_red[(r * p.CH + ch) * 16 + e];
-        // e = 2*q + k  ->  bstats[(n*C + ch*8 + q)*2 + k]
-        atomicAdd(a.bstats + ((long long)n * a.C + ch * 8) * 2 + e, s);
+        // o = ch * 16 + 2 * q + k  ->  accumulator of bstats[n][ch * 8 + q][k]: order-independent integer sums (sscg_ptx.cuh)
+        det_red_add(bacc + (long long)o * kDetWords, s);
     }
-    if (!FUSED) return;
-    // ---- all CTAs of this sample have added their partial sums? ------------------------------------
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        atomicAdd(p.sync + n, 1u);
-        const uint64_t t0 = globaltimer_ns();
-        unsigned int spins = 0;
-        while (*reinterpret_cast<volatile unsigned int*>(p.sync + n) < gridDim.x) {
-            if ((++spins & 0xfff) == 0 && globaltimer_ns() - t0 > SSCG_WAIT_TIMEOUT_NS) {
-                atomicCAS(&g_sscg_dev_error, 0u, (9u << 16) | (blockIdx.x & 0xffff) | 0x80000000u);
-                __threadfence_system();
-                __trap();
-            }
-        }
-        __threadfence();
-    }
-    __syncthreads();
-    if (!active) return;
-    {
-        const float inv_cnt = 1.f / (float)npix;
-        const float* bp = a.bstats + ((long long)n * a.C + c0) * 2;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            m1[q] = __ldcg(bp + 2 * q) * inv_cnt;       // L2 (the sums were produced by atomics of other SMs)
-            m2[q] = __ldcg(bp + 2 * q + 1) * inv_cnt;
-        }
-    }
-    sweep(2);
 }
 
 #ifndef SSCG_BAPPLY_BATCH
@@ -418,21 +382,14 @@ __global__ void __launch_bounds__(256, SSCG_BAPPLY_MINB) in_bwd_apply_kernel(con
     const int n = blockIdx.y;
     const int chunk = threadIdx.x % p.CH;
     const int row = threadIdx.x / p.CH;
-    if (row >= p.rows) return;
     const int c0 = chunk * 8;
     const float inv_cnt = 1.f / (float)(a.H * a.W);
     const bool raw_f32 = ANYF32 && a.raw_fp32 != 0, dz_f32 = ANYF32 && a.dz_fp32 != 0;
     float mean[8], rstd[8], m1[8], m2[8];
-    load_norm(a.stats, a.eps, (long long)n * a.C + c0, inv_cnt, mean, rstd);
-    {
-        const float4* bp = reinterpret_cast<const float4*>(a.bstats + ((long long)n * a.C + c0) * 2);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const float4 s = bp[q];
-            m1[2 * q] = s.x * inv_cnt; m2[2 * q] = s.y * inv_cnt;
-            m1[2 * q + 1] = s.z * inv_cnt; m2[2 * q + 1] = s.w * inv_cnt;
-        }
-    }
+    __shared__ float2 s_pairs[kMaxNormC];
+    cta_load_sums<false>(a.stats, n, a.C, inv_cnt, a.eps, s_pairs, threadIdx.x, 256, c0, row < p.rows, BarBlock(), mean, rstd);
+    cta_load_sums<true>(a.bstats, n, a.C, inv_cnt, 0.f, s_pairs, threadIdx.x, 256, c0, row < p.rows, BarBlock(), m1, m2);
+    if (row >= p.rows) return;
     const int npix = a.H * a.W;
     const int pix0 = blockIdx.x * p.rows * p.iters + row;
     const long long obase = (long long)n * npix * a.C + c0;

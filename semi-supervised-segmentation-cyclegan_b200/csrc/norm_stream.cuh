@@ -136,6 +136,7 @@ struct ApplyStreamDev {
 template <int kStrThreads>
 __global__ void __launch_bounds__(kStrThreads + 32, 1) in_apply_stream_kernel(const __grid_constant__ ApplyStreamDev p) {
     extern __shared__ uint8_t smem_raw[];
+    __shared__ float2 s_pairs[kMaxStreamC];
     const SscgApplyArgs& a = p.a;
     const StreamGeom& g = p.g;
     const StreamRing ring = stream_ring_init<kStrThreads>(smem_raw, g);
@@ -179,7 +180,8 @@ __global__ void __launch_bounds__(kStrThreads + 32, 1) in_apply_stream_kernel(co
         const int n = up.n, h = up.h, w0 = up.w0;
         if (n != cur_n) {
             cur_n = n;
-            if (norm) load_norm(a.stats, a.eps, (long long)n * a.C + c0, 1.f / (float)(a.H * a.W), mean, rstd);
+            if (norm) cta_load_sums<false>(a.stats, n, a.C, 1.f / (float)(a.H * a.W), a.eps, s_pairs, threadIdx.x, kStrThreads,
+                                           c0, true, BarNamed1<kStrThreads>(), mean, rstd);
         }
         int hm1 = -1, hm2 = -1;
         if (reflect) mirror_pos(h, a.H, a.pad, hm1, hm2);
@@ -264,7 +266,7 @@ struct BwdStreamDev {
 // (A first version used shared-memory float atomics: kStrThreads / CH-way contended CAS loops, ~6 us per
 // flush — as much as the whole streaming part of the kernel.)
 template <int kStrThreads>
-__device__ __forceinline__ void stream_flush_stats(float* s_red, float (&acc1)[8], float (&acc2)[8], float* bstats,
+__device__ __forceinline__ void stream_flush_stats(float* s_red, float (&acc1)[8], float (&acc2)[8], void* bstats,
                                                    int n, int C, int CH, int chunk) {
     const int row = threadIdx.x / CH, rows = kStrThreads / CH, width = CH * 16;
     float4* mine = reinterpret_cast<float4*>(s_red + row * width + chunk * 16);
@@ -278,8 +280,8 @@ __device__ __forceinline__ void stream_flush_stats(float* s_red, float (&acc1)[8
     for (int o = threadIdx.x; o < width; o += kStrThreads) {
         float t = 0.f;
         for (int r = 0; r < rows; ++r) t += s_red[r * width + o];
-        // o = ch * 16 + 2 * q + k  ->  bstats[(n * C + ch * 8 + q) * 2 + k]
-        atomicAdd(bstats + (long long)n * C * 2 + o, t);
+        // o = ch * 16 + 2 * q + k  ->  accumulator of bstats[n][ch * 8 + q][k]: order-independent integer sums (sscg_ptx.cuh)
+        det_red_add(reinterpret_cast<unsigned long long*>(bstats) + ((long long)n * C * 2 + o) * kDetWords, t);
     }
     named_bar_sync(1, kStrThreads);
 }
@@ -292,6 +294,7 @@ template <int kStrThreads, int SPEC>
 __global__ void __launch_bounds__(kStrThreads + 32, 1) in_bwd_prep_stream_kernel(const __grid_constant__ BwdStreamDev p) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(16) float s_red[kStrThreads * 16];
+    __shared__ float2 s_pairs[kMaxStreamC];
     const SscgBwdArgs& a = p.a;
     const StreamGeom& g = p.g;
     const StreamRing ring = stream_ring_init<kStrThreads>(smem_raw, g);
@@ -351,7 +354,8 @@ __global__ void __launch_bounds__(kStrThreads + 32, 1) in_bwd_prep_stream_kernel
         if (n != cur_n) {
             if (cur_n >= 0 && a.bstats != nullptr) stream_flush_stats<kStrThreads>(s_red, acc1, acc2, a.bstats, cur_n, a.C, g.CH, chunk);
             cur_n = n;
-            if (norm) load_norm(a.stats, a.eps, (long long)n * a.C + c0, 1.f / (float)(a.H * a.W), mean, rstd);
+            if (norm) cta_load_sums<false>(a.stats, n, a.C, 1.f / (float)(a.H * a.W), a.eps, s_pairs, threadIdx.x, kStrThreads,
+                                           c0, true, BarNamed1<kStrThreads>(), mean, rstd);
         }
         int hm1 = -1, hm2 = -1;
         if (fold) mirror_pos(h, a.H, a.pad, hm1, hm2);
@@ -466,6 +470,7 @@ __global__ void __launch_bounds__(kStrThreads + 32, 1) in_bwd_prep_stream_kernel
 template <int kStrThreads>
 __global__ void __launch_bounds__(kStrThreads + 32, 1) in_bwd_apply_stream_kernel(const __grid_constant__ BwdStreamDev p) {
     extern __shared__ uint8_t smem_raw[];
+    __shared__ float2 s_pairs[kMaxStreamC];
     const SscgBwdArgs& a = p.a;
     const StreamGeom& g = p.g;
     const StreamRing ring = stream_ring_init<kStrThreads>(smem_raw, g);
@@ -500,14 +505,10 @@ __global__ void __launch_bounds__(kStrThreads + 32, 1) in_bwd_apply_stream_kerne
         const int n = u / g.ups;
         if (n != cur_n) {
             cur_n = n;
-            load_norm(a.stats, a.eps, (long long)n * a.C + c0, inv_cnt, mean, rstd);
-            const float4* bp = reinterpret_cast<const float4*>(a.bstats + ((long long)n * a.C + c0) * 2);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const float4 s = bp[q];
-                m1[2 * q] = s.x * inv_cnt; m2[2 * q] = s.y * inv_cnt;
-                m1[2 * q + 1] = s.z * inv_cnt; m2[2 * q + 1] = s.w * inv_cnt;
-            }
+            cta_load_sums<false>(a.stats, n, a.C, inv_cnt, a.eps, s_pairs, threadIdx.x, kStrThreads, c0, true,
+                                 BarNamed1<kStrThreads>(), mean, rstd);
+            cta_load_sums<true>(a.bstats, n, a.C, inv_cnt, 0.f, s_pairs, threadIdx.x, kStrThreads, c0, true,
+                                BarNamed1<kStrThreads>(), m1, m2);
         }
         mbar_wait(ring.full(k), ring.parity(k), 13);
         const uint32_t st = ring.stage(k);

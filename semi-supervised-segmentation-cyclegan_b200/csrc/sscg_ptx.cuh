@@ -200,6 +200,80 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_ma
            (static_cast<uint32_t>(M >> 4) << 24);
 }
 
+
+// ----------------------------------------------------------------------------------------------
+// Reproducible cross-CTA sums.
+//
+// (1) Binned fixed-point accumulators (InstanceNorm plane sums, forward and backward): a float partial sum p is split
+//     exactly into hi = rint(p * 2^8) and lo = rint((p - hi * 2^-8) * 2^56) and both parts are added to 64-bit
+//     INTEGER accumulators with red.global.add.u64.  Integer addition is associative, so the totals — and the float
+//     decoded from them — do not depend on the order in which CTAs arrive: bit-reproducible without any fence,
+//     counter or extra launch (floating-point atomics are not: the earlier version differed from run to run).
+//     Resolution 2^-56 (1.4e-17) absolute per partial; |p| < 2^40 and up to 2^15 partials per accumulator keep both
+//     words far from overflow (|lo| <= 2^47 per partial).
+// (2) Fixed-order reductions through a workspace (split-K weight gradients, loss sums): contributors store partials to
+//     slots of their own and bump an arrival counter with a gpu-scope acq_rel atomic; the slots are then summed in
+//     slot order (by the last arriver, or slice-wise by every contributor once all have arrived).
+// ----------------------------------------------------------------------------------------------
+constexpr int kDetWords = 2;                      // 64-bit words per accumulated value
+__device__ __forceinline__ void det_red_add(unsigned long long* acc, float p) {
+    p = fminf(fmaxf(p, -1.0995116e12f), 1.0995116e12f);            // +-2^40: keeps the integer conversion defined
+    const float hi_f = rintf(p * 256.f);
+    const float r = p - hi_f * 0.00390625f;                         // exact: the bits of p below 2^-8 (|r| <= 2^-9)
+    const long long hi = __float2ll_rn(hi_f);
+    const long long lo = __float2ll_rn(r * 72057594037927936.f);    // 2^56
+    atomicAdd(acc, static_cast<unsigned long long>(hi));            // result unused: compiles to RED
+    atomicAdd(acc + 1, static_cast<unsigned long long>(lo));
+}
+// hi * 2^-8 + lo * 2^-56 as a float: each word as sign and magnitude, the magnitude from its 32-bit halves with fp32
+// FMAs (no fp64, no 64-bit conversions).  A pure function of the integers, hence as reproducible as they are;
+// relative error ~2^-23 of the larger word's contribution (fp32 level).
+__device__ __forceinline__ float det_word(long long x, float scale_hi, float scale_lo) {
+    const bool neg = x < 0;
+    const unsigned long long m = neg ? static_cast<unsigned long long>(-x) : static_cast<unsigned long long>(x);
+    const float v = fmaf(static_cast<float>(static_cast<unsigned int>(m >> 32)), scale_hi,
+                         static_cast<float>(static_cast<unsigned int>(m)) * scale_lo);
+    return neg ? -v : v;
+}
+__device__ __forceinline__ float det_decode(long long hi, long long lo) {
+    return det_word(hi, 16777216.f, 0.00390625f) +                                 // 2^24, 2^-8
+           det_word(lo, 5.9604644775390625e-8f, 1.3877787807814457e-17f);          // 2^-24, 2^-56
+}
+
+__device__ __forceinline__ unsigned int atom_add_acq_rel_gpu(unsigned int* addr, unsigned int v) {
+    unsigned int old;
+    asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(addr), "r"(v) : "memory");
+    return old;
+}
+__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* addr) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(addr) : "memory");
+    return v;
+}
+// Bounded spin until *addr >= target (all co-resident contributors have arrived); a protocol bug traps after ~2 s.
+__device__ __forceinline__ void spin_until_ge(const unsigned int* addr, unsigned int target, uint32_t code) {
+    if (ld_acquire_gpu(addr) >= target) return;
+    const uint64_t t0 = globaltimer_ns();
+    uint32_t spins = 0;
+    while (ld_acquire_gpu(addr) < target) {
+        if ((++spins & 0xff) == 0 && globaltimer_ns() - t0 > SSCG_WAIT_TIMEOUT_NS) {
+            atomicCAS(&g_sscg_dev_error, 0u, (code << 16) | (blockIdx.x & 0xffff) | 0x80000000u);
+            __threadfence_system();
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ float2 ld_cg_f2(const float* p) {
+    float2 v;
+    asm volatile("ld.global.cg.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float4 ld_cg_f4(const float* p) {
+    float4 v;
+    asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+
 // ----------------------------------------------------------------------------------------------
 // misc
 // ----------------------------------------------------------------------------------------------

@@ -192,7 +192,9 @@ class NetPlan:
         self.Cout = specs[-1].Cout
         self.ctx_pool: List[Ctx] = []
         self.drop_ctr = None      # optional device int64 counter mixed into dropout seeds (CUDA-graph replays)
-        self.fused_in_bwd = False  # one-launch InstanceNorm backward (sscg_in_bwd_fused): correct but slower than prep+apply on B200 (78 vs 64 us per residual stage), kept as an option
+        # scratch of the fixed-order split-K reduction of the weight gradients (all of a plan's wgrad launches are
+        # ordered on one stream)
+        self.ws_wg = K.WsPool(device)
         self.overlap_wgrad = False  # side-stream wgrad: measured no gain on B200 (power-capped, GEMMs contend); kept as an option
         self._scratch_ready = False
         self._args_cache = {}
@@ -220,14 +222,14 @@ class NetPlan:
             if s.norm:
                 c.raw.append(K.ActBuf(N, ho, wo, wt.Co_pitch, 0, self.device, fp32=sp))
                 c.stat_off.append(nstat)
-                nstat += N * wt.Co_pitch * 2
+                nstat += N * wt.Co_pitch * 2 * L.SSCG_STAT_WORDS
             elif not self._direct(s):
                 c.raw.append(K.ActBuf(N, ho, wo, wt.Co_pitch, 0, self.device, fp32=True))
                 c.stat_off.append(-1)
             else:
                 c.raw.append(None)
                 c.stat_off.append(-1)
-        c.stats = torch.zeros(max(nstat, 2), dtype=torch.float32, device=self.device)
+        c.stats = torch.zeros(max(nstat, 2), dtype=torch.int64, device=self.device)      # binned plane sums
         last = self.weights[-1]
         c.out = K.ActBuf(N, self.Hout, self.Wout, last.Co_pitch, 0, self.device, fp32=True)
         return c
@@ -291,15 +293,14 @@ class NetPlan:
                     if key not in self._flat_bufs:
                         self._flat_bufs[key] = [K.ActBuf(N, ho, wo, wt.Co_pitch, 2, dev) for _ in range(2)]
                     self.draw_flat[i] = self._flat_bufs[key][i & 1]
-        self.sync_ctr = torch.zeros(max(N, 1), dtype=torch.int32, device=dev)
         self.tbuf = [None, None]   # residual-path total gradients (ping-pong), allocated lazily
-        nb = sum(N * wt.Co_pitch * 2 for wt in self.weights)
-        self.bstats = torch.zeros(nb, dtype=torch.float32, device=dev)
+        nb = sum(N * wt.Co_pitch * 2 * L.SSCG_STAT_WORDS for wt in self.weights)
+        self.bstats = torch.zeros(nb, dtype=torch.int64, device=dev)                      # binned plane sums
         self.bstat_off = []
         o = 0
         for wt in self.weights:
             self.bstat_off.append(o)
-            o += N * wt.Co_pitch * 2
+            o += N * wt.Co_pitch * 2 * L.SSCG_STAT_WORDS
         self._scratch_ready = True
 
     def _tbuf(self, which, like: K.ActBuf):
@@ -327,7 +328,7 @@ class NetPlan:
         """x: NCHW fp32 (or labels int64 N x 1 x H x W to be one-hot encoded on the fly).
         Leaves the fp32 NHWC result in c.out; returns c."""
         sp = self.split
-        c.stats.zero_()
+        c.stats.zero_()          # plane-sum accumulators (the GEMM epilogues add into them)
         s0 = self.specs[0]
         mode0 = L.PAD_REFLECT if s0.in_reflect else L.PAD_ZERO
         if labels is not None:
@@ -438,16 +439,14 @@ class NetPlan:
             if overlap and wg_pending[par]:
                 main.wait_event(self.ev_wg[par])          # the wgrad that last read this dRaw buffer is done
                 wg_pending[par] = False
-            if not (use_apply and self.fused_in_bwd and i not in self.draw_nx and i not in self.draw_flat and
-                    K.run_bwd_fused(ba, self.draws[par], self.draws_lo[par], self.sync_ctr)):
-                K.run_bwd_prep(ba)
-                if use_apply:
-                    if i in self.draw_nx:
-                        K.run_bwd_apply(ba, self.draw_nx[i].hi, None)
-                    elif i in self.draw_flat:
-                        K.run_bwd_apply(ba, self.draw_flat[i].hi, None)
-                    else:
-                        K.run_bwd_apply(ba, self.draws[par], self.draws_lo[par])
+            K.run_bwd_prep(ba)
+            if use_apply:
+                if i in self.draw_nx:
+                    K.run_bwd_apply(ba, self.draw_nx[i].hi, None)
+                elif i in self.draw_flat:
+                    K.run_bwd_apply(ba, self.draw_flat[i].hi, None)
+                else:
+                    K.run_bwd_apply(ba, self.draws[par], self.draws_lo[par])
             self.draw, self.draw_lo = self.draws[par], self.draws_lo[par]
             if wa is not None and not overlap:
                 K.run_wgrad(wa)
@@ -547,14 +546,14 @@ class NetPlan:
             if s.kind == "convT":
                 table = G.taps_convT_dgrad(s.k, s.k, s.stride, s.pad)
                 wa = K.wgrad_args(xview, xlo, dview, dlo, table, wt.wg_Kc, wt.wg_rows, wt.dw, wt.wg_taps * wt.wg_rows,
-                                  split=sp, tag=6)
+                                  split=sp, tag=6, ws_pool=self.ws_wg)
             else:
                 table = self._fwd_table(s)
                 if wt.wg_window:
                     table = G.taps_conv_fwd_window(s.k, 1, 0)
                     xview, xlo = c.act[i].window_view(wt.wg_Kc), None
                 wa = K.wgrad_args(dview, dlo, xview, xlo, table, wt.wg_Kc, wt.wg_rows, wt.dw, wt.wg_taps * wt.wg_rows,
-                                  split=sp, tag=3 if s.name.startswith("res") else 6)
+                                  split=sp, tag=3 if s.name.startswith("res") else 6, ws_pool=self.ws_wg)
         # ---- 3. dgrad ------------------------------------------------------------------------
         da = None
         dkw = {}
@@ -612,13 +611,14 @@ class NetPlan:
         [(weight, bias) for every stage]; biases cancelled by InstanceNorm get exact zeros."""
         out = []
         for i, (s, wt) in enumerate(zip(self.specs, self.weights)):
+            # with `into`, a None entry is a parameter without a gradient buffer (frozen): nothing to add there
             gw = torch.zeros_like(s.weight, dtype=torch.float32) if into is None else into[i][0]
-            if weights:
+            if weights and gw is not None:
                 K.run_wgrad_unpack(wt.unpack_wg, wt.dw, gw, scale)
             gb = None
             if s.bias is not None:
                 gb = torch.zeros_like(s.bias, dtype=torch.float32) if into is None else into[i][1]
-                if not s.norm:
+                if not s.norm and gb is not None:
                     K.bias_grad(self.bstats[self.bstat_off[i]:], self.N, s.Cout, wt.Co_pitch, gb, scale)
             out.append((gw, gb))
         return out

@@ -83,6 +83,41 @@ class ActBuf:
         return t
 
 
+class WsPool:
+    """Grow-only zeroed device scratch for the fixed-order reductions (statistics / plane sums / split-K partials):
+    arrival counters at the head (every launch leaves them zero) + partial slots.  One pool serves launches that
+    are ordered on one stream; an argument block keeps the tensor it points into alive (`_keep`)."""
+
+    def __init__(self, device="cuda"):
+        self.device, self.buf = device, None
+
+    def get(self, nbytes):
+        if nbytes is None or nbytes <= 0:
+            return None
+        if self.buf is None or self.buf.numel() < nbytes:
+            self.buf = torch.zeros(int(nbytes) + 256, dtype=torch.uint8, device=self.device)
+        return self.buf
+
+
+_DEFAULT_POOLS = {}
+
+
+def default_pool(kind, device="cuda"):
+    """Pools used when a caller (kernel tests, tools) does not bring its own."""
+    key = (kind, str(torch.device(device)))
+    if key not in _DEFAULT_POOLS:
+        _DEFAULT_POOLS[key] = WsPool(device)
+    return _DEFAULT_POOLS[key]
+
+
+def _attach_ws(a, field, nbytes, pool, kind):
+    if nbytes < 0:
+        raise L.SscgError("workspace query failed for " + kind)
+    buf = (pool or default_pool(kind)).get(nbytes)
+    setattr(a, field, _ptr(buf))
+    a._keep = getattr(a, "_keep", []) + [buf]
+
+
 def fill_taps(dst_taps, table: TapTable):
     assert len(table.taps) <= L.SSCG_MAX_TAPS, "too many taps"
     for i, (dh, dw, brow) in enumerate(table.taps):
@@ -91,7 +126,7 @@ def fill_taps(dst_taps, table: TapTable):
 
 def conv_args(xview, x_lo, table: TapTable, Kc, w, w_lo, w_rows, Co_pad, y_ptr, y_fp32, y_strides, y_off, Ho, Wo,
               bias=None, act=L.ACT_NONE, slope=0.2, stats=None, BN=None, tile=None, split=1, tag=4,
-              shift_kw=0, shift_brow_step=1, shift_base_mode=2, flat=None):
+              shift_kw=0, shift_brow_step=1, shift_base_mode=2, flat=None, ws_pool=None):
     a = L.ConvArgs()
     a.x = xview
     a.x_lo = x_lo
@@ -126,7 +161,7 @@ def conv_args(xview, x_lo, table: TapTable, Kc, w, w_lo, w_rows, Co_pad, y_ptr, 
 
 
 def wgrad_args(dyview, dy_lo, xview, x_lo, table: TapTable, Kc, Co_pad, dw, w_rows, BN=None, tile=None, ksplit=None,
-               split=1, tag=6):
+               split=1, tag=6, ws_pool=None):
     assert table.n_phases == 1
     a = L.WgradArgs()
     a.dy, a.dy_lo, a.x, a.x_lo = dyview, dy_lo, xview, x_lo
@@ -150,6 +185,7 @@ def wgrad_args(dyview, dy_lo, xview, x_lo, table: TapTable, Kc, Co_pad, dw, w_ro
         ksplit = pick_ksplit(ctas, blocks)
     a.ksplit = ksplit
     a.tag = tag
+    _attach_ws(a, "ws", L.lib().sscg_conv_wgrad_ws_bytes(C.byref(a)), ws_pool, "wgrad")
     return a
 
 
@@ -205,13 +241,22 @@ def run_bwd_apply(a, draw, draw_lo=None):
     L.check(L.lib().sscg_in_bwd_apply(C.byref(a), _ptr(draw), _ptr(draw_lo), _stream()), "sscg_in_bwd_apply")
 
 
-def run_bwd_fused(a, draw, draw_lo, sync_ctr):
-    """One-launch InstanceNorm backward; returns False when the caller must fall back to prep + apply."""
-    rc = L.lib().sscg_in_bwd_fused(C.byref(a), _ptr(draw), _ptr(draw_lo), _ptr(sync_ctr), _stream())
-    if rc == 3:
-        return False
-    L.check(rc, "sscg_in_bwd_fused")
-    return True
+def stats_buffer(N, Cc, device="cuda"):
+    """Zeroed plane-sum accumulators [N][C][2][SSCG_STAT_WORDS] (int64; binned fixed point, include/sscg_b200.h)."""
+    return torch.zeros(N, Cc, 2, L.SSCG_STAT_WORDS, dtype=torch.int64, device=device)
+
+
+def stats_encode(values):
+    """float [..., 2] plane sums -> int64 [..., 2, SSCG_STAT_WORDS] in the kernels' accumulator format."""
+    v = values.double()
+    hi = torch.round(v * 256.0)
+    lo = torch.round((v - hi / 256.0) * 2.0 ** 56)
+    return torch.stack([hi, lo], dim=-1).to(torch.int64).contiguous()
+
+
+def stats_decode(acc):
+    """int64 [..., SSCG_STAT_WORDS] accumulators -> float32 values (the rounding the kernels apply)."""
+    return (acc[..., 0].double() / 256.0 + acc[..., 1].double() * 2.0 ** -56).float()
 
 
 def wprep_args(w, transposed, Co, Ci, KH, KW, mode, Cp, rows_pad, Kc, dst, dst_lo=None):

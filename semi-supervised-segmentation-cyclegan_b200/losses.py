@@ -12,44 +12,63 @@ from . import _lib as L
 from .kernels import _ptr, _stream
 
 
+_LOSS_WS = {}
+
+
+def _loss_ws(device):
+    """Scratch of the fixed-order loss reductions (SSCG_LOSS_WS_BYTES, zeroed once; every launch leaves its arrival
+    counter zero).  One per (device, stream): launches that share it are ordered."""
+    key = (str(device), torch.cuda.current_stream(device).cuda_stream)
+    ws = _LOSS_WS.get(key)
+    if ws is None:
+        ws = _LOSS_WS[key] = torch.zeros(L.SSCG_LOSS_WS_BYTES, dtype=torch.uint8, device=device)
+    return ws
+
+
 class _SegHead(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, logits, labels, want_probs):
+    def forward(ctx, logits, labels, ignore_index):
         ctx.set_materialize_grads(False)        # unused outputs arrive as None, not as zero tensors
+        assert logits.is_cuda and logits.dtype == torch.float32, "seg_head: CUDA fp32 logits"
         logits = logits.contiguous()
         N, Cc, H, W = logits.shape
         dev = logits.device
         probs = torch.empty_like(logits)
         argmax = torch.empty((N, H, W), dtype=torch.int64, device=dev)
-        loss = torch.zeros((), dtype=torch.float32, device=dev)
+        out = torch.zeros(2, dtype=torch.float32, device=dev)      # (sum of -log p[label], counted pixels)
         lab = None
         if labels is not None:
-            lab = labels.reshape(N, H, W).contiguous()
-        L.check(L.lib().sscg_seg_head_fwd(_ptr(logits), _ptr(lab), N, Cc, H * W, _ptr(probs), _ptr(argmax),
-                                          _ptr(loss) if lab is not None else None, _stream()), "sscg_seg_head_fwd")
-        if lab is not None:
-            loss = loss / float(N * H * W)
-        ctx.save_for_backward(probs, lab if lab is not None else torch.empty(0, device=dev))
+            if labels.is_floating_point() or labels.numel() != N * H * W:
+                raise TypeError("seg_head: labels must be an integer map with N*H*W elements (nn.CrossEntropyLoss target)")
+            lab = labels.reshape(N, H, W).long().contiguous()        # int64 is what the kernel reads
+        L.check(L.lib().sscg_seg_head_fwd(_ptr(logits), _ptr(lab), N, Cc, H * W, int(ignore_index), _ptr(probs),
+                                          _ptr(argmax), _ptr(out) if lab is not None else None, _ptr(_loss_ws(dev)),
+                                          _stream()), "sscg_seg_head_fwd")
+        loss = out[0] / out[1] if lab is not None else out[0]      # mean over the counted pixels (reduction='mean')
+        ctx.save_for_backward(probs, lab if lab is not None else torch.empty(0, device=dev), out)
         ctx.has_labels = lab is not None
         ctx.mark_non_differentiable(argmax)
         return loss, probs, argmax
 
     @staticmethod
     def backward(ctx, dloss, dprobs, _dargmax):
-        probs, lab = ctx.saved_tensors
+        probs, lab, out = ctx.saved_tensors
         N, Cc, H, W = probs.shape
         dlogits = torch.empty_like(probs)
         lab_p = lab if ctx.has_labels else None
         dl = dloss.contiguous().float() if (dloss is not None and ctx.has_labels) else None
         dp = dprobs.contiguous() if dprobs is not None else None
-        L.check(L.lib().sscg_seg_head_bwd(_ptr(probs), _ptr(lab_p), _ptr(dl), _ptr(dp), N, Cc, H * W, _ptr(dlogits),
-                                          _stream()), "sscg_seg_head_bwd")
+        L.check(L.lib().sscg_seg_head_bwd(_ptr(probs), _ptr(lab_p), _ptr(dl), _ptr(out, 4) if dl is not None else None,
+                                          _ptr(dp), N, Cc, H * W, _ptr(dlogits), _stream()), "sscg_seg_head_bwd")
         return dlogits, None, None
 
 
-def seg_head(logits, labels=None):
-    """-> (mean cross-entropy (0 if labels is None), softmax probabilities, argmax label map)."""
-    return _SegHead.apply(logits, labels, True)
+def seg_head(logits, labels=None, ignore_index=-100):
+    """-> (mean cross-entropy (0 if labels is None), softmax probabilities, argmax label map).
+    nn.CrossEntropyLoss semantics for the labels: pixels equal to ignore_index are left out of the mean and of the
+    gradient; any other label outside [0, C) raises the device error flag (kernels.device_error() -> code 31;
+    torch device-asserts on those)."""
+    return _SegHead.apply(logits, labels, ignore_index)
 
 
 class _LsganLoss(torch.autograd.Function):
@@ -58,8 +77,9 @@ class _LsganLoss(torch.autograd.Function):
         x = x.contiguous()
         assert x.dtype == torch.float32 and x.is_cuda
         n = x.numel()
-        loss = torch.zeros((), dtype=torch.float32, device=x.device)
-        L.check(L.lib().sscg_lsgan_fwd(_ptr(x), n, float(target), 1.0 / n, _ptr(loss), _stream()), "sscg_lsgan_fwd")
+        loss = torch.empty((), dtype=torch.float32, device=x.device)
+        L.check(L.lib().sscg_lsgan_fwd(_ptr(x), n, float(target), 1.0 / n, _ptr(loss), _ptr(_loss_ws(x.device)), _stream()),
+                "sscg_lsgan_fwd")
         ctx.save_for_backward(x)
         ctx.target = float(target)
         return loss
@@ -84,8 +104,9 @@ class _L1Loss(torch.autograd.Function):
         x, y = x.contiguous(), y.contiguous()
         assert x.dtype == torch.float32 and y.dtype == torch.float32 and x.shape == y.shape and x.is_cuda
         n = x.numel()
-        loss = torch.zeros((), dtype=torch.float32, device=x.device)
-        L.check(L.lib().sscg_l1_fwd(_ptr(x), _ptr(y), n, 1.0 / n, _ptr(loss), _stream()), "sscg_l1_fwd")
+        loss = torch.empty((), dtype=torch.float32, device=x.device)
+        L.check(L.lib().sscg_l1_fwd(_ptr(x), _ptr(y), n, 1.0 / n, _ptr(loss), _ptr(_loss_ws(x.device)), _stream()),
+                "sscg_l1_fwd")
         ctx.save_for_backward(x, y)
         return loss
 

@@ -29,6 +29,14 @@ def default_precision() -> str:
     return _DEFAULT_PRECISION
 
 
+def _rank_salt() -> int:
+    """Per-rank term of the dropout seeds: data-parallel ranks seed torch identically (same initial weights), but
+    each must draw its own masks.  0 on rank 0 / single process."""
+    import torch.distributed as dist
+    rank = dist.get_rank() if (dist.is_available() and dist.is_initialized()) else int(os.environ.get("RANK", "0"))
+    return (rank * 0x9E3779B1) & 0x7FFFFFFF
+
+
 class NetRunner:
     def __init__(self, build_specs: Callable[[], List[StageSpec]], residual_plan=None):
         self._build_specs = build_specs
@@ -196,6 +204,7 @@ class _FusedNet(torch.autograd.Function):
         seed = 0
         if dropout_on:
             seed = int(torch.randint(1, 2 ** 31 - 1, (1,)).item())   # CPU generator: follows torch.manual_seed
+            seed = (seed ^ _rank_salt()) or 1                        # ... and differs between data-parallel ranks
         if labels:
             assert x.shape[1] == 1, "label maps are N x 1 x H x W"
             plan.forward(c, labels=x, n_classes=runner.specs[0].Cin, training=dropout_on, drop_seed=seed)

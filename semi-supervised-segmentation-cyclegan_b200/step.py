@@ -180,6 +180,7 @@ class SemiSupCycleGAN:
                 n._runner.defer_unpack = True
         P = GraphPool if graph_safe else DevicePool
         self.pool_recon, self.pool_fake_img, self.pool_fake_gt = P(), P(), P()           # model.py:350-352
+        self._dec_fed = False
         if graph_safe:
             self.pool_dec = torch.zeros(3, 3, dtype=torch.int64, device=device)
             self.pool_dec_host = torch.zeros(3, 3, dtype=torch.int64).pin_memory()
@@ -296,7 +297,13 @@ class SemiSupCycleGAN:
         # ---- discriminator phase (model.py:481-542) ----------------------------------------
         set_grad(frozen_d, True)                                                         # :481
         self.d_grads.zero()                                                              # :482
-        if self.graph_safe:   # decisions were drawn by feed_pool_decisions() before this step
+        if self.graph_safe:
+            # the decisions of this step come from feed_pool_decisions(): GraphedStep / train_step_host call it before
+            # the step; a direct train_step() draws them here (never during capture: a replay reads whatever was fed)
+            if not torch.cuda.is_current_stream_capturing():
+                if not self._dec_fed:
+                    self.feed_pool_decisions()
+                self._dec_fed = False
             recon_img = self.pool_recon.device_apply(recon_img.detach())                 # :490
             fake_img = self.pool_fake_img.device_apply(fake_img.detach())                # :491
             fake_gt = self.pool_fake_gt.device_apply(fake_gt.detach())                   # :493
@@ -341,6 +348,7 @@ class SemiSupCycleGAN:
             d = p.host_decide()
             self.pool_dec_host[i, 0], self.pool_dec_host[i, 1], self.pool_dec_host[i, 2] = d
         self.pool_dec.copy_(self.pool_dec_host, non_blocking=True)
+        self._dec_fed = True
 
     def train_step_host(self, l_img_host, l_gt_host, unl_img_host):
         """End-to-end entry: pinned host buffers in, the 9 scalars out on the host."""
@@ -421,6 +429,7 @@ class GraphedStep:
             g.replay()
             if i < len(self.points):
                 (self.m.g_grads if self.points[i] == "g" else self.m.d_grads).allreduce_mean()
+        self.m._dec_fed = False           # consumed by the replay
         return self.losses
 
     def step_host(self, l_img_host, l_gt_host, unl_img_host):

@@ -75,7 +75,7 @@ def case_conv_fwd(N=2, H=16, W=16, Cin=64, Cout=64, k=3, stride=1, pad=1, reflec
     slab, slab_lo, _ = _wslab(w, False, 0, 0, Co_pad, Kc, k, k, Cout, Cin, split == 3)
     Ho, Wo = G.conv_out(H, k, stride, pad), G.conv_out(W, k, stride, pad)
     y = torch.zeros(N, Ho, Wo, Co_pad, device=DEV, dtype=torch.float32 if out_fp32 else torch.bfloat16)
-    st = torch.zeros(N, Co_pad, 2, device=DEV) if stats else None
+    st = K.stats_buffer(N, Co_pad, DEV) if stats else None      # binned plane-sum accumulators (zeroed)
     bias_pad = None
     if bias:
         bias_pad = torch.zeros(Co_pad, device=DEV)
@@ -89,6 +89,13 @@ def case_conv_fwd(N=2, H=16, W=16, Cin=64, Cout=64, k=3, stride=1, pad=1, reflec
                     act=act, stats=st, split=split, shift_kw=(k if shift else 0), shift_base_mode=2)
     K.run_conv(a)
     torch.cuda.synchronize()
+    if stats:                         # order-independent integer accumulation: a second launch reproduces every bit
+        st1, y1 = st.clone(), y.clone()
+        st.zero_()
+        K.run_conv(a)
+        torch.cuda.synchronize()
+        assert torch.equal(st1, st) and torch.equal(y1, y), "conv_igemm statistics are not reproducible"
+        st = K.stats_decode(st)
     xp = F.pad(x, (pad,) * 4, mode="reflect" if reflect else "constant") if pad else x
     ref = F.conv2d(xp, w, b, stride=stride)
     if act == L.ACT_RELU:
@@ -226,6 +233,12 @@ def case_conv_wgrad(N=2, H=16, W=16, Cin=64, Cout=128, k=3, stride=1, pad=1, ksp
     a = K.wgrad_args(dyb.view(interior=True), None, xb.view(interior=True), None, table, Kc, Co_pad, dw,
                      k * k * Co_pad, ksplit=ksplit)
     K.run_wgrad(a)
+    torch.cuda.synchronize()
+    dw1 = dw.clone()
+    K.run_wgrad(a)                    # accumulates: second launch doubles every element exactly; fixed split order
+    torch.cuda.synchronize()
+    assert torch.equal(dw, 2 * dw1), "conv_wgrad is not reproducible / does not accumulate"
+    dw.copy_(dw1)
     grad = torch.zeros(Cout, Cin, k, k, device=DEV)
     ua = K.wprep_args(grad, False, Cout, Cin, k, k, 0, 0, Co_pad, Kc, None)
     K.run_wgrad_unpack(ua, dw, grad)
@@ -249,6 +262,12 @@ def case_wgrad_window(N=2, H=16, W=16, Cin=3, Cout=64, k=7, pad=3):
     table = G.taps_conv_fwd_window(k, 1, 0)
     a = K.wgrad_args(dyb.view(interior=True), None, xb.window_view(kwpad), None, table, kwpad, Co_pad, dw, k * Co_pad)
     K.run_wgrad(a)
+    torch.cuda.synchronize()
+    dw1 = dw.clone()
+    K.run_wgrad(a)
+    torch.cuda.synchronize()
+    assert torch.equal(dw, 2 * dw1), "conv_wgrad (window) is not reproducible / does not accumulate"
+    dw.copy_(dw1)
     grad = torch.zeros(Cout, Cin, k, k, device=DEV)
     ua = K.wprep_args(grad, False, Cout, Cin, k, k, 1, Cp, Co_pad, kwpad, None)
     K.run_wgrad_unpack(ua, dw, grad)
@@ -301,7 +320,7 @@ def case_apply_fwd(N=2, H=12, W=12, Cc=64, pad=1, reflect=True, act=L.ACT_RELU, 
     _setup()
     raw = _bf(torch.randn(N, Cc, H, W, device=DEV) * 2 + 0.5)
     rawb = raw.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
-    st = torch.stack([raw.sum(dim=(2, 3)), (raw * raw).sum(dim=(2, 3))], dim=-1).contiguous()
+    st = K.stats_encode(torch.stack([raw.sum(dim=(2, 3)), (raw * raw).sum(dim=(2, 3))], dim=-1))
     dst = K.ActBuf(N, H, W, Cc, pad, DEV)
     a = L.ApplyArgs()
     a.raw, a.raw_fp32 = rawb.data_ptr(), 0
@@ -331,7 +350,7 @@ def case_apply_fwd(N=2, H=12, W=12, Cc=64, pad=1, reflect=True, act=L.ACT_RELU, 
     return _result(got, ref, 2e-2)
 
 
-def case_apply_bwd(N=2, H=12, W=12, Cc=64, pad=1, act=L.ACT_RELU, skip=True, fused=False, dz_bf16=False):
+def case_apply_bwd(N=2, H=12, W=12, Cc=64, pad=1, act=L.ACT_RELU, skip=True, dz_bf16=False, stream_mode=2):
     """Backward of pad(act(IN(raw))) (+ skip gradient): dRaw vs autograd."""
     _setup()
     raw = _bf(torch.randn(N, Cc, H, W, device=DEV) * 2 + 0.5)
@@ -346,7 +365,7 @@ def case_apply_bwd(N=2, H=12, W=12, Cc=64, pad=1, act=L.ACT_RELU, skip=True, fus
         loss = loss + (y * sk).sum()
     loss.backward()
     rawb = raw.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
-    st = torch.stack([raw.sum(dim=(2, 3)), (raw * raw).sum(dim=(2, 3))], dim=-1).contiguous()
+    st = K.stats_encode(torch.stack([raw.sum(dim=(2, 3)), (raw * raw).sum(dim=(2, 3))], dim=-1))
     dypb = K.ActBuf(N, H, W, Cc, pad, DEV)
     t = dyp.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
     dypb.hi[: t.numel()].copy_(t.reshape(-1))
@@ -362,18 +381,21 @@ def case_apply_bwd(N=2, H=12, W=12, Cc=64, pad=1, act=L.ACT_RELU, skip=True, fus
         a.skip = L.make_view(skb.data_ptr(), N, H, W, Cc, H * W * Cc, W * Cc, Cc)
         a.skip_fp32 = 0
     dz = torch.zeros(N, H, W, Cc, device=DEV, dtype=torch.bfloat16 if dz_bf16 else torch.float32)
-    bst = torch.zeros(N, Cc, 2, device=DEV)
+    bst = K.stats_buffer(N, Cc, DEV)
     a.dz, a.dz_fp32, a.dz_lo = dz.data_ptr(), 0 if dz_bf16 else 1, None
     a.bstats = bst.data_ptr()
     draw = torch.zeros(N, H, W, Cc, device=DEV, dtype=torch.bfloat16)
-    L.lib().sscg_set_stream_norm(2)
-    if fused:
-        sync = torch.zeros(N, dtype=torch.int32, device=DEV)
-        assert K.run_bwd_fused(a, draw, None, sync)
-    else:
-        K.run_bwd_prep(a)
-        K.run_bwd_apply(a, draw)
+    L.lib().sscg_set_stream_norm(stream_mode)
+    K.run_bwd_prep(a)
+    K.run_bwd_apply(a, draw)
     torch.cuda.synchronize()
+    first = (bst.clone(), draw.clone())
+    bst.zero_()
+    K.run_bwd_prep(a)                # order-independent integer accumulation: a second run reproduces every bit
+    K.run_bwd_apply(a, draw)
+    torch.cuda.synchronize()
+    L.lib().sscg_set_stream_norm(2)
+    assert torch.equal(first[0], bst) and torch.equal(first[1], draw), "in_bwd_prep / apply are not reproducible"
     # bf16 dZ (the fast-mode layout, served by the bulk-pipelined kernels) adds one bf16 rounding of values up to ~10
     return _result(draw.float().permute(0, 3, 1, 2), rr.grad, 5e-2 if dz_bf16 else 2e-2)
 
@@ -385,7 +407,7 @@ def case_stream_ab(N=3, H=16, W=64, Cc=256, pad=1, act=L.ACT_RELU, skip=True, re
     _setup()
     lib = L.lib()
     raw = (torch.randn(N, H, W, Cc, device=DEV) * 2 + 0.5).to(torch.bfloat16)
-    st = torch.stack([raw.float().sum(dim=(1, 2)), (raw.float() ** 2).sum(dim=(1, 2))], dim=-1).contiguous()
+    st = K.stats_encode(torch.stack([raw.float().sum(dim=(1, 2)), (raw.float() ** 2).sum(dim=(1, 2))], dim=-1))
     seed = 0x1234567 if drop else 0
     worst = 0.0
     # ---- forward ------------------------------------------------------------------------------
@@ -430,7 +452,7 @@ def case_stream_ab(N=3, H=16, W=64, Cc=256, pad=1, act=L.ACT_RELU, skip=True, re
         gout = torch.zeros(N, H, W, Cc, device=DEV, dtype=torch.bfloat16)
         a.g_out, a.g_fp32 = gout.data_ptr(), 0
         dz = torch.zeros(N, H, W, Cc, device=DEV, dtype=torch.bfloat16)
-        bst = torch.zeros(N, Cc, 2, device=DEV)
+        bst = K.stats_buffer(N, Cc, DEV)
         a.dz, a.dz_fp32, a.dz_lo = dz.data_ptr(), 0, None
         a.bstats = bst.data_ptr()
         K.run_bwd_prep(a)
@@ -447,7 +469,8 @@ def case_stream_ab(N=3, H=16, W=64, Cc=256, pad=1, act=L.ACT_RELU, skip=True, re
         worst = max(worst, float((res[0][i].float() - res[1][i].float()).abs().max()))
     assert float(res[1][3].float().abs().max()) > 0
     # plane sums: same terms, different summation order
-    rel = float((res[1][2] - res[0][2]).abs().max() / res[0][2].abs().max().clamp_min(1e-6))
+    b0, b1 = K.stats_decode(res[0][2]), K.stats_decode(res[1][2])
+    rel = float((b1 - b0).abs().max() / b0.abs().max().clamp_min(1e-6))
     assert rel < 1e-4, rel
     return worst, 1.0, 0.0
 
@@ -500,6 +523,29 @@ def case_seg_head(N=2, Cc=21, H=24, W=40):
     r2 = logits.detach().clone().requires_grad_(True)
     (F.softmax(r2, dim=1) * wprobe).sum().backward()
     e = max(e, (l2.grad - r2.grad).abs().max().item())
+    # nn.CrossEntropyLoss label semantics: ignore_index pixels (-100 by default; 255 = VOC void) are left out of the mean
+    # and of the gradient; int32 label maps are accepted; the loss itself is reproducible bit for bit
+    for ign, dt in ((-100, torch.int64), (255, torch.int32)):
+        lab_i = labels.clone()
+        lab_i[torch.rand(lab_i.shape, device=DEV) < 0.3] = ign
+        l3 = logits.detach().clone().requires_grad_(True)
+        loss3, _, _ = seg_head(l3, lab_i.to(dt), ignore_index=ign)
+        loss3b, _, _ = seg_head(l3.detach(), lab_i.to(dt), ignore_index=ign)
+        assert torch.equal(loss3.detach(), loss3b), "seg_head loss is not reproducible"
+        loss3.backward()
+        r3 = logits.detach().clone().requires_grad_(True)
+        rl3 = F.cross_entropy(r3, lab_i.squeeze(1), ignore_index=ign)
+        rl3.backward()
+        e = max(e, abs(float(loss3) - float(rl3)),
+                (l3.grad - r3.grad).abs().max().item() / max(1e-9, r3.grad.abs().max().item()) * 1e-1)
+    assert K.device_error() == 0
+    # a label outside [0, C) that is not ignore_index raises the device error flag (torch device-asserts)
+    bad = labels.clone()
+    bad[0, 0, 0, 0] = Cc + 3
+    seg_head(logits.detach(), bad)
+    torch.cuda.synchronize()
+    code = K.device_error()
+    assert (code >> 16) & 0x7fff == 31, code
     return (e if exact else 1.0), 1.0, 2e-5
 
 
@@ -700,10 +746,10 @@ CASES = {
     "apply_bwd_relu": lambda: case_apply_bwd(),
     "apply_bwd_nopad": lambda: case_apply_bwd(pad=0, act=L.ACT_LRELU, skip=False),
     "apply_bwd_pad3": lambda: case_apply_bwd(pad=3, act=L.ACT_RELU, skip=False),
-    "apply_bwd_fused_relu": lambda: case_apply_bwd(fused=True),
-    "apply_bwd_fused_big": lambda: case_apply_bwd(N=16, H=64, W=64, Cc=256, pad=1, fused=True),
-    "apply_bwd_fused_lrelu_nopad": lambda: case_apply_bwd(N=3, H=31, W=31, Cc=512, pad=0, act=L.ACT_LRELU, skip=False,
-                                                          fused=True),
+    "apply_bwd_generic_big": lambda: case_apply_bwd(N=16, H=64, W=64, Cc=256, pad=1, stream_mode=0),
+    "apply_bwd_generic_lrelu_nopad": lambda: case_apply_bwd(N=3, H=31, W=31, Cc=512, pad=0, act=L.ACT_LRELU, skip=False,
+                                                            stream_mode=0),
+    "apply_bwd_stream_res_shape": lambda: case_apply_bwd(N=16, H=64, W=64, Cc=256, pad=1, dz_bf16=True),
     # bulk-pipelined (cp.async.bulk ring) variants: eligible all-bf16 shapes
     "apply_fwd_stream_res": lambda: case_apply_fwd(N=3, H=16, W=64, Cc=256, pad=1, act=L.ACT_NONE, residual=True),
     "apply_fwd_stream_pad3": lambda: case_apply_fwd(N=2, H=20, W=128, Cc=64, pad=3),

@@ -19,7 +19,7 @@ def timeit(fn, reps=30):
 def run(N, H, W, C, pad, residual, skip, drop=12345, act=None, norm=True):
     dev = "cuda"
     raw = torch.randn(N, H, W, C, device=dev).to(torch.bfloat16)
-    st = torch.stack([raw.float().sum(dim=(1, 2)), (raw.float() ** 2).sum(dim=(1, 2))], dim=-1).contiguous()
+    st = K.stats_encode(torch.stack([raw.float().sum(dim=(1, 2)), (raw.float() ** 2).sum(dim=(1, 2))], dim=-1))
     dst = K.ActBuf(N, H, W, C, pad, dev)
     a = L.ApplyArgs()
     a.raw, a.raw_fp32, a.stats, a.eps = raw.data_ptr(), 0, st.data_ptr(), 1e-5
@@ -43,20 +43,17 @@ def run(N, H, W, C, pad, residual, skip, drop=12345, act=None, norm=True):
         ba.skip = L.make_view(sk.data_ptr(), N, H, W, C, H * W * C, W * C, C)
         ba.g_out, ba.g_fp32 = gout.data_ptr(), 0
     dz = torch.zeros(N, H, W, C, device=dev, dtype=torch.bfloat16)
-    bst = torch.zeros(N, C, 2, device=dev)
+    bst = K.stats_buffer(N, C, dev)
     ba.dz, ba.dz_fp32, ba.dz_lo, ba.bstats = dz.data_ptr(), 0, None, bst.data_ptr()
     t_prep = timeit(lambda: K.run_bwd_prep(ba))
     b_prep = N * H * W * C * 2 * (3 + (2 if skip else 0))
     draw = torch.zeros(N, H, W, C, device=dev, dtype=torch.bfloat16)
     t_bapply = timeit(lambda: K.run_bwd_apply(ba, draw))
     b_bapply = N * H * W * C * 2 * 3
-    sync = torch.zeros(N, dtype=torch.int32, device=dev)
-    t_fused = timeit(lambda: (bst.zero_(), K.run_bwd_fused(ba, draw, None, sync)))
     return {"shape": [N, H, W, C, pad, residual, skip, drop, act, norm],
             "apply_us": round(t_apply, 1), "apply_GBs": round(b_apply / t_apply / 1e3),
             "prep_us": round(t_prep, 1), "prep_GBs": round(b_prep / t_prep / 1e3),
-            "bapply_us": round(t_bapply, 1), "bapply_GBs": round(b_bapply / t_bapply / 1e3),
-            "fused_us(+zero)": round(t_fused, 1)}
+            "bapply_us": round(t_bapply, 1), "bapply_GBs": round(b_bapply / t_bapply / 1e3)}
 
 if __name__ == "__main__":
     print(os.environ.get("SSCG_LIB", "default"))
