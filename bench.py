@@ -32,6 +32,26 @@ UNIT = "img/s"
 H = W = 256
 NCLS = 21
 BATCH = 16
+CIMG = 3
+# BASELINE.json configs (index = position in `configs`, 1-based as SURVEY.md §8d numbers them): per-GPU shapes
+CONFIGS = {
+    2: dict(name="configs[1]: full semisupervised_cycleGAN step, synthetic VOC 3x256x256 / 21-class, bs=16 per GPU",
+            cimg=3, ncls=21, h=256, w=256, batch=16, gpus=1),
+    3: dict(name="configs[2]: Cityscapes 3x256x512 / 19-class, bs=8 per GPU (8 GPUs in BASELINE.json)",
+            cimg=3, ncls=19, h=256, w=512, batch=8, gpus=8),
+    4: dict(name="configs[3]: ACDC 1x256x256 / 4-class, bs=32, 1 GPU", cimg=1, ncls=4, h=256, w=256, batch=32, gpus=1),
+    5: dict(name="configs[4]: VOC 3x512x512 / 21-class, bs=4 per GPU (4 GPUs in BASELINE.json)",
+            cimg=3, ncls=21, h=512, w=512, batch=4, gpus=4),
+}
+
+
+def apply_config(idx, batch=None):
+    """Select the workload (module-level shape constants used by the data / FLOP helpers)."""
+    global H, W, NCLS, BATCH, CIMG
+    c = CONFIGS[idx]
+    H, W, NCLS, CIMG = c["h"], c["w"], c["ncls"], c["cimg"]
+    BATCH = batch or c["batch"]
+    return c
 
 
 # ------------------------------------------------------------------------------------------------
@@ -50,9 +70,10 @@ def f_dis(h, w, ci, ndf=64):
                 + (h // 8 - 1) * (w // 8 - 1) * 16 * 4 * ndf * 8 * ndf + (h // 8 - 2) * (w // 8 - 2) * 16 * 8 * ndf)
 
 
-def step_flops_per_sample(variant, h=H, w=W, c=NCLS, cimg=3):
+def step_flops_per_sample(variant, h=None, w=None, c=None, cimg=None):
     """Per labeled sample per step.  Routes follow SURVEY.md §3.2: Gsi 3 fwd + 3 bwd, Gis 3 fwd + 2 bwd
     (first-layer dgrad skipped where the input needs no gradient is ignored here: < 1 %)."""
+    h, w, c, cimg = h or H, w or W, c or NCLS, cimg or CIMG
     gis, gsi = f_gen(h, w, c, cimg), f_gen(h, w, cimg, c)
     di, ds = f_dis(h, w, cimg), f_dis(h, w, c)
     fwd = 3 * gis + 3 * gsi
@@ -72,8 +93,8 @@ def step_flops_per_sample(variant, h=H, w=W, c=NCLS, cimg=3):
     return fwd, bwd
 
 
-def res_conv_flops(n, h=H, w=W, ngf=64):
-    return 2 * n * (h // 4) * (w // 4) * 9 * (4 * ngf) * (4 * ngf)
+def res_conv_flops(n, h=None, w=None, ngf=64):
+    return 2 * n * ((h or H) // 4) * ((w or W) // 4) * 9 * (4 * ngf) * (4 * ngf)
 
 
 def load_peaks():
@@ -138,8 +159,8 @@ def make_batches(n_batches, batch, device, seed, pin=False):
     g = torch.Generator().manual_seed(seed)
     out = []
     for _ in range(n_batches):
-        l_img = torch.rand(batch, 3, H, W, generator=g) * 2 - 1
-        unl_img = torch.rand(batch, 3, H, W, generator=g) * 2 - 1
+        l_img = torch.rand(batch, CIMG, H, W, generator=g) * 2 - 1
+        unl_img = torch.rand(batch, CIMG, H, W, generator=g) * 2 - 1
         coarse = torch.randint(0, NCLS, (batch, 1, H // 16, W // 16), generator=g)      # blocky masks
         l_gt = coarse.repeat_interleave(16, 2).repeat_interleave(16, 3).contiguous()
         if pin:
@@ -162,14 +183,14 @@ def cpu_reference_step_factory(n, variant, threads=None):
     import contextlib
     import io
     with contextlib.redirect_stdout(io.StringIO()):
-        nets = {"Gis": define_Gen(NCLS, 3, 64, "resnet_9blocks", "instance", False, []).state_dict(),
-                "Gsi": define_Gen(3, NCLS, 64, "resnet_9blocks_softmax", "instance", False, []).state_dict(),
-                "Di": define_Dis(3, 64, "n_layers", 3, "instance", []).state_dict(),
+        nets = {"Gis": define_Gen(NCLS, CIMG, 64, "resnet_9blocks", "instance", False, []).state_dict(),
+                "Gsi": define_Gen(CIMG, NCLS, 64, "resnet_9blocks_softmax", "instance", False, []).state_dict(),
+                "Di": define_Dis(CIMG, 64, "n_layers", 3, "instance", []).state_dict(),
                 "Ds": define_Dis(NCLS, 64, "n_layers", 3, "instance", []).state_dict()}
         if variant == "head":
-            nets["old_Gis"] = define_Gen(NCLS, 3, 64, "resnet_9blocks", "instance", False, []).state_dict()
-            nets["old_Gsi"] = define_Gen(3, NCLS, 64, "resnet_9blocks_softmax", "instance", False, []).state_dict()
-            nets["old_Di"] = define_Dis(3, 64, "n_layers", 3, "instance", []).state_dict()
+            nets["old_Gis"] = define_Gen(NCLS, CIMG, 64, "resnet_9blocks", "instance", False, []).state_dict()
+            nets["old_Gsi"] = define_Gen(CIMG, NCLS, 64, "resnet_9blocks_softmax", "instance", False, []).state_dict()
+            nets["old_Di"] = define_Dis(CIMG, 64, "n_layers", 3, "instance", []).state_dict()
     nets = {k: {kk: vv.detach().clone() for kk, vv in sd.items()} for k, sd in nets.items()}
     g_params = [p.requires_grad_(True) for k in ("Gis", "Gsi") for p in nets[k].values()]
     d_params = [p.requires_grad_(True) for k in ("Di", "Ds") for p in nets[k].values()]
@@ -213,16 +234,77 @@ def run_reference(args):
         step()
     dt = time.perf_counter() - t0
     value = n * args.steps / dt
-    sample = "%d-image (of %d) 256x256 batch per step, %s variant, fp32, oracle port + torch Adam" % (n, BATCH, args.variant)
+    sample = "%d-image (of %d) %dx%d batch per step, %s variant, fp32, oracle port + torch Adam" % (n, BATCH, H, W, args.variant)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "configs[1]: full semisupervised_cycleGAN step, synthetic VOC 3x256x256 / 21-class",
-                       "variant": args.variant, "per_step_sample": sample},
+            "config": {"workload": args.cfg["name"], "variant": args.variant, "per_step_sample": sample},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def gpu_baseline(args, dev, batches, steps=4, warmup=2):
+    """The on-box GPU baseline SURVEY.md §8d asks for: the SAME step (step.SemiSupCycleGAN, model.py:379-542) on the
+    stock torch.nn module trees — the reference's own modules (arch/ops.py:40-74) executed by cuDNN / ATen with
+    torch.optim.Adam(fused) and a device-resident history pool — at the same batch and shapes, in three precisions:
+    fp32 (TF32 off), TF32 (PyTorch's default for cuDNN convolutions) and bf16 autocast + channels_last.  Eager
+    launches (the reference's step cannot be graph-captured: its pool round-trips through numpy); the bf16 arm is also
+    timed as CUDA-graph replays of the same stock step, the most generous form of the baseline.  Returns img/s per arm."""
+    import contextlib
+    import gc
+    import io
+    from sscg_b200.step import GraphedStep, SemiSupCycleGAN
+    out = {"what": "same training step on stock torch.nn modules (cuDNN convolutions, ATen InstanceNorm / losses, "
+                   "torch.optim.Adam(fused=True), device pool), batch %d, %dx%d, eager launches" % (args.batch, H, W),
+           "steps_timed": steps}
+    saved = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark)
+    torch.backends.cudnn.benchmark = True
+    arms = [("fp32", "fp32", False, False), ("tf32", "tf32", True, False), ("bf16_autocast", "bf16_autocast", True, False),
+            ("bf16_autocast_cudagraph", "bf16_autocast", True, True)]
+    for name, stock, tf32, graph in arms:
+        torch.backends.cudnn.allow_tf32 = tf32
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        try:
+            torch.manual_seed(0)
+            with contextlib.redirect_stdout(io.StringIO()):
+                m = SemiSupCycleGAN(n_classes=NCLS, img_channels=CIMG, variant=args.variant,
+                                    use_dropout=not args.no_dropout, device=dev, stock=stock, graph_safe=graph)
+            if graph:
+                gs = GraphedStep(m, *batches[0], warmup=warmup + 1)
+                step = lambda b: gs(*b)                              # noqa: E731
+            else:
+                step = lambda b: m.train_step(*b)                    # noqa: E731
+            for i in range(warmup):
+                step(batches[i % len(batches)])
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(steps):
+                last = step(batches[i % len(batches)])
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            out[name] = {"value": args.batch / (ms / 1e3), "unit": UNIT, "ms_per_step": ms,
+                         "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 2 ** 30}
+            if not graph:
+                out[name]["lab_loss_CE"] = float(last["lab_loss_CE"])
+            del m, step, last
+            if graph:
+                del gs
+        except Exception as e:                                       # noqa: BLE001 — report, keep the other arms
+            out[name] = {"error": "%s: %s" % (type(e).__name__, str(e)[:200])}
+        gc.collect()
+        torch.cuda.empty_cache()
+        torch.cuda.reset_peak_memory_stats(dev)
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark = saved
+    vals = {k: v["value"] for k, v in out.items() if isinstance(v, dict) and "value" in v}
+    if vals:
+        best = max(vals, key=vals.get)
+        out["best"] = {"arm": best, "value": vals[best], "unit": UNIT}
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -261,8 +343,8 @@ def run_ours(args):
     use_graph = not args.no_graph
     torch.manual_seed(0)          # identical initial weights on every rank
     with contextlib.redirect_stdout(io.StringIO()):
-        model = SemiSupCycleGAN(n_classes=NCLS, variant=args.variant, use_dropout=not args.no_dropout, device=dev,
-                                precision=args.precision, graph_safe=use_graph)
+        model = SemiSupCycleGAN(n_classes=NCLS, img_channels=CIMG, variant=args.variant, use_dropout=not args.no_dropout,
+                                device=dev, precision=args.precision, graph_safe=use_graph)
     if world > 1:
         for p in list(model.g_grads.params) + list(model.d_grads.params):
             dist.broadcast(p.data, 0)
@@ -325,8 +407,9 @@ def run_ours(args):
             model.feed_pool_decisions()
         model.train_step(*dev_batches[i % 3])
     prof, prof_complete = K.prof_end()
-    # ---- north-star sub-metric: one fused generator forward (Gsi, bs 16, 256x256, train mode) ----
-    gen_ms = None
+    # ---- north-star sub-metric: one fused generator forward (Gsi, train mode) -------------------------
+    # eager launches and, so that ~50 ctypes launches cannot be host-bound, replays of a CUDA graph of the same pass
+    gen_ms = gen_graph_ms = None
     with torch.no_grad():
         x_img = dev_batches[0][0]
         for _ in range(3):
@@ -339,7 +422,37 @@ def run_ours(args):
         g1.record()
         torch.cuda.synchronize()
         gen_ms = g0.elapsed_time(g1) / 10
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                model.Gsi(x_img)
+            torch.cuda.current_stream().wait_stream(side)
+            gg = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gg):
+                model.Gsi(x_img)
+            for _ in range(3):
+                gg.replay()
+            torch.cuda.synchronize()
+            g0.record()
+            for _ in range(20):
+                gg.replay()
+            g1.record()
+            torch.cuda.synchronize()
+            gen_graph_ms = g0.elapsed_time(g1) / 20
+            del gg
+        except Exception:                                            # noqa: BLE001
+            gen_graph_ms = None
     dev_err = K.device_error()
+    gpu_base = None
+    if world == 1 and not args.no_gpu_baseline:
+        del model
+        if use_graph:
+            del gs, step_dev, step_host
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
+        gpu_base = gpu_baseline(args, dev, dev_batches)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -354,15 +467,15 @@ def run_ours(args):
     roof = None
     traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")     # dram bytes of the same kernel from `ncu --set full`
-    if os.path.exists(tpath) and args.batch == BATCH:
+    if os.path.exists(tpath) and args.batch == 16 and args.config == 2:
         with open(tpath) as f:
             tj = json.load(f)
         traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source")
     if res_n:
         achieved = res_conv_flops(args.batch) / 1e12 / (res_ms / res_n / 1e3)
         peak = peaks["bf16_tflops_sustained"]
-        roof = {"bound": "tensor", "kernel": "conv_igemm_kernel<256,1>: 3x3 256->256 @64x64 residual-block conv, forward "
-                                             "(108 launches per step)",
+        roof = {"bound": "tensor", "kernel": "conv_igemm_kernel<256,1>: 3x3 256->256 @%dx%d residual-block conv, forward "
+                                             "(108 launches per step)" % (H // 4, W // 4),
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
                 "traffic_source": traffic_src,
                 "peak_source": peak_src + " (sustained cuBLAS bf16: kernel timed inside a long step)",
@@ -374,9 +487,11 @@ def run_ours(args):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if args.precision == "bf16" else "bf16x3", "data": "synthetic",
-            "config": {"workload": "configs[1]: full semisupervised_cycleGAN step, synthetic VOC 3x256x256 / 21-class, "
-                                   "bs=16 labeled + 16 unlabeled per GPU, Gis/Gsi = resnet_9blocks[_softmax], "
-                                   "Di/Ds = n_layers(3), dropout %s" % ("off" if args.no_dropout else "on"),
+            "config": {"workload": "%s; %d labeled + %d unlabeled %dx%dx%d images per GPU and step, %d classes, "
+                                   "Gis/Gsi = resnet_9blocks[_softmax], Di/Ds = n_layers(3), dropout %s"
+                                   % (args.cfg["name"], args.batch, args.batch, CIMG, H, W, NCLS,
+                                      "off" if args.no_dropout else "on"),
+                       "baseline_config_index": args.config,
                        "variant": args.variant, "batch_per_gpu": args.batch, "global_batch": world * args.batch,
                        "parallelism": "dp%d" % world, "precision": args.precision,
                        "cuda_graph": use_graph,
@@ -385,11 +500,15 @@ def run_ours(args):
                        "step_tflops_achieved": tf_step / (ms_step / 1e3),
                        "step_frac_of_sustained_peak": tf_step / (ms_step / 1e3) / peaks["bf16_tflops_sustained"]},
             "roofline": roof,
-            "generator_forward": {"what": "Gsi = resnet_9blocks_softmax forward incl. NCHW<->NHWC boundary, bs %d, 256x256, "
-                                          "eager launches" % args.batch,
-                                  "ms": gen_ms, "tflops": f_gen(H, W, 3, NCLS) * args.batch / 1e12 / (gen_ms / 1e3),
-                                  "frac_of_sustained_peak": f_gen(H, W, 3, NCLS) * args.batch / 1e12 / (gen_ms / 1e3)
-                                  / peaks["bf16_tflops_sustained"]},
+            "generator_forward": {"what": "Gsi = resnet_9blocks_softmax forward incl. NCHW<->NHWC boundary, bs %d, %dx%d"
+                                          % (args.batch, H, W),
+                                  "ms": gen_ms, "ms_cuda_graph": gen_graph_ms,
+                                  "tflops": f_gen(H, W, CIMG, NCLS) * args.batch / 1e12 / (gen_ms / 1e3),
+                                  "frac_of_sustained_peak": f_gen(H, W, CIMG, NCLS) * args.batch / 1e12 / (gen_ms / 1e3)
+                                  / peaks["bf16_tflops_sustained"],
+                                  "frac_of_sustained_peak_cuda_graph":
+                                      (f_gen(H, W, CIMG, NCLS) * args.batch / 1e12 / (gen_graph_ms / 1e3)
+                                       / peaks["bf16_tflops_sustained"]) if gen_graph_ms else None},
             "kernel_time_ms_per_step": {k: v[0] / prof_steps for k, v in prof.items()},
             "kernel_launches_per_step": {k: v[1] / prof_steps for k, v in prof.items()},
             "kernel_profile_complete": prof_complete,
@@ -397,14 +516,19 @@ def run_ours(args):
                     "d2h_bytes_per_step": 9 * 4, "ms_per_step": t_e2e / args.steps * 1e3},
             "gpu_launches": int(launches), "clocks": clocks, "device_error": dev_err,
             "losses_last_step": last}
+    if gpu_base is not None:
+        line["gpu_baseline"] = gpu_base
+        if "best" in gpu_base:
+            line["gpu_baseline"]["ratio_vs_best"] = value / gpu_base["best"]["value"]
+            line["gpu_baseline"]["e2e_ratio_vs_best"] = line["e2e"]["value"] / gpu_base["best"]["value"]
     if world == 1 and not args.no_cpu_baseline:
         step, threads = cpu_reference_step_factory(args.ref_batch, args.variant)
         t0 = time.perf_counter()
         step()
         dt = time.perf_counter() - t0
         line["cpu_baseline"] = {"value": args.ref_batch / dt, "unit": UNIT, "cores": threads, "kind": "port",
-                                "sample": "1 step on a %d-image (of %d) 256x256 batch, %s variant, fp32, oracle port + "
-                                          "torch Adam, %.1f s" % (args.ref_batch, BATCH, args.variant, dt)}
+                                "sample": "1 step on a %d-image (of %d) %dx%d batch, %s variant, fp32, oracle port + "
+                                          "torch Adam, %.1f s" % (args.ref_batch, BATCH, H, W, args.variant, dt)}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -418,12 +542,18 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--variant", default="classic", choices=["classic", "head"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16x3"])
-    ap.add_argument("--batch", type=int, default=BATCH)
-    ap.add_argument("--ref-batch", type=int, default=1, help="images per CPU-reference step (bounded sample)")
+    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS),
+                    help="BASELINE.json config (1-based index as in SURVEY.md 8d): 2 = the headline workload")
+    ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (default: the config's)")
+    ap.add_argument("--ref-batch", type=int, default=2,
+                    help="images per CPU-reference step (bounded sample; 2 is the reference's minimum, model.py:435)")
+    ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the stock-torch/cuDNN arm on the same GPU")
     ap.add_argument("--no-dropout", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of one CUDA graph per step")
     args = ap.parse_args()
+    args.cfg = apply_config(args.config, args.batch)
+    args.batch = BATCH
     if args.impl == "reference":
         run_reference(args)
     else:

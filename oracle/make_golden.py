@@ -182,9 +182,31 @@ def golden_step():
     return first
 
 
+def golden_pool(steps=140, seed=7):
+    """Decision sequence of the reference's history pool (utils.py:278-299 Sample_from_Pool) under a fixed numpy
+    seed, in the call order of the training loop (model.py:490-493: recon_img, fake_img, fake_gt once per step, one
+    whole batch per call).  Item k of pool p is identified by the integer 1000 * p + k; the fixture records which
+    item every call returned."""
+    _import_reference()
+    import utils as ref_utils
+    np.random.seed(seed)
+    pools = [ref_utils.Sample_from_Pool() for _ in range(3)]
+    ret = np.zeros((steps, 3), dtype=np.int64)
+    for k in range(steps):
+        for p in range(3):
+            ret[k, p] = int(pools[p]([np.array([1000 * p + k])])[0][0])
+    np.savez_compressed(os.path.join(OUT, "pool_decisions.npz"), returned=ret, seed=np.int64(seed))
+    return ret
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "pool":        # add the pool fixture without touching the others
+        r = golden_pool()
+        print("pool_decisions:", r.shape, "stored batches returned:", int((r != np.arange(len(r))[:, None] + 1000 * np.arange(3)).sum()))
+        sys.exit(0)
     golden_modules()
+    golden_pool()
     print(golden_step())
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -31,11 +31,13 @@ class StepWeights:
 
 
 def _gen(sd, x, tanh, e):
-    return RA.resnet_generator(sd, x, 9, tanh=tanh, use_dropout=False, emulate_bf16=e)
+    # bf16 emulation drops the conv biases that InstanceNorm cancels, like the kernels (they would shift the bf16
+    # rounding of the raw conv outputs)
+    return RA.resnet_generator(sd, x, 9, tanh=tanh, use_dropout=False, emulate_bf16=e, live_norm_bias=not e)
 
 
 def _dis(sd, x, e):
-    return RA.nlayer_discriminator(sd, x, 3, emulate_bf16=e)
+    return RA.nlayer_discriminator(sd, x, 3, emulate_bf16=e, live_norm_bias=not e)
 
 
 def _mse_to(x, target):

@@ -124,11 +124,35 @@ class FlatGrads:
             self.flat.div_(dist.get_world_size(group))
 
 
+class _StockGrads:
+    """Gradient bookkeeping of the stock-torch arm: plain .grad tensors owned by autograd."""
+
+    def __init__(self, params):
+        self.params = list(params)
+
+    def zero(self):
+        for p in self.params:
+            p.grad = None
+
+    def allreduce_mean(self, group=None):
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            for p in self.params:
+                if p.grad is not None:
+                    dist.all_reduce(p.grad, op=dist.ReduceOp.SUM, group=group)
+                    p.grad.div_(dist.get_world_size(group))
+
+
 class SemiSupCycleGAN:
     def __init__(self, n_classes=21, img_channels=3, ngf=64, ndf=64, variant="classic", use_dropout=True, lr=2e-4,
                  device="cuda", precision=None, weights=None, keep_dead_forward=True, fused_adam=True,
-                 graph_safe=False):
+                 graph_safe=False, stock=None):
+        """stock: None = this repo's fused path on CUDA.  "fp32" | "tf32" | "bf16_autocast" = the SAME step on the
+        stock torch.nn module trees (cuDNN convolutions, ATen InstanceNorm / losses, torch.optim.Adam): the on-box GPU
+        baseline of bench.py (the reference's own modules executed by stock PyTorch, arch/ops.py:40-74)."""
         assert variant in ("classic", "head")
+        assert stock in (None, "fp32", "tf32", "bf16_autocast")
+        self.stock = stock
         self.C, self.variant = n_classes, variant
         self.w = weights or StepWeights()
         self.keep_dead_forward = keep_dead_forward
@@ -150,6 +174,10 @@ class SemiSupCycleGAN:
             self.nets.update({"old_Gis": self.old_Gis, "old_Gsi": self.old_Gsi, "old_Di": self.old_Di})
         for n in self.nets.values():
             n.precision = precision
+            if stock is not None:
+                n.fusable = False                      # forward() takes the stock nn.Sequential path
+                if stock == "bf16_autocast":
+                    n.to(memory_format=torch.channels_last)
         self.MSE, self.L1, self.CE = nn.MSELoss(), nn.L1Loss(), nn.CrossEntropyLoss()     # model.py:270-272
         self.softmax = nn.Softmax2d()                                                     # model.py:273
         g_params = list(itertools.chain(self.Gis.parameters(), self.Gsi.parameters()))
@@ -162,8 +190,15 @@ class SemiSupCycleGAN:
             for n in self.nets.values():
                 if getattr(n, "_runner", None) is not None:
                     n._runner.drop_ctr = self.step_counter
-        self.g_grads, self.d_grads = FlatGrads(g_params), FlatGrads(d_params)
-        if fused_adam and cuda:
+        if stock is not None:
+            self.g_grads, self.d_grads = _StockGrads(g_params), _StockGrads(d_params)
+        else:
+            self.g_grads, self.d_grads = FlatGrads(g_params), FlatGrads(d_params)
+        if stock is not None:
+            kw = {"capturable": True} if graph_safe else {}
+            self.g_optimizer = torch.optim.Adam(g_params, lr=lr, betas=(0.5, 0.999), fused=cuda or None, **kw)
+            self.d_optimizer = torch.optim.Adam(d_params, lr=lr, betas=(0.5, 0.999), fused=cuda or None, **kw)
+        elif fused_adam and cuda:
             # one flat-bucket Adam launch per optimizer (optim.FlatAdam, sscg_adam_flat); graph capturable
             from .optim import FlatAdam
             self.g_optimizer = FlatAdam(g_params, self.g_grads, lr=lr, betas=(0.5, 0.999),
@@ -215,8 +250,15 @@ class SemiSupCycleGAN:
     def train_step(self, l_img, l_gt, unl_img):
         """One optimisation step on device tensors: l_img, unl_img N x Cimg x H x W fp32 in [-1, 1],
         l_gt N x 1 x H x W int64.  Returns the 9 logged scalars (model.py:548-550) as 0-d device tensors."""
-        for point in self.step_segments(l_img, l_gt, unl_img):
-            (self.g_grads if point == "g" else self.d_grads).allreduce_mean()
+        import contextlib
+        ctx = contextlib.nullcontext()
+        if self.stock == "bf16_autocast":
+            ctx = torch.autocast("cuda", dtype=torch.bfloat16)
+            l_img = l_img.contiguous(memory_format=torch.channels_last)
+            unl_img = unl_img.contiguous(memory_format=torch.channels_last)
+        with ctx:
+            for point in self.step_segments(l_img, l_gt, unl_img):
+                (self.g_grads if point == "g" else self.d_grads).allreduce_mean()
         return self.last_losses
 
     def step_segments(self, l_img, l_gt, unl_img):
@@ -232,13 +274,13 @@ class SemiSupCycleGAN:
         if head:
             set_grad([self.old_Gsi, self.old_Gis], False)                                # :380
         self.g_grads.zero()                                                              # :381
-        onehot_in = l_img.is_cuda     # label glue: one-hot inputs go in as label maps (arch.*.forward_onehot)
+        onehot_in = l_img.is_cuda and self.stock is None     # label glue: one-hot inputs go in as label maps (arch.*.forward_onehot)
         fake_img = (self.Gis.forward_onehot(l_gt) if onehot_in
                     else self.Gis(make_one_hot(l_gt, C).float()))                        # :385
         fake_gt = self.Gsi(unl_img.float())                                              # :386
         lab_gt = self.Gsi(l_img)                                                         # :387
         assert fake_img.shape[2:] == l_img.shape[2:] and fake_gt.shape[2:] == l_img.shape[2:]   # interp == identity
-        fused = l_img.is_cuda            # fused softmax + cross-entropy + argmax kernel (losses.py)
+        fused = l_img.is_cuda and self.stock is None         # fused softmax + cross-entropy + argmax kernel (losses.py)
         if fused:
             lab_loss_CE, lab_gt, _ = seg_head(lab_gt, l_gt)                              # :398,401
             _, fake_gt, fake_gt_arg = seg_head(fake_gt, None)                            # :402,435

@@ -608,6 +608,31 @@ def case_conv7_nexp_dgrad(N=2, H=20, W=40, Cout=21):
     return err, scale, scale * 2.0 ** -8
 
 
+def case_conv7_nexp_stem_dgrad(N=2, H=20, W=40, Cin=3):
+    """Data gradient of the 7x7 STEM (Cin -> 64) w.r.t. its halo-padded network input, as the engine launches it
+    (engine.py `nexp_stem`): dRaw (64 channels) in a zero-haloed (6) buffer, CoW = 8 / 16 / 24 / 32 output columns per
+    horizontal tap for Cin <= 8 / 16 / 24 / 32, fp32 output with the channel pitch of gact[0]; vs conv_transpose2d."""
+    _setup()
+    Cout = 64
+    dy = _bf(torch.randn(N, Cout, H, W, device=DEV))
+    w = _bf(torch.randn(Cout, Cin, 7, 7, device=DEV) * 0.05)
+    buf = K.ActBuf(N, H, W, Cout, 6, DEV)
+    _fill_act(buf, dy, L.PAD_ZERO)
+    CoW = 8 if Cin <= 8 else (16 if Cin <= 16 else (24 if Cin <= 24 else 32))
+    slab, nn = _nexp_slab(w, 4, CoW)
+    assert nn == 1
+    Cpitch = G.pad_out_channels(G.pad_in_channels(Cin))
+    Ho, Wo = H + 6, W + 6
+    gx = torch.zeros(N, Ho, Wo, Cpitch, device=DEV)
+    a = K.conv7_args(buf.hi.data_ptr(), Cout, N, buf.Hp, buf.Wp, slab, CoW, 1, 4, CoW, gx.data_ptr(), True,
+                     (Ho * Wo * Cpitch, Wo * Cpitch, Cpitch), tag=5)
+    K.run_conv7(a)
+    torch.cuda.synchronize()
+    ref = F.conv_transpose2d(dy, w)
+    err, scale, _ = _result(gx[..., :Cin].permute(0, 3, 1, 2), ref, 0)
+    return err, scale, 3e-4 * max(1.0, scale)
+
+
 def case_lsgan(shape=(16, 1, 30, 30), target=1.0):
     """Fused LSGAN loss (forward mean + gradient) vs nn.MSELoss against a constant target."""
     _setup()
@@ -770,6 +795,10 @@ CASES = {
     "conv7_nexp_dgrad_c21": lambda: case_conv7_nexp_dgrad(),
     "conv7_nexp_dgrad_c3": lambda: case_conv7_nexp_dgrad(Cout=3),
     "conv7_nexp_dgrad_big": lambda: case_conv7_nexp_dgrad(N=2, H=128, W=256, Cout=20),
+    "conv7_nexp_stem_dgrad_c3": lambda: case_conv7_nexp_stem_dgrad(),                       # CoW = 8
+    "conv7_nexp_stem_dgrad_c1": lambda: case_conv7_nexp_stem_dgrad(N=3, H=13, W=23, Cin=1),  # CoW = 8, ACDC input
+    "conv7_nexp_stem_dgrad_c21": lambda: case_conv7_nexp_stem_dgrad(Cin=21),                 # CoW = 24, label-map input
+    "conv7_nexp_stem_dgrad_c19_big": lambda: case_conv7_nexp_stem_dgrad(N=2, H=128, W=256, Cin=19),
     "lsgan_real": lambda: case_lsgan(),
     "lsgan_fake_odd": lambda: case_lsgan(shape=(3, 1, 7, 5), target=0.0),
     "l1_loss": lambda: case_l1(),

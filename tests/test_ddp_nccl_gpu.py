@@ -1,0 +1,102 @@
+"""-m gpu, needs >= 2 GPUs (skipped otherwise): two ranks over NCCL, each with half of the batch, reproduce the
+single-GPU gradients of the whole batch on the FUSED path: InstanceNorm has no cross-sample
+coupling and every loss is a batch mean, so the all-reduced (averaged) per-rank gradients equal the global-batch
+gradients up to the fp32 summation order of the weight-gradient GEMMs.  Run in parity mode (bf16x3, 1e-5) and in
+the benchmarked bf16 mode (per-sample activations are bit-identical there too; only the fp32 accumulation order of
+the pixel contraction differs)."""
+import os
+import socket
+import subprocess
+import sys
+import tempfile
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+WORKER = r'''
+import os, sys, contextlib, io
+import torch, torch.distributed as dist
+sys.path.insert(0, os.environ["SSCG_ROOT"])
+sys.path.insert(0, os.path.join(os.environ["SSCG_ROOT"], "tests"))
+from test_ddp_nccl_gpu import _make, _data
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(rank)
+dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+prec = os.environ["SSCG_PREC"]
+m = _make(prec, "cuda:%d" % rank)
+l_img, l_gt, unl = [t.cuda() for t in _data()]
+per = l_img.shape[0] // world
+sl = slice(rank * per, rank * per + per)
+out = m.train_step(l_img[sl].contiguous(), l_gt[sl].contiguous(), unl[sl].contiguous())
+torch.cuda.synchronize()
+if rank == 0:
+    torch.save({"g": m.g_grads.flat.cpu(), "d": m.d_grads.flat.cpu()}, os.environ["SSCG_OUT"])
+dist.barrier()
+dist.destroy_process_group()
+'''
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _make(precision, device):
+    import contextlib
+    import io
+    if ROOT not in sys.path:
+        sys.path.insert(0, ROOT)
+    import sscg_b200  # noqa: F401
+    from sscg_b200.step import SemiSupCycleGAN
+    torch.manual_seed(0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = SemiSupCycleGAN(n_classes=21, ngf=16, ndf=16, variant="classic", use_dropout=False, device=device,
+                            precision=precision)
+    return m
+
+
+def _data():
+    g = torch.Generator().manual_seed(3)
+    l_img = torch.rand(4, 3, 64, 64, generator=g) * 2 - 1
+    unl = torch.rand(4, 3, 64, 64, generator=g) * 2 - 1
+    l_gt = torch.randint(0, 21, (4, 1, 64, 64), generator=g)
+    return l_img, l_gt, unl
+
+
+@pytest.mark.parametrize("precision,tol", [("bf16x3", 1e-5), ("bf16", 1e-5)])
+def test_two_rank_nccl_matches_single_gpu(precision, tol):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    m = _make(precision, "cuda:0")
+    l_img, l_gt, unl = [t.cuda() for t in _data()]
+    m.train_step(l_img, l_gt, unl)
+    torch.cuda.synchronize()
+    g_ref, d_ref = m.g_grads.flat.cpu(), m.d_grads.flat.cpu()
+    del m
+    torch.cuda.empty_cache()
+    port = _free_port()
+    with tempfile.TemporaryDirectory() as td:
+        out_path = os.path.join(td, "rank0.pt")
+        wpath = os.path.join(td, "worker.py")
+        with open(wpath, "w") as f:
+            f.write(WORKER)
+        procs = []
+        for r in range(2):
+            env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", LOCAL_RANK=str(r), MASTER_ADDR="127.0.0.1",
+                       MASTER_PORT=str(port), SSCG_ROOT=ROOT, SSCG_OUT=out_path, SSCG_PREC=precision)
+            procs.append(subprocess.Popen([sys.executable, wpath], env=env, stdout=subprocess.PIPE,
+                                          stderr=subprocess.STDOUT))
+        for p in procs:
+            out, _ = p.communicate(timeout=900)
+            assert p.returncode == 0, out.decode()[-3000:]
+        res = torch.load(out_path)
+    eg = float((res["g"] - g_ref).abs().max()) / float(g_ref.abs().max())
+    ed = float((res["d"] - d_ref).abs().max()) / float(d_ref.abs().max())
+    print("2-rank vs 1-GPU gradients (%s): G %.2e, D %.2e (max abs / max abs)" % (precision, eg, ed))
+    assert eg <= tol and ed <= tol, (eg, ed)

@@ -4,12 +4,23 @@ the CPU oracle and the golden vectors generated from the unmodified reference.
 Tolerances (north_star: 1e-3 relative to the fp32 reference, exact argmax):
   * precision 'bf16x3' (parity mode): forward max|a-b| <= 1e-3 * max|b| and argmax identical off the
     near-tie set (top-2 margin < 1e-3 * max|logit|); gradients of the tiny golden nets rel-L2 <= 1e-3.
-    For full-width nets gradients are checked at rel-L2 <= 3e-2: ReLU/LeakyReLU kinks turn a 1e-5
-    forward perturbation into rare O(1) errors of single gradient elements (rel-L2 ~ sqrt(fraction
-    flipped)); this is a property of the function, not of the kernels (tools/debug_bwd.py).
-  * precision 'bf16' (fast mode): bit-level agreement with the bf16-emulated oracle on the tiny nets
-    (<= 1e-5: proves the rounding points are exactly the documented ones) and, for full-width nets,
-    a deviation from the fp32 oracle no larger than 2x the emulated oracle's own deviation.
+    For full-width nets the gradient error is set by ReLU / LeakyReLU kinks, not by arithmetic: a forward deviation
+    d flips the sign of ~d * (density of pre-activations at 0) of the units, each flipped unit is an O(1) error of its
+    gradient, so rel-L2 ~ sqrt(fraction flipped) (3e-5 forward -> ~5e-3 gradient).  test_parity_mode_gradients_sit_
+    at_the_kink_floor DEMONSTRATES this: the fp64 oracle itself, evaluated at an input perturbed so that its output
+    moves as much as the kernels' output deviates, shows the same gradient change; the kernels must stay within 3x
+    of that floor (measured 0.6-1.5x).  The fixed bound 3e-2 is kept as a backstop.
+  * precision 'bf16' (fast mode, the benchmarked one): on the tiny golden nets the forward agrees with the
+    bf16-emulated oracle to <= 1e-5 (proves the forward rounding points are exactly the documented ones) and every
+    gradient agrees with autograd through the emulated oracle (gradients rounded to bf16 where the kernels store them in
+    bf16) to rel-L2 <= 3e-2 — measured 0.6-1.5e-2, which is the noise of ~70 independent bf16 roundings of
+    gradient tensors along the chain (each 2^-9 / sqrt(3) = 1.1e-3 rel-L2; the emulation rounds at the same tensors
+    but not always before / after the same fp32 additions); a wrong tap table, stride, halo or mask gives >= 0.5.
+    For full-width nets (K = 2304 contractions) two bf16 implementations diverge chaotically at the 1e-2 level
+    (different fp32 summation order -> different bf16 roundings of raw outputs), so outputs AND gradients are checked
+    against the envelope: deviation from the fp32 oracle <= 1.5x (outputs: 2x) the deviation of the emulated oracle
+    itself (measured ratio 0.97-1.02): the kernels are as accurate as a plain bf16 PyTorch implementation of the same
+    rounding points.
 """
 import os
 
@@ -81,10 +92,17 @@ def test_generator_golden(tag, name, precision):
         if tag == "softmax":
             assert torch.equal(y.argmax(1).cpu(), _t(z[tag + ".y"]).argmax(1))
     else:
-        sd = _sd(z, tag + ".w.")
-        ye = RA.resnet_generator(sd, _t(z[tag + ".x"]), 9, tanh=(tag == "tanh"), emulate_bf16=True,
-                                 live_norm_bias=False)
+        sd = {k: v.clone().requires_grad_(True) for k, v in _sd(z, tag + ".w.").items()}
+        xe = _t(z[tag + ".x"]).clone().requires_grad_(True)
+        ye = RA.resnet_generator(sd, xe, 9, tanh=(tag == "tanh"), emulate_bf16=True, live_norm_bias=False)
         assert _max_rel(y, ye) <= 1e-5
+        (ye * _t(z[tag + ".probe"])).sum().backward()          # autograd through the emulation: bf16-rounded gradients
+        assert _rel_l2(x.grad, xe.grad) <= 3e-2, _rel_l2(x.grad, xe.grad)
+        for k, p in net.named_parameters():
+            if _norm_cancelled_bias(k):
+                assert float(p.grad.abs().max()) == 0.0
+                continue
+            assert _rel_l2(p.grad, sd[k].grad) <= 3e-2, (k, _rel_l2(p.grad, sd[k].grad))
 
 
 @pytest.mark.parametrize("precision", ["bf16x3", "bf16"])
@@ -106,11 +124,19 @@ def test_discriminator_golden(precision):
                 continue
             assert _rel_l2(p.grad, _t(z["g." + k])) <= 1e-3, k
     else:
-        ye = RA.nlayer_discriminator(_sd(z, "w."), _t(z["x"]), 3, emulate_bf16=True, live_norm_bias=False)
+        sd = {k: v.clone().requires_grad_(True) for k, v in _sd(z, "w.").items()}
+        xe = _t(z["x"]).clone().requires_grad_(True)
+        ye = RA.nlayer_discriminator(sd, xe, 3, emulate_bf16=True, live_norm_bias=False)
         assert _max_rel(y, ye) <= 1e-5
+        (ye * _t(z["probe"])).sum().backward()
+        assert _rel_l2(x.grad, xe.grad) <= 3e-2, _rel_l2(x.grad, xe.grad)
+        for k, p in net.named_parameters():
+            if _norm_cancelled_bias(k):
+                continue
+            assert _rel_l2(p.grad, sd[k].grad) <= 3e-2, (k, _rel_l2(p.grad, sd[k].grad))
 
 
-def _full_width(kind, cfg, N, H, W, precision):
+def _full_width(kind, cfg, N, H, W, precision, want_emulated_grads=False):
     from sscg_b200.arch import define_Dis, define_Gen
     torch.manual_seed(0)
     if kind == "gen":
@@ -132,17 +158,20 @@ def _full_width(kind, cfg, N, H, W, precision):
     (y * probe.cuda()).sum().backward()
     sdr = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
     xr = x.clone().requires_grad_(True)
+    sde = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    xe = x.clone().requires_grad_(True)
     if kind == "gen":
         tanh = not name.endswith("softmax")
         yr = RA.resnet_generator(sdr, xr, 9, tanh=tanh)
-        with torch.no_grad():
-            ye = RA.resnet_generator(sd, x, 9, tanh=tanh, emulate_bf16=True, live_norm_bias=False)
+        ye = RA.resnet_generator(sde, xe, 9, tanh=tanh, emulate_bf16=True, live_norm_bias=False)
     else:
         yr = RA.nlayer_discriminator(sdr, xr, 3)
-        with torch.no_grad():
-            ye = RA.nlayer_discriminator(sd, x, 3, emulate_bf16=True, live_norm_bias=False)
+        ye = RA.nlayer_discriminator(sde, xe, 3, emulate_bf16=True, live_norm_bias=False)
     (yr * probe).sum().backward()
-    return net, y, yr, ye, xg.grad, xr.grad, sdr
+    if want_emulated_grads:
+        (ye * probe).sum().backward()
+    _full_width.extra = dict(sd=sd, x=x, probe=probe, xe=xe, sde=sde)
+    return net, y, yr, ye.detach(), xg.grad, xr.grad, sdr
 
 
 FULL = [("gen", (3, 21, "resnet_9blocks_softmax"), 2, 64, 64),
@@ -172,11 +201,55 @@ def test_full_width_parity_mode(kind, cfg, N, H, W):
 
 @pytest.mark.parametrize("kind,cfg,N,H,W", FULL)
 def test_full_width_fast_mode(kind, cfg, N, H, W):
-    """bf16: deviation from fp32 no larger than 2x that of the bf16-emulated oracle."""
+    """bf16: outputs and gradients deviate from the fp32 oracle no more than a plain bf16 implementation does
+    (the bf16-emulated oracle and autograd through it): outputs <= 2x, gradients <= 1.5x of its deviation."""
     _setup()
-    net, y, yr, ye, gx, gxr, sdr = _full_width(kind, cfg, N, H, W, "bf16")
+    net, y, yr, ye, gx, gxr, sdr = _full_width(kind, cfg, N, H, W, "bf16", want_emulated_grads=True)
+    ex = _full_width.extra
     envelope = _rel_l2(ye, yr)
     assert _rel_l2(y, yr) <= 2.0 * envelope + 1e-4, (_rel_l2(y, yr), envelope)
+    env_gx = _rel_l2(ex["xe"].grad, gxr)
+    assert _rel_l2(gx, gxr) <= 1.5 * env_gx + 1e-3, (_rel_l2(gx, gxr), env_gx)
+    for k, p in net.named_parameters():
+        if _norm_cancelled_bias(k):
+            continue
+        env = _rel_l2(ex["sde"][k].grad, sdr[k].grad)
+        # + 5e-3: the bias of the last conv sums the OUTPUT gradient, which the kernels hold in bf16 (one rounding,
+        # measured 1.3-2.8e-3) while the emulation keeps that one tensor in fp32 (its envelope there is exactly 0)
+        assert _rel_l2(p.grad, sdr[k].grad) <= 1.5 * env + 5e-3, (k, _rel_l2(p.grad, sdr[k].grad), env)
+
+
+@pytest.mark.parametrize("kind,cfg,N,H,W", [FULL[0], FULL[4]])
+def test_parity_mode_gradients_sit_at_the_kink_floor(kind, cfg, N, H, W):
+    """The 3e-2 gradient tolerance of the parity mode is a property of ReLU networks, not of the kernels: evaluate the
+    fp64 oracle at an input perturbed so that ITS output moves by as much as the kernels' output deviates from it
+    (~3e-5); its gradients then change by the 'kink floor' (units whose pre-activation changed sign).  The kernels'
+    gradient errors must stay within 3x of that floor."""
+    _setup()
+    net, y, yr, ye, gx, gxr, sdr = _full_width(kind, cfg, N, H, W, "bf16x3")
+    ex = _full_width.extra
+    tanh = kind == "gen" and not cfg[2].endswith("softmax")
+
+    def oracle64(xin):
+        sd64 = {k: v.double().clone().requires_grad_(True) for k, v in ex["sd"].items()}
+        x64 = xin.double().clone().requires_grad_(True)
+        y64 = (RA.resnet_generator(sd64, x64, 9, tanh=tanh) if kind == "gen" else RA.nlayer_discriminator(sd64, x64, 3))
+        (y64 * ex["probe"].double()).sum().backward()
+        return y64.detach(), x64.grad, {k: v.grad for k, v in sd64.items()}
+
+    y0, gx0, gw0 = oracle64(ex["x"])
+    d_kernel = _rel_l2(y, y0)
+    assert d_kernel <= 2e-4
+    noise = torch.randn(ex["x"].shape, generator=torch.Generator().manual_seed(11), dtype=torch.float64)
+    y1, _, _ = oracle64(ex["x"].double() + 1e-6 * noise)
+    amp = 1e-6 * d_kernel / max(_rel_l2(y1, y0), 1e-30)          # forward is linear in a perturbation this small
+    y2, gx2, gw2 = oracle64(ex["x"].double() + amp * noise)
+    assert 0.5 * d_kernel <= _rel_l2(y2, y0) <= 2.0 * d_kernel
+    floor_gx = _rel_l2(gx2, gx0)
+    worst_floor = max(_rel_l2(gw2[k], gw0[k]) for k in gw0 if not _norm_cancelled_bias(k))
+    worst_kernel = max(_rel_l2(p.grad, gw0[k]) for k, p in net.named_parameters() if not _norm_cancelled_bias(k))
+    assert _rel_l2(gx, gx0) <= 3.0 * floor_gx + 1e-4, (_rel_l2(gx, gx0), floor_gx)
+    assert worst_kernel <= 3.0 * worst_floor + 1e-4, (worst_kernel, worst_floor)
 
 
 def test_state_dict_roundtrip_and_dropout_determinism():
@@ -224,35 +297,3 @@ def test_generator_odd_shapes_and_inference_path(N, H, W):
     yr = RA.resnet_generator(sd, x, 9, tanh=False, use_dropout=True)
     assert y.shape == (N, 21, H, W)
     assert _max_rel(y, yr) <= 1e-3
-
-
-@pytest.mark.parametrize("name,cin,cout", [("resnet_9blocks_softmax", 3, 21), ("resnet_9blocks", 21, 3)])
-def test_fast_mode_gradients_track_parity_mode(name, cin, cout):
-    """The bf16 mode has kernel paths of its own in the BACKWARD pass (N-expanded 7x7 head / stem data gradients,
-    flattened residual data gradients, pipelined normalisation passes) that the parity mode never takes.  Their
-    kernels are pinned case by case in kernel_cases.py; this checks the engine wiring around them: full-width
-    generator, same weights and input, gradients of the two modes agree to the level bf16 storage allows: measured
-    worst case 0.23-0.24 relative L2, at the stem weight — the end of a 24-convolution backward chain in which every
-    bf16-stored gradient and every ReLU kink flip adds its noise — while a wrong tap table, stride or halo gives
-    an O(1) error (uncorrelated gradients: ~1.4)."""
-    _setup()
-    from sscg_b200.arch import define_Gen
-    torch.manual_seed(3)
-    net = define_Gen(cin, cout, 64, name, norm="instance", use_dropout=False, gpu_ids=[0])
-    x0 = (torch.rand(2, cin, 64, 64) * 2 - 1).cuda()
-    probe = torch.randn(2, cout, 64, 64).cuda()
-    grads = {}
-    for precision in ("bf16x3", "bf16"):
-        net.precision = precision
-        net.zero_grad(set_to_none=True)
-        x = x0.clone().requires_grad_(True)
-        (net(x) * probe).sum().backward()
-        grads[precision] = {"x": x.grad.clone(), **{k: p.grad.clone() for k, p in net.named_parameters()}}
-    worst = ("", 0.0)
-    for k, g in grads["bf16x3"].items():
-        if k != "x" and _norm_cancelled_bias(k):
-            continue
-        r = _rel_l2(grads["bf16"][k], g)
-        if r > worst[1]:
-            worst = (k, r)
-    assert worst[1] <= 0.4, worst
