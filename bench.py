@@ -472,15 +472,20 @@ def run_ours(args):
             tj = json.load(f)
         traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source")
     if res_n:
-        achieved = res_conv_flops(args.batch) / 1e12 / (res_ms / res_n / 1e3)
+        # 18 residual-block convs per generator pass, 6 passes per step at `batch` samples each (some passes run batched
+        # two at a time, so launches differ in size): total algorithmic FLOPs of the class / total time of the class
+        res_flops_step = 108 * res_conv_flops(args.batch)
+        achieved = res_flops_step * prof_steps / 1e12 / (res_ms / 1e3)
         peak = peaks["bf16_tflops_sustained"]
         roof = {"bound": "tensor", "kernel": "conv_igemm_kernel<256,1>: 3x3 256->256 @%dx%d residual-block conv, forward "
-                                             "(108 launches per step)" % (H // 4, W // 4),
+                                             "(108 sample-pass launches per step; passes that share a network run batched)"
+                                             % (H // 4, W // 4),
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
                 "traffic_source": traffic_src,
                 "peak_source": peak_src + " (sustained cuBLAS bf16: kernel timed inside a long step)",
                 "avg_launch_ms": res_ms / res_n, "launches_timed": res_n,
-                "algorithmic_flops_per_launch": res_conv_flops(args.batch),
+                "algorithmic_flops_per_launch": res_flops_step * prof_steps / res_n,
+                "algorithmic_flops_per_sample_pass_launch": res_conv_flops(args.batch),
                 "timed_in": "eager pass of %d identical steps right after the timed region, CUDA events on the "
                             "launching stream around every launch" % prof_steps}
     h2d = sum(t.numel() * t.element_size() for t in host_batches[0])

@@ -326,6 +326,15 @@ int sscg_l1_bwd(const float* x, const float* y, int64_t n, const float* dloss, f
 int sscg_adam_flat(float* p, const float* g, float* m, float* v, int64_t n, const float* lr, float beta1, float beta2,
                    float eps, const float* step, void* stream);
 
+/* sscg_interp_bilinear_fwd / _bwd: bilinear resize with align_corners = True on NCHW fp32 — the reference's `interp`
+ * = nn.Upsample(size=(crop_height, crop_width), mode='bilinear', align_corners=True) (model.py:62-63,268), applied to
+ * every generator output when the generator (deeplab) works at 1/8 resolution (model.py:390-392,413-415).  x [N][C][Hi][Wi]
+ * -> y [N][C][Ho][Wo]; backward: dy -> dx as a gather over the output gradient (no atomics, reproducible). */
+int sscg_interp_bilinear_fwd(const float* x, int32_t N, int32_t C, int32_t Hi, int32_t Wi, float* y, int32_t Ho, int32_t Wo,
+                             void* stream);
+int sscg_interp_bilinear_bwd(const float* dy, int32_t N, int32_t C, int32_t Hi, int32_t Wi, int32_t Ho, int32_t Wo,
+                             float* dx, void* stream);
+
 /* sscg_confusion: hist[t * n_class + p] += #{i : label_true[i] == t, label_pred[i] == p, 0 <= t, p < n_class} —
  * the device form of runningScore._fast_hist (utils.py:363-369) used by the validation loop (model.py:555-572). */
 int sscg_confusion(const int64_t* label_true, const int64_t* label_pred, int64_t n, int32_t n_class, uint64_t* hist,

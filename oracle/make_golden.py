@@ -199,14 +199,46 @@ def golden_pool(steps=140, seed=7):
     return ret
 
 
+def golden_extra():
+    """state_dict layout (keys, shapes, trainable flags) and a seeded output checksum of the reference's non-hot
+    families that sscg_b200.arch.extra restates as stock torch modules: deeplab, unet_128, unet_256, fc_disc."""
+    import contextlib
+    import io
+    import json
+    arch = _import_reference()
+    out = {}
+    cases = [("deeplab", lambda: arch.define_Gen(3, 21, 64, "deeplab", norm="instance", use_dropout=True, gpu_ids=[]), (1, 3, 65, 65)),
+             ("unet_128", lambda: arch.define_Gen(3, 5, 8, "unet_128", norm="instance", use_dropout=True, gpu_ids=[]), (1, 3, 128, 128)),
+             ("unet_256", lambda: arch.define_Gen(3, 5, 8, "unet_256", norm="batch", use_dropout=False, gpu_ids=[]), (1, 3, 256, 256)),
+             ("fc_disc", lambda: arch.define_Dis(21, 16, "fc_disc", gpu_ids=[]), (1, 21, 64, 64))]
+    for name, make, shape in cases:
+        torch.manual_seed(0)
+        with contextlib.redirect_stdout(io.StringIO()):
+            net = make()
+        net.eval()
+        x = torch.rand(*shape, generator=torch.Generator().manual_seed(1))
+        with torch.no_grad():
+            y = net(x)
+        out[name] = {"keys": [[k, list(v.shape)] for k, v in net.state_dict().items()],
+                     "trainable": [k for k, p in net.named_parameters() if p.requires_grad],
+                     "out_shape": list(y.shape), "out_sum": float(y.double().sum()), "out_abs_sum": float(y.double().abs().sum())}
+    with open(os.path.join(OUT, "extra_modules.json"), "w") as f:
+        json.dump(out, f)
+    return {k: (len(v["keys"]), v["out_shape"]) for k, v in out.items()}
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "extra":
+        print(golden_extra())
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "pool":        # add the pool fixture without touching the others
         r = golden_pool()
         print("pool_decisions:", r.shape, "stored batches returned:", int((r != np.arange(len(r))[:, None] + 1000 * np.arange(3)).sum()))
         sys.exit(0)
     golden_modules()
     golden_pool()
+    golden_extra()
     print(golden_step())
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

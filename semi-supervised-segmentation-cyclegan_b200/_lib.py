@@ -144,6 +144,10 @@ _SIGNATURES = {
     "sscg_l1_bwd": [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p],
     "sscg_adam_flat": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_float, C.c_float,
                        C.c_float, C.c_void_p, C.c_void_p],
+    "sscg_interp_bilinear_fwd": [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
+                                 C.c_void_p],
+    "sscg_interp_bilinear_bwd": [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                 C.c_void_p],
     "sscg_confusion": [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p],
     "sscg_device_error": [],
     "sscg_version": [],

@@ -60,6 +60,22 @@ class NLayerDiscriminator(nn.Module):
             return self._runner(input, self.training, False, self.precision)
         return self.dis_model(input)
 
+    def forward_parts(self, parts):
+        """ONE batched pass over several inputs (float N x C x H x W tensors and / or int64 label maps N x 1 x H x W that
+        stand for their one-hot encodings): returns the concatenation of what separate calls would return.  The
+        normalisation is per sample, so batching changes no result; it halves the launches and lengthens every
+        kernel's work list (step.py uses it for the two passes that share a network and have independent inputs)."""
+        if parts[0].is_cuda and self.fusable:
+            return self._runner([p.long() if not p.is_floating_point() else p for p in parts], self.training, False,
+                                self.precision)
+        dense = []
+        for p in parts:
+            if not p.is_floating_point():
+                p = torch.zeros(p.size(0), self.input_nc, p.size(2), p.size(3), dtype=torch.float32,
+                                device=p.device).scatter_(1, p.long(), 1)
+            dense.append(p.float())
+        return self.forward(torch.cat(dense))
+
     def forward_onehot(self, labels):
         """forward(make_one_hot(labels, input_nc)) for an int64 label map N x 1 x H x W (model.py:435-438,506-512)
         without materialising the one-hot tensor on the fused path."""
@@ -97,9 +113,9 @@ def define_Dis(input_nc, ndf, netD, n_layers_D=3, norm='batch', gpu_ids=[0]):
     elif netD == 'pixel':
         dis_net = PixelDiscriminator(input_nc, ndf, norm_layer=norm_layer, use_bias=use_bias)
     elif netD == 'fc_disc':
-        # AdvSemiSeg FCDiscriminator (reference discriminators.py:8-39): outside the hot path
-        raise NotImplementedError('Discriminator model name [%s] is outside the B200 hot path '
-                                  '(n_layers and pixel are implemented)' % netD)
+        # AdvSemiSeg FCDiscriminator (reference discriminators.py:8-39,95-96): stock torch, outside the hot path
+        from .extra import FCDiscriminator
+        dis_net = FCDiscriminator(input_nc, ndf)
     else:
         raise NotImplementedError('Discriminator model name [%s] is not recognized' % netD)
 

@@ -77,6 +77,22 @@ class ResnetGenerator(nn.Module):
             return self._runner(x, self.training, self.use_dropout, self.precision)
         return self.res_model(x)
 
+    def forward_parts(self, parts):
+        """ONE batched pass over several inputs (float N x C x H x W tensors and / or int64 label maps N x 1 x H x W that
+        stand for their one-hot encodings): returns the concatenation of what separate calls would return.  The
+        normalisation is per sample, so batching changes no result; it halves the launches and lengthens every
+        kernel's work list (step.py uses it for the two passes that share a network and have independent inputs)."""
+        if parts[0].is_cuda and self.fusable:
+            return self._runner([p.long() if not p.is_floating_point() else p for p in parts], self.training, self.use_dropout,
+                                self.precision)
+        dense = []
+        for p in parts:
+            if not p.is_floating_point():
+                p = torch.zeros(p.size(0), self.input_nc, p.size(2), p.size(3), dtype=torch.float32,
+                                device=p.device).scatter_(1, p.long(), 1)
+            dense.append(p.float())
+        return self.forward(torch.cat(dense))
+
     def forward_onehot(self, labels):
         """forward(make_one_hot(labels, input_nc)) for an int64 label map N x 1 x H x W (model.py:385) without
         materialising the one-hot tensor on the fused path."""
@@ -130,11 +146,28 @@ def define_Gen(input_nc, output_nc, ngf, netG, norm='batch', use_dropout=False, 
     elif netG == 'resnet_6blocks_softmax':
         gen_net = ResnetGenerator(input_nc, output_nc, ngf, norm_layer=norm_layer, use_dropout=use_dropout,
                                   num_blocks=6, softmax=True)
-    elif netG in ('unet_128', 'unet_256', 'enet', 'lednet_128', 'lednet_256', 'deeplab'):
-        # alternative generator families of the reference (generators.py:7-63,98-441): outside the
-        # hot path this package implements — not silently substituted.
-        raise NotImplementedError('Generator model name [%s] is outside the B200 hot path '
-                                  '(only resnet_{6,9}blocks[_softmax] are implemented)' % netG)
+    elif netG in ('unet_128', 'unet_256', 'deeplab'):
+        # not on the B200 hot path: stock torch.nn modules with the reference's module tree (arch/extra.py; SURVEY.md
+        # §7.2, §8 f5) — cuDNN / ATen execute them, exactly as in the reference (generators.py:499-502,510-511)
+        from . import extra
+        if netG == 'deeplab':
+            gen_net = extra.deeplab(input_nc, output_nc)
+        else:
+            gen_net = extra.UnetGenerator(input_nc, output_nc, 7 if netG == 'unet_128' else 8, ngf,
+                                          norm_layer=norm_layer, use_dropout=use_dropout)
+    elif netG in ('enet', 'lednet_128', 'lednet_256'):
+        # reference generators.py:503-509 — delegated to the reference's own modules when its `arch` package is
+        # importable next to this one (~700 lines of blocks outside the hot path are not restated here)
+        from . import extra
+        ref = extra.reference_generators()
+        if ref is None:
+            raise NotImplementedError('Generator model name [%s] is outside the B200 hot path and the reference '
+                                      'package `arch` (which defines it) is not importable' % netG)
+        if netG == 'enet':
+            gen_net = ref.ENet(num_classes=output_nc, encoder_relu=False, decoder_relu=True)
+        else:
+            gen_net = ref.LEDNet(in_channels=input_nc, n_classes=output_nc, encoder_relu=False, decoder_relu=True,
+                                 image_dim=128 if netG == 'lednet_128' else 256)
     else:
         raise NotImplementedError('Generator model name [%s] is not recognized' % netG)
 

@@ -341,6 +341,80 @@ __global__ void wgrad_unpack_batch_kernel(const SscgWbatchEntry* __restrict__ ta
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Bilinear resize, align_corners = True, NCHW fp32 — nn.Upsample(size, mode='bilinear', align_corners=True), the
+// reference's `interp` (model.py:62-63,268; applied at model.py:132,390-392,413-415,562,581-594).  Same index
+// arithmetic and operation order as ATen's upsample_bilinear2d (source index = dst * (in - 1) / (out - 1) in fp32).
+// The backward is a GATHER over the output gradient (each input element sums the outputs that read it, in raster
+// order): no atomics, reproducible.
+// ---------------------------------------------------------------------------------------------
+struct InterpTap {
+    int i0, i1;
+    float l0, l1;
+};
+__device__ __forceinline__ InterpTap interp_tap(int o, float scale, int in_size) {
+    InterpTap t;
+    const float src = scale * (float)o;
+    t.i0 = (int)src;                                   // src >= 0
+    if (t.i0 > in_size - 1) t.i0 = in_size - 1;
+    t.i1 = t.i0 + (t.i0 < in_size - 1 ? 1 : 0);
+    t.l1 = src - (float)t.i0;
+    t.l0 = 1.f - t.l1;
+    return t;
+}
+__global__ void __launch_bounds__(256) interp_fwd_kernel(const float* __restrict__ x, int NC, int Hi, int Wi,
+                                                         float* __restrict__ y, int Ho, int Wo, float sh, float sw) {
+    const long long total = (long long)NC * Ho * Wo;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int ow = idx % Wo;
+        const int oh = (idx / Wo) % Ho;
+        const long long nc = idx / ((long long)Wo * Ho);
+        const InterpTap th = interp_tap(oh, sh, Hi), tw = interp_tap(ow, sw, Wi);
+        const float* p = x + nc * Hi * Wi;
+        y[idx] = th.l0 * (tw.l0 * p[th.i0 * Wi + tw.i0] + tw.l1 * p[th.i0 * Wi + tw.i1]) +
+                 th.l1 * (tw.l0 * p[th.i1 * Wi + tw.i0] + tw.l1 * p[th.i1 * Wi + tw.i1]);
+    }
+}
+__global__ void __launch_bounds__(256) interp_bwd_kernel(const float* __restrict__ dy, int NC, int Hi, int Wi,
+                                                         float* __restrict__ dx, int Ho, int Wo, float sh, float sw) {
+    const long long total = (long long)NC * Hi * Wi;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int iw = idx % Wi;
+        const int ih = (idx / Wi) % Hi;
+        const long long nc = idx / ((long long)Wi * Hi);
+        // candidate outputs: those whose source index lies within one input pixel of (ih, iw); tested exactly below
+        int oh0 = 0, oh1 = Ho - 1, ow0 = 0, ow1 = Wo - 1;
+        if (sh > 0.f) {
+            oh0 = max(0, (int)floorf((float)(ih - 1) / sh) - 1);
+            oh1 = min(Ho - 1, (int)ceilf((float)(ih + 1) / sh) + 1);
+        }
+        if (sw > 0.f) {
+            ow0 = max(0, (int)floorf((float)(iw - 1) / sw) - 1);
+            ow1 = min(Wo - 1, (int)ceilf((float)(iw + 1) / sw) + 1);
+        }
+        const float* g = dy + nc * Ho * Wo;
+        float acc = 0.f;
+        for (int oh = oh0; oh <= oh1; ++oh) {
+            const InterpTap th = interp_tap(oh, sh, Hi);
+            float wh = 0.f;
+            if (th.i0 == ih) wh += th.l0;
+            if (th.i1 == ih) wh += th.l1;            // i1 == i0 at the last row: both weights land on it (l1 = 0 there)
+            if (wh == 0.f && th.i0 != ih && th.i1 != ih) continue;
+            for (int ow = ow0; ow <= ow1; ++ow) {
+                const InterpTap tw = interp_tap(ow, sw, Wi);
+                float ww = 0.f;
+                if (tw.i0 == iw) ww += tw.l0;
+                if (tw.i1 == iw) ww += tw.l1;
+                if (tw.i0 != iw && tw.i1 != iw) continue;
+                acc += wh * ww * g[oh * Wo + ow];
+            }
+        }
+        dx[idx] = acc;
+    }
+}
+
 static inline int ew_grid(long long total, int block) {
     long long g = (total + block - 1) / block;
     if (g > 148 * 16) g = 148 * 16;
@@ -618,6 +692,32 @@ extern "C" int sscg_in_bwd_apply(const SscgBwdArgs* a, void* draw, void* draw_lo
             in_bwd_apply_kernel<false><<<dim3(gridx, a->N), 256, 0, static_cast<cudaStream_t>(stream)>>>(d);
     }
     SSCG_CHECK_LAUNCH("in_bwd_apply");
+    return 0;
+}
+
+static inline float interp_scale(int in_size, int out_size) {
+    return out_size > 1 ? (float)(in_size - 1) / (float)(out_size - 1) : 0.f;
+}
+extern "C" int sscg_interp_bilinear_fwd(const float* x, int32_t N, int32_t C, int32_t Hi, int32_t Wi, float* y, int32_t Ho,
+                                        int32_t Wo, void* stream) {
+    if (!x || !y || N < 1 || C < 1 || Hi < 1 || Wi < 1 || Ho < 1 || Wo < 1) return set_error("interp_bilinear_fwd: bad arguments");
+    {
+        LaunchScope ls_(9, static_cast<cudaStream_t>(stream));
+        interp_fwd_kernel<<<ew_grid((long long)N * C * Ho * Wo, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+            x, N * C, Hi, Wi, y, Ho, Wo, interp_scale(Hi, Ho), interp_scale(Wi, Wo));
+    }
+    SSCG_CHECK_LAUNCH("interp_bilinear_fwd");
+    return 0;
+}
+extern "C" int sscg_interp_bilinear_bwd(const float* dy, int32_t N, int32_t C, int32_t Hi, int32_t Wi, int32_t Ho,
+                                        int32_t Wo, float* dx, void* stream) {
+    if (!dy || !dx || N < 1 || C < 1 || Hi < 1 || Wi < 1 || Ho < 1 || Wo < 1) return set_error("interp_bilinear_bwd: bad arguments");
+    {
+        LaunchScope ls_(9, static_cast<cudaStream_t>(stream));
+        interp_bwd_kernel<<<ew_grid((long long)N * C * Hi * Wi, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+            dy, N * C, Hi, Wi, dx, Ho, Wo, interp_scale(Hi, Ho), interp_scale(Wi, Wo));
+    }
+    SSCG_CHECK_LAUNCH("interp_bilinear_bwd");
     return 0;
 }
 

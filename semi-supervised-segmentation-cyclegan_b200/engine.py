@@ -324,17 +324,24 @@ class NetPlan:
             return buf.view(interior=True), buf.lo_ptr(interior=True)
         return buf.view(interior=False), buf.lo_ptr(interior=False)
 
-    def forward(self, c: Ctx, x=None, labels=None, n_classes=None, training=True, drop_seed=0):
-        """x: NCHW fp32 (or labels int64 N x 1 x H x W to be one-hot encoded on the fly).
+    def forward(self, c: Ctx, x=None, labels=None, n_classes=None, training=True, drop_seed=0, parts=None):
+        """x: NCHW fp32 (or labels int64 N x 1 x H x W to be one-hot encoded on the fly), or `parts`: a list of such
+        tensors whose batches are packed one after the other (one batched pass instead of several, step.py).
         Leaves the fp32 NHWC result in c.out; returns c."""
         sp = self.split
         c.stats.zero_()          # plane-sum accumulators (the GEMM epilogues add into them)
         s0 = self.specs[0]
         mode0 = L.PAD_REFLECT if s0.in_reflect else L.PAD_ZERO
-        if labels is not None:
-            K.onehot_pack(labels, n_classes, c.act[0], mode0)
-        else:
-            K.pack_nchw(x, c.act[0], mode0)
+        if parts is None:
+            parts = [labels if labels is not None else x]
+        n_off = 0
+        for t in parts:
+            if t.dtype == torch.int64:
+                K.onehot_pack(t, s0.Cin if n_classes is None else n_classes, c.act[0], mode0, n_off)
+            else:
+                K.pack_nchw(t, c.act[0], mode0, n_off)
+            n_off += t.shape[0]
+        assert n_off == self.N
         c.drop_seed = drop_seed if training else 0
         nst = len(self.specs)
         for i, (s, wt) in enumerate(zip(self.specs, self.weights)):
@@ -404,10 +411,13 @@ class NetPlan:
 
     # ------------------------------------------------------------------ backward
     def backward(self, c: Ctx, grad_out=None, need_dx=True, need_dw=True, accumulate_dw=False, gout_ready=False,
-                 debug_hook=None):
+                 debug_hook=None, dx_range=None):
         """grad_out: NCHW fp32 gradient of the network output (or gout_ready=True when self.gout was
         filled by a fused loss kernel).  Weight-gradient slabs are accumulated in self.weights[i].dw
-        (zeroed first unless accumulate_dw).  Returns grad_in NCHW fp32 (or None)."""
+        (zeroed first unless accumulate_dw).  Returns grad_in NCHW fp32 (or None); with dx_range = (n0, n1) the input
+        gradient is computed and returned for those samples only (batched passes whose other parts are data)."""
+        if dx_range is not None and tuple(dx_range) == (0, self.N):
+            dx_range = None
         self._ensure_scratch()
         sp = self.split
         N = self.N
@@ -425,10 +435,10 @@ class NetPlan:
         for i in range(nst - 1, -1, -1):
             s, wt = self.specs[i], self.weights[i]
             hin, win, ho, wo = self.geom[i]
-            key = ("b", id(c), i, need_dx, need_dw)
+            key = ("b", id(c), i, need_dx, need_dw, dx_range if i == 0 else None)
             args = self._args_cache.get(key)
             if args is None:
-                args = self._build_bwd_args(c, i, need_dx, need_dw)
+                args = self._build_bwd_args(c, i, need_dx, need_dw, dx_range if i == 0 else None)
                 self._args_cache[key] = args
             ba, use_apply, wa, da = args
             ba.drop_seed = (c.drop_seed * 1000003 + i + 1) if (s.dropout and c.drop_seed) else 0
@@ -470,8 +480,9 @@ class NetPlan:
         gx = None
         if need_dx:
             s0 = self.specs[0]
-            gx = torch.empty(N, s0.Cin, self.H, self.W, dtype=torch.float32, device=self.device)
-            K.unpack_fold(self.gact[0], s0.Cin, gx, L.PAD_REFLECT if s0.in_reflect else L.PAD_ZERO)
+            n0, n1 = dx_range if dx_range is not None else (0, N)
+            gx = torch.empty(n1 - n0, s0.Cin, self.H, self.W, dtype=torch.float32, device=self.device)
+            K.unpack_fold(self.gact[0], s0.Cin, gx, L.PAD_REFLECT if s0.in_reflect else L.PAD_ZERO, n0, n1)
         return gx
 
     def _draw_view(self, i, lo=False):
@@ -485,7 +496,7 @@ class NetPlan:
         cp = wt.Co_pitch
         return L.make_view(t.data_ptr(), self.N, ho, wo, cp, ho * wo * cp, wo * cp, cp)
 
-    def _build_bwd_args(self, c: Ctx, i, need_dx, need_dw):
+    def _build_bwd_args(self, c: Ctx, i, need_dx, need_dw, dx_range=None):
         s, wt = self.specs[i], self.weights[i]
         sp = self.split
         N = self.N
@@ -557,11 +568,13 @@ class NetPlan:
         # ---- 3. dgrad ------------------------------------------------------------------------
         da = None
         dkw = {}
+        n0, n1 = dx_range if dx_range is not None else (0, N)      # stage 0 only: samples whose input gradient is wanted
         if i == 0 and i in self.draw_nx and need_dx and wt.need_dgrad:
             gin, src = self.gact[0], self.draw_nx[0]          # fp32 gradient w.r.t. the halo-padded network input
             assert gin.pad == 3 and gin.fp32 and gin.C >= wt.nx_CoW
-            da = K.conv7_args(src.hi.data_ptr(), src.C, N, src.Hp, src.Wp, wt.w_nx_dg, wt.nx_CoW, 1, 4, wt.nx_CoW,
-                              gin.hi.data_ptr(), True, (gin.sN, gin.sH, gin.sW), tag=5)
+            da = K.conv7_args(src.hi.data_ptr() + n0 * src.sN * src.esize, src.C, n1 - n0, src.Hp, src.Wp, wt.w_nx_dg,
+                              wt.nx_CoW, 1, 4, wt.nx_CoW, gin.hi.data_ptr() + n0 * gin.sN * gin.esize, True,
+                              (gin.sN, gin.sH, gin.sW), tag=5)
         elif i in self.draw_nx and i > 0 and wt.need_dgrad and not self.gact[i].fp32:
             gin, src = self.gact[i], self.draw_nx[i]
             assert gin.pad == 3 and gin.C == 32 * wt.nx_dg_tiles
@@ -594,8 +607,13 @@ class NetPlan:
                     Ho_d, Wo_d, yoff = gin.Hp, gin.Wp, (0, 0)
                 else:
                     Ho_d, Wo_d, yoff = hin, win, (0, 0)
+            gptr = gin.hi.data_ptr()
+            if i == 0 and dx_range is not None:
+                dview = K.sub_view(dview, n0, n1)
+                dlo = (dlo + n0 * dview.sN * 2) if dlo is not None else None
+                gptr += n0 * gin.sN * gin.esize
             da = K.conv_args(dview, dlo, table, wt.Kc_d, wt.w_dg, wt.w_dg_lo, s.k * s.k * wt.Ci_pad, wt.Ci_pad,
-                             gin.hi.data_ptr(), gin.fp32, (gin.sN, gin.sH, gin.sW), yoff, Ho_d, Wo_d, split=sp,
+                             gptr, gin.fp32, (gin.sN, gin.sH, gin.sW), yoff, Ho_d, Wo_d, split=sp,
                              tag=2 if s.name.startswith("res") else 5, **dkw)
         return ba, use_apply, wa, da
 

@@ -277,27 +277,38 @@ def run_wgrad_unpack(a, slab, grad, scale=1.0):
             "sscg_wgrad_unpack")
 
 
-def pack_nchw(src, dst: ActBuf, pad_mode):
+def pack_nchw(src, dst: ActBuf, pad_mode, n_off=0):
+    """NCHW fp32 -> samples [n_off, n_off + N) of the NHWC buffer (a batched pass packs its parts one after the other)."""
     N, Cc, H, W = src.shape
-    assert src.dtype == torch.float32 and src.is_contiguous()
-    L.check(L.lib().sscg_pack_nchw(_ptr(src), N, Cc, H, W, _ptr(dst.hi), _ptr(dst.lo), 1 if dst.fp32 else 0, dst.C,
-                                   dst.pad, pad_mode, _stream()), "sscg_pack_nchw")
+    assert src.dtype == torch.float32 and src.is_contiguous() and n_off + N <= dst.N
+    off = n_off * dst.sN * dst.esize
+    L.check(L.lib().sscg_pack_nchw(_ptr(src), N, Cc, H, W, _ptr(dst.hi, off), _ptr(dst.lo, off), 1 if dst.fp32 else 0,
+                                   dst.C, dst.pad, pad_mode, _stream()), "sscg_pack_nchw")
 
 
-def onehot_pack(labels, Cc, dst: ActBuf, pad_mode):
+def onehot_pack(labels, Cc, dst: ActBuf, pad_mode, n_off=0):
     N, one, H, W = labels.shape
-    assert labels.dtype == torch.int64 and labels.is_contiguous() and one == 1
-    L.check(L.lib().sscg_onehot_pack(_ptr(labels), N, Cc, H, W, _ptr(dst.hi), _ptr(dst.lo), dst.C, dst.pad, pad_mode,
-                                     _stream()), "sscg_onehot_pack")
+    assert labels.dtype == torch.int64 and labels.is_contiguous() and one == 1 and n_off + N <= dst.N
+    off = n_off * dst.sN * dst.esize
+    L.check(L.lib().sscg_onehot_pack(_ptr(labels), N, Cc, H, W, _ptr(dst.hi, off), _ptr(dst.lo, off), dst.C, dst.pad,
+                                     pad_mode, _stream()), "sscg_onehot_pack")
 
 
 def unpack_nhwc(src_f32, N, Cc, H, W, Cp, dst):
     L.check(L.lib().sscg_unpack_nhwc(_ptr(src_f32), N, Cc, H, W, Cp, _ptr(dst), _stream()), "sscg_unpack_nhwc")
 
 
-def unpack_fold(src: ActBuf, Cc, dst, pad_mode):
-    L.check(L.lib().sscg_unpack_fold(_ptr(src.hi), 1 if src.fp32 else 0, src.N, Cc, src.H, src.W, src.C, src.pad,
+def unpack_fold(src: ActBuf, Cc, dst, pad_mode, n0=0, n1=None):
+    """Samples [n0, n1) of the padded NHWC gradient buffer -> NCHW fp32 (halo gradients folded back)."""
+    n1 = src.N if n1 is None else n1
+    off = n0 * src.sN * src.esize
+    L.check(L.lib().sscg_unpack_fold(_ptr(src.hi, off), 1 if src.fp32 else 0, n1 - n0, Cc, src.H, src.W, src.C, src.pad,
                                      pad_mode, _ptr(dst), _stream()), "sscg_unpack_fold")
+
+
+def sub_view(v, n0, n1, esize=2):
+    """Samples [n0, n1) of a view."""
+    return L.make_view(v.ptr + n0 * v.sN * esize, n1 - n0, v.H, v.W, v.C, v.sN, v.sH, v.sW)
 
 
 def bias_grad(bstats, N, Cc, Cp, grad, scale=1.0):

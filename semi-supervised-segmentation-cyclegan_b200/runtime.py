@@ -165,12 +165,15 @@ class NetRunner:
     def __call__(self, x, training, use_dropout, precision=None):
         """x: NCHW fp32, or an int64 label map N x 1 x H x W that stands for its one-hot encoding over the
         network's input channels (make_one_hot, utils.py:314-350): the first stage's operand buffer is then written
-        straight from the labels (sscg_onehot_pack) and no N x C x H x W fp32 tensor is materialised."""
-        if not x.is_cuda:
+        straight from the labels (sscg_onehot_pack) and no N x C x H x W fp32 tensor is materialised.
+        A list / tuple of such tensors runs ONE batched pass over the concatenation of their batches (InstanceNorm is
+        per sample, so every sample's result is the one a separate call would give); the output is the concatenation."""
+        parts = list(x) if isinstance(x, (list, tuple)) else [x]
+        if not all(p.is_cuda for p in parts):
             raise RuntimeError("fused path needs CUDA tensors")
-        self._setup(x.device, precision or _DEFAULT_PRECISION)
+        self._setup(parts[0].device, precision or _DEFAULT_PRECISION)
         params = self.params()
-        return _FusedNet.apply(self, training and use_dropout, x, *params)
+        return _FusedNet.apply(self, training and use_dropout, len(parts), *parts, *params)
 
 
 class _CtxLease:
@@ -191,13 +194,19 @@ class _CtxLease:
 
 class _FusedNet(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, runner: NetRunner, dropout_on, x, *params):
-        x = x.detach()
-        labels = x.dtype == torch.int64
-        if not labels and x.dtype != torch.float32:
-            x = x.float()
-        x = x.contiguous()
-        N, _, H, W = x.shape
+    def forward(ctx, runner: NetRunner, dropout_on, nparts, *rest):
+        parts, params = rest[:nparts], rest[nparts:]
+        prepared = []
+        for x in parts:
+            x = x.detach()
+            if x.dtype != torch.int64 and x.dtype != torch.float32:
+                x = x.float()
+            if x.dtype == torch.int64:
+                assert x.shape[1] == 1, "label maps are N x 1 x H x W"
+            prepared.append(x.contiguous())
+        N = sum(p.shape[0] for p in prepared)
+        H, W = prepared[0].shape[2:]
+        assert all(p.shape[2:] == prepared[0].shape[2:] for p in prepared), "batched parts must share H x W"
         runner.ensure_weights()
         plan = runner.plan(N, H, W)
         c = plan.acquire_ctx()
@@ -205,16 +214,14 @@ class _FusedNet(torch.autograd.Function):
         if dropout_on:
             seed = int(torch.randint(1, 2 ** 31 - 1, (1,)).item())   # CPU generator: follows torch.manual_seed
             seed = (seed ^ _rank_salt()) or 1                        # ... and differs between data-parallel ranks
-        if labels:
-            assert x.shape[1] == 1, "label maps are N x 1 x H x W"
-            plan.forward(c, labels=x, n_classes=runner.specs[0].Cin, training=dropout_on, drop_seed=seed)
-        else:
-            plan.forward(c, x, training=dropout_on, drop_seed=seed)
+        plan.forward(c, parts=prepared, training=dropout_on, drop_seed=seed)
         y = plan.output_nchw(c)
         # (grad mode is always off inside Function.forward; needs_input_grad already reflects no_grad())
-        need_grad = any(ctx.needs_input_grad[2:])
+        need_grad = any(ctx.needs_input_grad[3:])
         if need_grad:
             ctx.runner, ctx.plan, ctx.lease = runner, plan, _CtxLease(plan, c)
+            ctx.nparts = nparts
+            ctx.part_sizes = [p.shape[0] for p in prepared]
         else:
             plan.release_ctx(c)
             ctx.plan = None
@@ -225,20 +232,35 @@ class _FusedNet(torch.autograd.Function):
         plan, c, runner = ctx.plan, ctx.lease.c, ctx.runner
         if c is None:
             raise RuntimeError("fused network: backward called twice on the same graph (activations were released)")
-        need_dx = ctx.needs_input_grad[2]
-        need_dw = any(ctx.needs_input_grad[3:])
+        nparts = ctx.nparts
+        part_need = list(ctx.needs_input_grad[3:3 + nparts])
+        need_dx = any(part_need)
+        need_dw = any(ctx.needs_input_grad[3 + nparts:])
+        # input gradient only for the sample range spanned by the parts that want one
+        starts = [sum(ctx.part_sizes[:j]) for j in range(nparts + 1)]
+        dx_range = None
+        if need_dx:
+            want = [j for j in range(nparts) if part_need[j]]
+            dx_range = (starts[want[0]], starts[want[-1] + 1])
         direct = need_dw and runner.direct_grad and all(p.grad is not None for p in runner.params() if p.requires_grad)
         defer = direct and runner.defer_unpack
-        gx = plan.backward(c, gy.float(), need_dx=need_dx, need_dw=need_dw, accumulate_dw=defer)
+        gx = plan.backward(c, gy.float(), need_dx=need_dx, need_dw=need_dw, accumulate_dw=defer, dx_range=dx_range)
+        gparts = [None] * nparts
+        if need_dx:
+            for j in range(nparts):
+                if part_need[j]:
+                    a0 = starts[j] - dx_range[0]
+                    gparts[j] = gx[a0:a0 + ctx.part_sizes[j]]
         grads = []
+        nparams = len(ctx.needs_input_grad) - 3 - nparts
         if direct:
             into = [(s.weight.grad, s.bias.grad if s.bias is not None else None) for s in plan.specs]
             plan.param_grads(into=into, weights=not defer)
             runner._dw_dirty = runner._dw_dirty or defer
-            grads = [None] * (len(ctx.needs_input_grad) - 3)
+            grads = [None] * nparams
         elif need_dw:
             pg = plan.param_grads()
-            flags = list(ctx.needs_input_grad[3:])
+            flags = list(ctx.needs_input_grad[3 + nparts:])
             j = 0
             for (gw, gb), s in zip(pg, plan.specs):
                 grads.append(gw if flags[j] else None)
@@ -247,6 +269,6 @@ class _FusedNet(torch.autograd.Function):
                     grads.append(gb if flags[j] else None)
                     j += 1
         else:
-            grads = [None] * (len(ctx.needs_input_grad) - 3)
+            grads = [None] * nparams
         ctx.lease.release()
-        return (None, None, gx, *grads)
+        return (None, None, None, *gparts, *grads)

@@ -146,13 +146,18 @@ class _StockGrads:
 class SemiSupCycleGAN:
     def __init__(self, n_classes=21, img_channels=3, ngf=64, ndf=64, variant="classic", use_dropout=True, lr=2e-4,
                  device="cuda", precision=None, weights=None, keep_dead_forward=True, fused_adam=True,
-                 graph_safe=False, stock=None):
+                 graph_safe=False, stock=None, batch_passes=None):
         """stock: None = this repo's fused path on CUDA.  "fp32" | "tf32" | "bf16_autocast" = the SAME step on the
         stock torch.nn module trees (cuDNN convolutions, ATen InstanceNorm / losses, torch.optim.Adam): the on-box GPU
         baseline of bench.py (the reference's own modules executed by stock PyTorch, arch/ops.py:40-74)."""
         assert variant in ("classic", "head")
         assert stock in (None, "fp32", "tf32", "bf16_autocast")
         self.stock = stock
+        # batch_passes: run the pairs of passes that share a network and have independent inputs — Gsi(unl_img) with
+        # Gsi(l_img) (model.py:386-387), Gis(one_hot(l_gt)) with Gis(fake_gt) (:385,408), Di(unl_img) with Di(fake_img)
+        # (:499-500), Ds(real) with Ds(fake) (:506-512) — as ONE pass over the concatenated batch.  InstanceNorm is per
+        # sample and every loss is a batch mean, so no result changes; default on for the fused CUDA path.
+        self.batch_passes = batch_passes
         self.C, self.variant = n_classes, variant
         self.w = weights or StepWeights()
         self.keep_dead_forward = keep_dead_forward
@@ -275,21 +280,36 @@ class SemiSupCycleGAN:
             set_grad([self.old_Gsi, self.old_Gis], False)                                # :380
         self.g_grads.zero()                                                              # :381
         onehot_in = l_img.is_cuda and self.stock is None     # label glue: one-hot inputs go in as label maps (arch.*.forward_onehot)
-        fake_img = (self.Gis.forward_onehot(l_gt) if onehot_in
-                    else self.Gis(make_one_hot(l_gt, C).float()))                        # :385
-        fake_gt = self.Gsi(unl_img.float())                                              # :386
-        lab_gt = self.Gsi(l_img)                                                         # :387
-        assert fake_img.shape[2:] == l_img.shape[2:] and fake_gt.shape[2:] == l_img.shape[2:]   # interp == identity
         fused = l_img.is_cuda and self.stock is None         # fused softmax + cross-entropy + argmax kernel (losses.py)
-        if fused:
-            lab_loss_CE, lab_gt, _ = seg_head(lab_gt, l_gt)                              # :398,401
-            _, fake_gt, fake_gt_arg = seg_head(fake_gt, None)                            # :402,435
+        batched = fused and (self.batch_passes if self.batch_passes is not None else True)
+        N = l_img.shape[0]
+        if batched:
+            # Gsi(unl_img) and Gsi(l_img) as one pass (:386-387); softmax / CE / argmax of both halves in one launch: the
+            # unlabeled half carries ignore_index labels, so the mean cross-entropy is over the labeled half (:398)
+            logits2 = self.Gsi.forward_parts([unl_img.float(), l_img])
+            lab2 = torch.cat([torch.full_like(l_gt, -100), l_gt])
+            lab_loss_CE, probs2, arg2 = seg_head(logits2, lab2)                          # :398,401-402,435
+            fake_gt, lab_gt = probs2[:N], probs2[N:]
+            fake_gt_arg = arg2[:N]
+            # Gis(one_hot(l_gt)) and Gis(fake_gt) as one pass (:385,408); the input gradient is computed for the second
+            # half only (the first is data)
+            img2 = self.Gis.forward_parts([l_gt, fake_gt])
+            fake_img, recon_img = img2[:N], img2[N:]
         else:
-            lab_loss_CE = self.CE(lab_gt, l_gt.squeeze(1))                               # :398
-            lab_gt = self.softmax(lab_gt)                                                # :401
-            fake_gt = self.softmax(fake_gt)                                              # :402
-            fake_gt_arg = fake_gt.data.max(1)[1]                                         # :435
-        recon_img = self.Gis(fake_gt.float())                                            # :408
+            fake_img = (self.Gis.forward_onehot(l_gt) if onehot_in
+                        else self.Gis(make_one_hot(l_gt, C).float()))                    # :385
+            fake_gt = self.Gsi(unl_img.float())                                          # :386
+            lab_gt = self.Gsi(l_img)                                                     # :387
+            if fused:
+                lab_loss_CE, lab_gt, _ = seg_head(lab_gt, l_gt)                          # :398,401
+                _, fake_gt, fake_gt_arg = seg_head(fake_gt, None)                        # :402,435
+            else:
+                lab_loss_CE = self.CE(lab_gt, l_gt.squeeze(1))                           # :398
+                lab_gt = self.softmax(lab_gt)                                            # :401
+                fake_gt = self.softmax(fake_gt)                                          # :402
+                fake_gt_arg = fake_gt.data.max(1)[1]                                     # :435
+            recon_img = self.Gis(fake_gt.float())                                        # :408
+        assert fake_img.shape[2:] == l_img.shape[2:] and fake_gt.shape[2:] == l_img.shape[2:]   # interp == identity
         if self.keep_dead_forward:
             with torch.no_grad():
                 self.Gis(lab_gt.float())      # recon_lab_img (:409) feeds no loss: forward only
@@ -354,9 +374,17 @@ class SemiSupCycleGAN:
             recon_img = self.pool_recon([recon_img.detach()])[0]                         # :490
             fake_img = self.pool_fake_img([fake_img.detach()])[0]                        # :491
             fake_gt = self.pool_fake_gt([fake_gt.detach()])[0]                           # :493
-        unl_img_dis = self.Di(unl_img)                                                   # :499
-        fake_img_dis = self.Di(fake_img)                                                 # :500
-        if onehot_in:
+        if batched:
+            d2 = self.Di.forward_parts([unl_img, fake_img])                              # :499-500 as one pass
+            unl_img_dis, fake_img_dis = d2[:N], d2[N:]
+            s2 = self.Ds.forward_parts([l_gt, fake_gt.data.max(1)[1].unsqueeze(1)])      # :506-512 as one pass
+            real_gt_dis, fake_gt_dis = s2[:N], s2[N:]
+        else:
+            unl_img_dis = self.Di(unl_img)                                               # :499
+            fake_img_dis = self.Di(fake_img)                                             # :500
+        if batched:
+            pass
+        elif onehot_in:
             real_gt_dis = self.Ds.forward_onehot(l_gt)                                   # :506-507
             fake_gt_dis = self.Ds.forward_onehot(fake_gt.data.max(1)[1].unsqueeze(1))    # :509-512
         else:

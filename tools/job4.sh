@@ -1,0 +1,12 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -12 gpurun_out/pytest_gpu.log
+timeout 600 python tools/determinism_probe.py > gpurun_out/determinism.log 2>&1; echo "det rc=$?"; grep check gpurun_out/determinism.log | cut -c1-250
+timeout 900 python bench.py --steps 10 --warmup 3 --no-gpu-baseline --no-cpu-baseline > gpurun_out/bench_d.json 2> gpurun_out/bench_d.err; echo "bench rc=$?"; tail -3 gpurun_out/bench_d.err
+python - <<'PY'
+import json
+d=json.loads(open("gpurun_out/bench_d.json").read().strip().splitlines()[-1])
+print(d["value"], d["ms_per_step"], d["e2e"]["value"], d["roofline"]["frac"], d["gpu_launches"]/d["steps"])
+print(json.dumps(d["kernel_time_ms_per_step"]))
+print(json.dumps(d["kernel_launches_per_step"]))
+PY
