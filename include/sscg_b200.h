@@ -148,6 +148,27 @@ typedef struct SscgWgradArgs {
 int sscg_conv_wgrad(const SscgWgradArgs* a, void* stream);
 int64_t sscg_conv_wgrad_ws_bytes(const SscgWgradArgs* a);
 
+/* sscg_conv_wgrad7 — weight gradient of the 7x7 stride-1 generator HEAD (64 -> <= 32 channels, arch/generators.py:84-85,
+ * 89-90) with the seven horizontal taps as GEMM columns (csrc/conv_wgrad7.cu): replaces the window-mode launch of
+ * sscg_conv_wgrad for that layer (631 -> ~100 us at 16 x 256 x 256).
+ *   x : bf16 [N][H+6][W+6][64]   the head's input activation with its explicit (reflect) halo of 3
+ *   dy: bf16 [N][H+12][W+12][Cy] the gradient w.r.t. the head's raw output in a buffer with a ZERO halo of 6 (the layout
+ *       sscg_conv7_nexp's data gradient reads); Cy = 16 or 32 channels per pixel, padding channels zero
+ *   dw: fp32 [7 kh][64 rows = co][448 = (kw, ci)], ADDED to — the window-mode slab layout (sscg_wprep mode 1)
+ *   ws: sscg_conv_wgrad7_ws_bytes() bytes (counters zero before the first launch, left zero by every launch); the
+ *       per-CTA tiles are combined in CTA order: reproducible. */
+typedef struct SscgWgrad7Args {
+    const void* x;
+    const void* dy;
+    int32_t N, H, W;
+    int32_t Cy;
+    float* dw;
+    void* ws;
+    int32_t tag;
+} SscgWgrad7Args;
+int sscg_conv_wgrad7(const SscgWgrad7Args* a, void* stream);
+int64_t sscg_conv_wgrad7_ws_bytes(const SscgWgrad7Args* a);
+
 /* ---------------------------------------------------------------------------------------------
  * Elementwise / reduction kernels around the GEMMs.
  * ------------------------------------------------------------------------------------------- */

@@ -60,6 +60,11 @@ class WgradArgs(C.Structure):
     ]
 
 
+class Wgrad7Args(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("dy", C.c_void_p), ("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+                ("Cy", C.c_int32), ("dw", C.c_void_p), ("ws", C.c_void_p), ("tag", C.c_int32)]
+
+
 class ApplyArgs(C.Structure):
     _fields_ = [
         ("raw", C.c_void_p), ("raw_fp32", C.c_int32),
@@ -116,6 +121,8 @@ _SIGNATURES = {
     "sscg_conv_igemm": [C.POINTER(ConvArgs), C.c_void_p],
     "sscg_conv_wgrad": [C.POINTER(WgradArgs), C.c_void_p],
     "sscg_conv_wgrad_ws_bytes": [C.POINTER(WgradArgs)],
+    "sscg_conv_wgrad7": [C.POINTER(Wgrad7Args), C.c_void_p],
+    "sscg_conv_wgrad7_ws_bytes": [C.POINTER(Wgrad7Args)],
     "sscg_pack_nchw": [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
                        C.c_int32, C.c_int32, C.c_int32, C.c_void_p],
     "sscg_unpack_fold": [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,

@@ -146,6 +146,7 @@ extern "C" int sscg_fill_zero(void* ptr, int64_t bytes, void* stream) {
 
 #include "conv_igemm.cu"
 #include "conv_wgrad.cu"
+#include "conv_wgrad7.cu"
 #include "conv_nexp.cu"
 #include "elementwise.cu"
 #include "loss_kernels.cu"

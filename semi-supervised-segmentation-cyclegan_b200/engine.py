@@ -194,7 +194,7 @@ class NetPlan:
         self.drop_ctr = None      # optional device int64 counter mixed into dropout seeds (CUDA-graph replays)
         # scratch of the fixed-order split-K reduction of the weight gradients (all of a plan's wgrad launches are
         # ordered on one stream)
-        self.ws_wg = K.WsPool(device)
+        self.ws_wg, self.ws_wg7 = K.WsPool(device), K.WsPool(device)
         self.overlap_wgrad = False  # side-stream wgrad: measured no gain on B200 (power-capped, GEMMs contend); kept as an option
         self._scratch_ready = False
         self._args_cache = {}
@@ -563,8 +563,13 @@ class NetPlan:
                 if wt.wg_window:
                     table = G.taps_conv_fwd_window(s.k, 1, 0)
                     xview, xlo = c.act[i].window_view(wt.wg_Kc), None
-                wa = K.wgrad_args(dview, dlo, xview, xlo, table, wt.wg_Kc, wt.wg_rows, wt.dw, wt.wg_taps * wt.wg_rows,
-                                  split=sp, tag=3 if s.name.startswith("res") else 6, ws_pool=self.ws_wg)
+                if (wt.wg_window and wt.nexp and i in self.draw_nx and sp == 1 and wt.wg_rows == 64 and wt.wg_Kc == 448
+                        and self.draw_nx[i].C in (16, 32) and min(ho, wo) >= 8 and os.environ.get("SSCG_WGRAD7", "1") != "0"):
+                    # 7x7 head: horizontal taps as GEMM columns (csrc/conv_wgrad7.cu), same slab layout
+                    wa = K.wgrad7_args(c.act[i], self.draw_nx[i], wt.dw, tag=6, ws_pool=self.ws_wg7)
+                else:
+                    wa = K.wgrad_args(dview, dlo, xview, xlo, table, wt.wg_Kc, wt.wg_rows, wt.dw, wt.wg_taps * wt.wg_rows,
+                                      split=sp, tag=3 if s.name.startswith("res") else 6, ws_pool=self.ws_wg)
         # ---- 3. dgrad ------------------------------------------------------------------------
         da = None
         dkw = {}

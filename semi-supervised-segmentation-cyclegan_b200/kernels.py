@@ -225,7 +225,23 @@ def conv7_args(x_ptr, x_pitch, N, Hp, Wp, w, CoW, n_ntiles, ksteps, c_store, y_p
     return a
 
 
+def wgrad7_args(x: ActBuf, dy: ActBuf, dw, tag=6, ws_pool=None):
+    """7x7 head weight gradient (csrc/conv_wgrad7.cu): x = the head's 64-channel input with its halo of 3, dy = dRaw in
+    a zero-haloed (6) buffer of 16 / 32 channels, dw = the window-mode slab [7][64][448]."""
+    assert x.C == 64 and x.pad == 3 and dy.pad == 6 and dy.C in (16, 32) and not x.fp32 and not dy.fp32
+    assert (x.N, x.H, x.W) == (dy.N, dy.H, dy.W)
+    a = L.Wgrad7Args()
+    a.x, a.dy = _ptr(x.hi), _ptr(dy.hi)
+    a.N, a.H, a.W, a.Cy = x.N, x.H, x.W, dy.C
+    a.dw, a.tag = _ptr(dw), tag
+    _attach_ws(a, "ws", L.lib().sscg_conv_wgrad7_ws_bytes(C.byref(a)), ws_pool, "wgrad7")
+    return a
+
+
 def run_wgrad(a):
+    if isinstance(a, L.Wgrad7Args):
+        L.check(L.lib().sscg_conv_wgrad7(C.byref(a), _stream()), "sscg_conv_wgrad7")
+        return
     L.check(L.lib().sscg_conv_wgrad(C.byref(a), _stream()), "sscg_conv_wgrad")
 
 

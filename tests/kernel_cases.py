@@ -277,6 +277,34 @@ def case_wgrad_window(N=2, H=16, W=16, Cin=3, Cout=64, k=7, pad=3):
     return _result(grad, ref, 2e-4 * (N * H * W) ** 0.5)
 
 
+def case_wgrad7(N=2, H=16, W=40, Cout=21):
+    """7x7 head weight gradient with the horizontal taps as GEMM columns (conv_wgrad7.cu): x = 64-channel activation with
+    its reflect halo of 3, dY in a zero-haloed (6) buffer; accumulate semantics and bit reproducibility included."""
+    _setup()
+    Cin = 64
+    x = _bf(torch.randn(N, Cin, H, W, device=DEV))
+    dy = _bf(torch.randn(N, Cout, H, W, device=DEV))
+    xb = K.ActBuf(N, H, W, Cin, 3, DEV)
+    _fill_act(xb, x, L.PAD_REFLECT)
+    dyb = K.ActBuf(N, H, W, G.pad_out_channels(Cout), 6, DEV)
+    _fill_act(dyb, dy, L.PAD_ZERO)
+    dw = torch.zeros(7 * 64 * 448, device=DEV)
+    a = K.wgrad7_args(xb, dyb, dw)
+    K.run_wgrad(a)
+    torch.cuda.synchronize()
+    dw1 = dw.clone()
+    K.run_wgrad(a)
+    torch.cuda.synchronize()
+    assert torch.equal(dw, 2 * dw1), "conv_wgrad7 is not reproducible / does not accumulate"
+    dw.copy_(dw1)
+    grad = torch.zeros(Cout, Cin, 7, 7, device=DEV)
+    ua = K.wprep_args(grad, False, Cout, Cin, 7, 7, 1, 64, 64, 448, None)
+    K.run_wgrad_unpack(ua, dw, grad)
+    torch.cuda.synchronize()
+    ref = torch.nn.grad.conv2d_weight(F.pad(x, (3,) * 4, mode="reflect"), (Cout, Cin, 7, 7), dy, stride=1, padding=0)
+    return _result(grad, ref, 2e-4 * (N * H * W) ** 0.5)
+
+
 def case_convT_bwd(N=2, H=8, W=8, Cin=128, Cout=64):
     """ConvTranspose2d dgrad (strided gather over dY) and wgrad (roles swapped)."""
     _setup()
@@ -763,6 +791,10 @@ CASES = {
     "wgrad_window_c21": lambda: case_wgrad_window(Cin=21),            # Kc = 192 -> one 192-wide tile
     "wgrad_window_c64_wide": lambda: case_wgrad_window(Cin=64, Cout=21),   # head conv: Kc = 448 -> 448-wide tile
     "wgrad_window_c64_wide_big": lambda: case_wgrad_window(N=2, H=24, W=40, Cin=64, Cout=3),
+    "wgrad7_head_c21": lambda: case_wgrad7(),
+    "wgrad7_head_c3": lambda: case_wgrad7(N=3, H=24, W=72, Cout=3),            # Cy = 16 (SWIZZLE_32B segments)
+    "wgrad7_head_c19_wide": lambda: case_wgrad7(N=2, H=32, W=250, Cout=19),    # 4 column blocks, the last one partial
+    "wgrad7_head_c4_many_units": lambda: case_wgrad7(N=20, H=64, W=64, Cout=4),
     # elementwise
     "apply_fwd_relu_reflect": lambda: case_apply_fwd(),
     "apply_fwd_res": lambda: case_apply_fwd(act=L.ACT_NONE, residual=True),

@@ -38,7 +38,7 @@ def test_ctypes_structs_match_the_header_layout(tmp_path):
     if shutil.which("gcc") is None:
         pytest.skip("no C compiler")
     pairs = [("SscgTap", _lib.Tap), ("SscgView", _lib.View), ("SscgConvArgs", _lib.ConvArgs),
-             ("SscgWgradArgs", _lib.WgradArgs), ("SscgApplyArgs", _lib.ApplyArgs), ("SscgBwdArgs", _lib.BwdArgs),
+             ("SscgWgradArgs", _lib.WgradArgs), ("SscgWgrad7Args", _lib.Wgrad7Args), ("SscgApplyArgs", _lib.ApplyArgs), ("SscgBwdArgs", _lib.BwdArgs),
              ("SscgWprepArgs", _lib.WprepArgs), ("SscgWbatchEntry", _lib.WbatchEntry), ("SscgConv7Args", _lib.Conv7Args)]
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "sscg_b200.h"', "int main(void) {"]
     for cname, ct in pairs:
