@@ -12,6 +12,7 @@
 // Arithmetic, rounding points and the dropout hash are identical to norm_kernels.cuh (the parity-mode
 // and odd-shape paths keep using those kernels).  Included by elementwise.cu inside namespace sscg.
 #pragma once
+#include <type_traits>
 
 #ifndef SSCG_STR_UNIT_KB
 #define SSCG_STR_UNIT_KB 32
@@ -186,68 +187,81 @@ __global__ void __launch_bounds__(kStrThreads + 32, 1) in_apply_stream_kernel(co
         int hm1 = -1, hm2 = -1;
         if (reflect) mirror_pos(h, a.H, a.pad, hm1, hm2);
         const bool hmirror = (hm1 >= 0) || (hm2 >= 0);
-        __nv_bfloat16* drow = reinterpret_cast<__nv_bfloat16*>(a.dst) + ((long long)n * Hp + (h + a.pad)) * Wp * a.C + c0;
         const long long spix0 = ((long long)n * a.H + h) * a.W;
         mbar_wait(ring.full(k), ring.parity(k), 11);
         const uint32_t st = ring.stage(k);
-        for (int px0 = prow; px0 < g.seg_px; px0 += 2 * pstep) {
-            uint4 rv[2], rr[2];
+        // per-unit pointers (64-bit arithmetic once per unit); a pixel then costs one 32-bit multiply
+        const uint32_t pxb = (uint32_t)a.C * 2u;
+        const uint32_t s_v0 = st + (uint32_t)c0 * 2u;
+        uint8_t* d0 = reinterpret_cast<uint8_t*>(a.dst) + ((((long long)n * Hp + (h + a.pad)) * Wp + (w0 + a.pad)) * a.C + c0) * 2;
+        const uint32_t vec0 = (uint32_t)((spix0 + w0) * g.CH + chunk);
+        // does this unit hold a pixel that is mirrored into the halo?  (uniform per unit)
+        const bool border_unit = reflect && (hmirror || w0 <= a.pad || w0 + g.seg_px - 1 >= a.W - 1 - a.pad);
+        auto body = [&](auto border_tag) {
+            constexpr bool BORDER = decltype(border_tag)::value;
+            for (int px0 = prow; px0 < g.seg_px; px0 += 2 * pstep) {
+                uint4 rv[2], rr[2];
 #pragma unroll
-            for (int b = 0; b < 2; ++b) {
-                const int px = px0 + b * pstep;
-                if (px < g.seg_px) {
-                    const uint32_t so = st + (px * a.C + c0) * 2;
-                    rv[b] = lds128(so);
-                    if (has_res) rr[b] = lds128(so + g.ub);
+                for (int b = 0; b < 2; ++b) {
+                    const int px = px0 + b * pstep;
+                    if (px < g.seg_px) {
+                        const uint32_t so = s_v0 + (uint32_t)px * pxb;
+                        rv[b] = lds128(so);
+                        if (has_res) rr[b] = lds128(so + g.ub);
+                    }
+                }
+#pragma unroll
+                for (int b = 0; b < 2; ++b) {
+                    const int px = px0 + b * pstep;
+                    if (px >= g.seg_px) continue;
+                    float v[8];
+                    cvt8(rv[b], v);
+                    if (norm) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) v[q] = (v[q] - mean[q]) * rstd[q];
+                    }
+                    if (a.act == SSCG_ACT_RELU) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) v[q] = fmaxf(v[q], 0.f);
+                    } else if (a.act == SSCG_ACT_LRELU) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) v[q] = v[q] > 0.f ? v[q] : v[q] * a.slope;
+                    }
+                    if (seed != 0) {
+                        const uint32_t bits = drop_bits(seed, vec0 + (uint32_t)px * (uint32_t)g.CH);
+                        // keep -> x2, drop -> x0: bit q moved to the exponent position of 2.0f (0x40000000)
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) v[q] *= __uint_as_float((bits << (30 - q)) & 0x40000000u);
+                    }
+                    if (has_res) {
+                        float r8[8];
+                        cvt8(rr[b], r8);
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) v[q] += r8[q];
+                    }
+                    const uint4 out = pack8(v);
+                    *reinterpret_cast<uint4*>(d0 + (uint32_t)px * pxb) = out;
+                    if (BORDER) {
+                        // halo copies: only pixels within `pad` of a border have mirror positions
+                        const int w = w0 + px;
+                        if (hmirror || w <= a.pad || w >= a.W - 1 - a.pad) {
+                            int wm1, wm2;
+                            mirror_pos(w, a.W, a.pad, wm1, wm2);
+                            __nv_bfloat16* dbase = reinterpret_cast<__nv_bfloat16*>(a.dst) + (long long)n * Hp * Wp * a.C + c0;
+                            const int hh[3] = {h + a.pad, hm1, hm2}, ww[3] = {w + a.pad, wm1, wm2};
+#pragma unroll
+                            for (int x = 0; x < 3; ++x)
+#pragma unroll
+                                for (int y = 0; y < 3; ++y)
+                                    if (x + y > 0 && hh[x] >= 0 && ww[y] >= 0)
+                                        *reinterpret_cast<uint4*>(dbase + ((long long)hh[x] * Wp + ww[y]) * a.C) = out;
+                        }
+                    }
                 }
             }
-#pragma unroll
-            for (int b = 0; b < 2; ++b) {
-                const int px = px0 + b * pstep;
-                if (px >= g.seg_px) continue;
-                const int w = w0 + px;
-                float v[8];
-                cvt8(rv[b], v);
-                if (norm) {
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) v[q] = (v[q] - mean[q]) * rstd[q];
-                }
-                if (a.act == SSCG_ACT_RELU) {
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) v[q] = fmaxf(v[q], 0.f);
-                } else if (a.act == SSCG_ACT_LRELU) {
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) v[q] = v[q] > 0.f ? v[q] : v[q] * a.slope;
-                }
-                if (seed != 0) {
-                    const uint32_t bits = drop_bits(seed, (unsigned long long)(spix0 + w) * g.CH + chunk);
-                    // keep -> x2, drop -> x0: bit q moved to the exponent position of 2.0f (0x40000000)
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) v[q] *= __uint_as_float(((bits >> q) & 1u) << 30);
-                }
-                if (has_res) {
-                    float r8[8];
-                    cvt8(rr[b], r8);
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) v[q] += r8[q];
-                }
-                const uint4 out = pack8(v);
-                *reinterpret_cast<uint4*>(drow + (long long)(w + a.pad) * a.C) = out;
-                // halo copies: only pixels within `pad` of a border have mirror positions
-                if (reflect && (hmirror || w <= a.pad || w >= a.W - 1 - a.pad)) {
-                    int wm1, wm2;
-                    mirror_pos(w, a.W, a.pad, wm1, wm2);
-                    __nv_bfloat16* dbase = reinterpret_cast<__nv_bfloat16*>(a.dst) + (long long)n * Hp * Wp * a.C + c0;
-                    const int hh[3] = {h + a.pad, hm1, hm2}, ww[3] = {w + a.pad, wm1, wm2};
-#pragma unroll
-                    for (int x = 0; x < 3; ++x)
-#pragma unroll
-                        for (int y = 0; y < 3; ++y)
-                            if (x + y > 0 && hh[x] >= 0 && ww[y] >= 0)
-                                *reinterpret_cast<uint4*>(dbase + ((long long)hh[x] * Wp + ww[y]) * a.C) = out;
-                }
-            }
-        }
+        };
+        if (border_unit) body(std::true_type{});
+        else body(std::false_type{});
         ring.release(k);
     }
 }
@@ -365,100 +379,118 @@ __global__ void __launch_bounds__(kStrThreads + 32, 1) in_bwd_prep_stream_kernel
         const int col0 = w0 + a.pad - lpad;            // padded column held by staged pixel 0 of the gradient row
         mbar_wait(ring.full(k), ring.parity(k), 12);
         const uint32_t st = ring.stage(k);
+        // Everything that depends on the unit only is resolved here (64-bit pointer arithmetic once per unit); a pixel
+        // of the unit then costs one 32-bit multiply for its byte offset.  (The first version recomputed 64-bit element
+        // offsets per pixel: integer instructions were 60 % of the kernel, which is issue-bound.)
+        const uint32_t pxb = (uint32_t)a.C * 2u;                                   // bytes per pixel
+        const uint32_t s_g0 = st + (uint32_t)lpad * pxb + (uint32_t)c0 * 2u;      // gradient of pixel w0
+        const uint32_t s_k0 = st + (uint32_t)off_skip + (uint32_t)c0 * 2u;
+        const uint32_t s_z0 = st + (uint32_t)off_raw + (uint32_t)c0 * 2u;
+        uint8_t* gout0 = reinterpret_cast<uint8_t*>(a.g_out) + ((spix0 + w0) * a.C + c0) * 2;
+        uint8_t* dz0 = reinterpret_cast<uint8_t*>(a.dz) +
+                       (a.dz_pad > 0
+                            ? ((((long long)n * (a.H + 2 * a.dz_pad) + h + a.dz_pad) * (a.W + 2 * a.dz_pad) + w0 + a.dz_pad) * a.C + c0)
+                            : ((spix0 + w0) * a.C + c0)) * 2;
+        const uint32_t vec0 = (uint32_t)((spix0 + w0) * g.CH + chunk);              // dropout hash index of pixel w0 (mod 2^32)
         // rows next to the top / bottom border: the gradient of the mirrored halo row (same column) is fetched
         // from global memory up front, together with the shared-memory loads of the batch
         const int xf = hm1 >= 0 ? 1 : 2;
-        const __nv_bfloat16* mrow = reinterpret_cast<const __nv_bfloat16*>(a.dyp.ptr) + (long long)n * a.dyp.sN +
-                                    (long long)(hm1 >= 0 ? hm1 : (hm2 >= 0 ? hm2 : 0)) * a.dyp.sH + c0;
-        for (int px0 = prow; px0 < g.seg_px; px0 += 2 * pstep) {
-            uint4 rg[2], rs[2], rz[2], rm[2];
+        const uint8_t* mrow0 = reinterpret_cast<const uint8_t*>(
+            reinterpret_cast<const __nv_bfloat16*>(a.dyp.ptr) + (long long)n * a.dyp.sN +
+            (long long)(hm1 >= 0 ? hm1 : (hm2 >= 0 ? hm2 : 0)) * a.dyp.sH + (long long)(w0 + a.pad) * a.dyp.sW + c0);
+        // does this unit hold a pixel whose gradient receives mirrored halo contributions?  (uniform per unit)
+        const bool border_unit = hborder || (fold && (w0 <= a.pad || w0 + g.seg_px - 1 >= a.W - 1 - a.pad));
+        auto body = [&](auto border_tag) {
+            constexpr bool BORDER = decltype(border_tag)::value;
+            for (int px0 = prow; px0 < g.seg_px; px0 += 2 * pstep) {
+                uint4 rg[2], rs[2], rz[2], rm[2];
 #pragma unroll
-            for (int b = 0; b < 2; ++b) {
-                const int px = px0 + b * pstep;
-                if (px < g.seg_px) {
-                    const uint32_t so = st + (px * a.C + c0) * 2;
-                    if (hborder) rm[b] = *reinterpret_cast<const uint4*>(mrow + (long long)(w0 + px + a.pad) * a.dyp.sW);
-                    rg[b] = lds128(so + lpad * a.C * 2);
-                    if (has_skip) rs[b] = lds128(so + off_skip);
-                    if (need_raw) rz[b] = lds128(so + off_raw);
+                for (int b = 0; b < 2; ++b) {
+                    const int px = px0 + b * pstep;
+                    if (px < g.seg_px) {
+                        const uint32_t so = (uint32_t)px * pxb;
+                        if (BORDER && hborder) rm[b] = *reinterpret_cast<const uint4*>(mrow0 + so);
+                        rg[b] = lds128(s_g0 + so);
+                        if (has_skip) rs[b] = lds128(s_k0 + so);
+                        if (need_raw) rz[b] = lds128(s_z0 + so);
+                    }
                 }
-            }
 #pragma unroll
-            for (int b = 0; b < 2; ++b) {
-                const int px = px0 + b * pstep;
-                if (px >= g.seg_px) continue;
-                const int w = w0 + px;
-                const long long spix = spix0 + w;
-                const long long off = spix * a.C + c0;
-                float gv[8], z[8];
-                cvt8(rg[b], gv);
-                if (hborder || (fold && (w <= a.pad || w >= a.W - 1 - a.pad))) {
-                    int wm1, wm2;
-                    mirror_pos(w, a.W, a.pad, wm1, wm2);
-                    const int hh[3] = {h + a.pad, hm1, hm2}, ww[3] = {w + a.pad, wm1, wm2};
-                    // same accumulation order as fold_positions() in norm_kernels.cuh: (h, w) = base, m1, m2 nested
+                for (int b = 0; b < 2; ++b) {
+                    const int px = px0 + b * pstep;
+                    if (px >= g.seg_px) continue;
+                    const uint32_t so = (uint32_t)px * pxb;
+                    float gv[8], z[8];
+                    cvt8(rg[b], gv);
+                    if (BORDER) {
+                        const int w = w0 + px;
+                        if (hborder || (w <= a.pad || w >= a.W - 1 - a.pad)) {
+                            int wm1, wm2;
+                            mirror_pos(w, a.W, a.pad, wm1, wm2);
+                            const int hh[3] = {h + a.pad, hm1, hm2}, ww[3] = {w + a.pad, wm1, wm2};
+                            // same accumulation order as fold_positions() in norm_kernels.cuh: (h, w) = base, m1, m2 nested
 #pragma unroll
-                    for (int x = 0; x < 3; ++x)
+                            for (int x = 0; x < 3; ++x)
 #pragma unroll
-                        for (int y = 0; y < 3; ++y) {
-                            if (x + y == 0 || hh[x] < 0 || ww[y] < 0) continue;
-                            float t[8];
-                            if (x == 0)       // same row: the mirrored column was staged with the row
-                                cvt8(lds128(st + ((ww[y] - col0) * a.C + c0) * 2), t);
-                            else if (x == xf && y == 0)
-                                cvt8(rm[b], t);
-                            else
-                                load8(a.dyp.ptr, false,
-                                      (long long)n * a.dyp.sN + (long long)hh[x] * a.dyp.sH + (long long)ww[y] * a.dyp.sW + c0, t);
+                                for (int y = 0; y < 3; ++y) {
+                                    if (x + y == 0 || hh[x] < 0 || ww[y] < 0) continue;
+                                    float t[8];
+                                    if (x == 0)       // same row: the mirrored column was staged with the row
+                                        cvt8(lds128(st + ((ww[y] - col0) * a.C + c0) * 2), t);
+                                    else if (x == xf && y == 0)
+                                        cvt8(rm[b], t);
+                                    else
+                                        load8(a.dyp.ptr, false,
+                                              (long long)n * a.dyp.sN + (long long)hh[x] * a.dyp.sH + (long long)ww[y] * a.dyp.sW + c0, t);
 #pragma unroll
-                            for (int q = 0; q < 8; ++q) gv[q] += t[q];
+                                    for (int q = 0; q < 8; ++q) gv[q] += t[q];
+                                }
                         }
-                }
-                if (has_skip) {
-                    float t[8];
-                    cvt8(rs[b], t);
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) gv[q] += t[q];
-                }
-                if (has_gout)
-                    *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.g_out) + off) = pack8(gv);
-                if (seed != 0) {
-                    const uint32_t bits = drop_bits(seed, (unsigned long long)spix * g.CH + chunk);
-                    // keep -> x2, drop -> x0: bit q moved to the exponent position of 2.0f (0x40000000)
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) gv[q] *= __uint_as_float(((bits >> q) & 1u) << 30);
-                }
-                if (need_raw) {
-                    cvt8(rz[b], z);
-                    if (norm) {
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) z[q] = (z[q] - mean[q]) * rstd[q];
                     }
-                    if (act == SSCG_ACT_RELU) {
+                    if (has_skip) {
+                        float t[8];
+                        cvt8(rs[b], t);
 #pragma unroll
-                        for (int q = 0; q < 8; ++q) gv[q] = z[q] > 0.f ? gv[q] : 0.f;
-                    } else if (act == SSCG_ACT_LRELU) {
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) gv[q] = z[q] > 0.f ? gv[q] : gv[q] * a.slope;
-                    } else if (act == SSCG_ACT_TANH) {
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) gv[q] = gv[q] * (1.f - z[q] * z[q]);
+                        for (int q = 0; q < 8; ++q) gv[q] += t[q];
                     }
-                } else {
+                    if (has_gout) *reinterpret_cast<uint4*>(gout0 + so) = pack8(gv);
+                    if (seed != 0) {
+                        const uint32_t bits = drop_bits(seed, vec0 + (uint32_t)px * (uint32_t)g.CH);
+                        // keep -> x2, drop -> x0: bit q moved to the exponent position of 2.0f (0x40000000)
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) z[q] = 0.f;
-                }
-                const long long doff = a.dz_pad > 0
-                    ? ((((long long)n * (a.H + 2 * a.dz_pad) + h + a.dz_pad) * (a.W + 2 * a.dz_pad) + w + a.dz_pad) * a.C + c0)
-                    : off;
-                *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.dz) + doff) = pack8(gv);
+                        for (int q = 0; q < 8; ++q) gv[q] *= __uint_as_float((bits << (30 - q)) & 0x40000000u);
+                    }
+                    if (need_raw) {
+                        cvt8(rz[b], z);
+                        if (norm) {
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    acc1[q] += gv[q];
-                    acc2[q] += gv[q] * z[q];
+                            for (int q = 0; q < 8; ++q) z[q] = (z[q] - mean[q]) * rstd[q];
+                        }
+                        if (act == SSCG_ACT_RELU) {
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) gv[q] = z[q] > 0.f ? gv[q] : 0.f;
+                        } else if (act == SSCG_ACT_LRELU) {
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) gv[q] = z[q] > 0.f ? gv[q] : gv[q] * a.slope;
+                        } else if (act == SSCG_ACT_TANH) {
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) gv[q] = gv[q] * (1.f - z[q] * z[q]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) z[q] = 0.f;
+                    }
+                    *reinterpret_cast<uint4*>(dz0 + so) = pack8(gv);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        acc1[q] += gv[q];
+                        acc2[q] += gv[q] * z[q];
+                    }
                 }
             }
-        }
+        };
+        if (border_unit) body(std::true_type{});
+        else body(std::false_type{});
         ring.release(k);
     }
     if (a.bstats != nullptr) stream_flush_stats<kStrThreads>(s_red, acc1, acc2, a.bstats, cur_n, a.C, g.CH, chunk);
@@ -518,13 +550,16 @@ __global__ void __launch_bounds__(kStrThreads + 32, 1) in_bwd_apply_stream_kerne
             obase = reinterpret_cast<__nv_bfloat16*>(p.draw) +
                     (((long long)n * (a.H + 2 * a.draw_pad) + up.h + a.draw_pad) * (a.W + 2 * a.draw_pad) + up.w0 + a.draw_pad) * a.C + c0;
         }
+        const uint32_t pxb = (uint32_t)a.C * 2u;
+        const uint32_t s_z0 = st + (uint32_t)c0 * 2u;
+        uint8_t* ob = reinterpret_cast<uint8_t*>(obase);
         for (int px0 = prow; px0 < g.seg_px; px0 += 2 * pstep) {
             uint4 rz[2], rg[2];
 #pragma unroll
             for (int b = 0; b < 2; ++b) {
                 const int px = px0 + b * pstep;
                 if (px < g.seg_px) {
-                    const uint32_t so = st + (px * a.C + c0) * 2;
+                    const uint32_t so = s_z0 + (uint32_t)px * pxb;
                     rz[b] = lds128(so);
                     rg[b] = lds128(so + g.ub);
                 }
@@ -541,7 +576,7 @@ __global__ void __launch_bounds__(kStrThreads + 32, 1) in_bwd_apply_stream_kerne
                     const float zz = (z[q] - mean[q]) * rstd[q];
                     gv[q] = rstd[q] * (gv[q] - m1[q] - zz * m2[q]);
                 }
-                *reinterpret_cast<uint4*>(obase + (long long)px * a.C) = pack8(gv);
+                *reinterpret_cast<uint4*>(ob + (uint32_t)px * pxb) = pack8(gv);
             }
         }
         ring.release(k);
