@@ -31,6 +31,10 @@ struct NexpDev {
     int row_bytes;      // 32 * ksteps: operand rows are exactly as wide as the channels that enter the contraction,
                         // with the matching swizzle (128B / 64B / 32B) for TMA and the UMMA descriptors
     int stages;
+    int wstat;          // weight-stationary: the seven vertical-tap slabs of this CTA's N tile stay in shared memory for
+                        // the whole launch (they were 2/3 of the L2 -> SM traffic of a tile); needs gridDim.x % n_ntiles == 0
+    int halves;         // 1: the staging buffer holds all NT columns; 2 (CoW = 32 only): the shift-add runs in two passes
+                        // of 16 channels each through a half-size staging buffer (room for the resident weights)
     void* y;
     int y_fp32;
     long long y_sN, y_sH, y_sW;
@@ -72,16 +76,21 @@ conv_nexp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int a_bytes = kNxTileM * p.row_bytes;
     const int b_bytes = p.NT * p.row_bytes;
-    const int stage_bytes = ((a_bytes + 1023) & ~1023) + ((b_bytes + 1023) & ~1023);
-    const int b_off = (a_bytes + 1023) & ~1023;
-    float* S = reinterpret_cast<float*>(smem + p.stages * stage_bytes);
-    const int s_pitch = p.NT + 1;                       // odd: conflict-free row-wise stores and diagonal reads
+    const int a_al = (a_bytes + 1023) & ~1023, b_al = (b_bytes + 1023) & ~1023;
+    const int stage_bytes = p.wstat ? a_al : a_al + b_al;
+    const int b_off = a_al;
+    uint8_t* wres = smem + p.stages * stage_bytes;                       // resident weight slabs (wstat): 7 x b_al
+    float* S = reinterpret_cast<float*>(wres + (p.wstat ? 7 * b_al : 0));
+    const int ch_half = p.CoW / p.halves;                                // channels per shift-add pass
+    const int s_cols = p.halves == 1 ? p.NT : 7 * ch_half;               // staged columns per pass
+    const int s_pitch = s_cols + 1;                     // odd: conflict-free row-wise stores and diagonal reads
     uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(S) + ((kNxTileM * s_pitch * 4 + 15) & ~15));
     uint64_t* full_bar = bars;
     uint64_t* empty_bar = bars + 4;
     uint64_t* tmem_full_bar = bars + 8;        // [2]
     uint64_t* tmem_empty_bar = bars + 10;      // [2]
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 12);
+    uint64_t* w_bar = bars + 13;               // resident weights have landed
     float* bias_sm = reinterpret_cast<float*>(bars + 14);          // up to 64 output channels
 
     const int warp = threadIdx.x >> 5;
@@ -100,6 +109,7 @@ conv_nexp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             mbar_init(smem_u32(&tmem_full_bar[s]), 1);
             mbar_init(smem_u32(&tmem_empty_bar[s]), 128);
         }
+        mbar_init(smem_u32(w_bar), 1);
         fence_mbar_init();
     }
     if (warp == 1) {
@@ -120,7 +130,14 @@ conv_nexp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // ================================ TMA producer ==========================================
         if (lane == 0) {
             int stage = 0; uint32_t par = 0;
-            const uint32_t tx = (uint32_t)(a_bytes + b_bytes);
+            const uint32_t tx = (uint32_t)(p.wstat ? a_bytes : a_bytes + b_bytes);
+            if (p.wstat) {      // this CTA's N tile is blockIdx.x % n_ntiles for every tile it walks: load its slabs once
+                const int nt0 = blockIdx.x % p.n_ntiles;
+                const uint32_t wb = smem_u32(w_bar);
+                mbar_arrive_expect_tx(wb, (uint32_t)(7 * b_bytes));
+                for (int kh = 0; kh < 7; ++kh)
+                    tma_load_2d(smem_u32(wres + kh * b_al), &tmB, wb, 0, (kh * p.n_ntiles + nt0) * p.NT);
+            }
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
                 const int nt = tile % p.n_ntiles;
                 const int rest = tile / p.n_ntiles;
@@ -132,7 +149,7 @@ conv_nexp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     mbar_arrive_expect_tx(fb, tx);
                     uint8_t* st = smem + stage * stage_bytes;
                     tma_load_2d(smem_u32(st), &tmA, fb, 0, px0 + (kh - 3) * p.Wp);
-                    tma_load_2d(smem_u32(st + b_off), &tmB, fb, 0, (kh * p.n_ntiles + nt) * p.NT);
+                    if (!p.wstat) tma_load_2d(smem_u32(st + b_off), &tmB, fb, 0, (kh * p.n_ntiles + nt) * p.NT);
                     if (++stage == p.stages) { stage = 0; par ^= 1; }
                 }
             }
@@ -143,6 +160,10 @@ conv_nexp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const uint32_t idesc = make_idesc_bf16(kNxTileM, p.NT, 0, 0);
             int stage = 0; uint32_t par = 0;
             uint32_t it = 0;
+            if (p.wstat) {
+                mbar_wait(smem_u32(w_bar), 0, 25);
+                tc_fence_after();
+            }
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
                 const uint32_t acc = it & 1, acc_par = (it >> 1) & 1;
                 ++it;
@@ -155,7 +176,7 @@ conv_nexp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + stage * stage_bytes);
                     const uint64_t da = nexp_desc(sa, p.row_bytes);
-                    const uint64_t db = nexp_desc(sa + b_off, p.row_bytes);
+                    const uint64_t db = nexp_desc(p.wstat ? smem_u32(wres + kh * b_al) : sa + b_off, p.row_bytes);
                     for (int k = 0; k < p.ksteps; ++k) {
                         umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, accum);
                         accum = 1;
@@ -183,74 +204,95 @@ conv_nexp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             mbar_wait(smem_u32(&tmem_full_bar[acc]), acc_par, 24);
             tc_fence_after();
             const uint32_t t_acc = tmem_base + acc * acc_cols + (static_cast<uint32_t>(quad * 32) << 16);
-            // ---- accumulator -> staging buffer (row m), two 32-column TMEM loads in flight ------------------
-            for (int c0 = 0; c0 < p.NT; c0 += 64) {
-                uint32_t r0[32], r1[32];
-                const int w0 = p.NT - c0 >= 32 ? 32 : 16;
-                const int rem = p.NT - c0 - 32;
-                const int w1 = rem >= 32 ? 32 : (rem >= 16 ? 16 : 0);
-                if (w0 == 32) tmem_ld_32x32(t_acc + c0, r0);
-                else tmem_ld_32x16(t_acc + c0, r0);
-                if (w1 == 32) tmem_ld_32x32(t_acc + c0 + 32, r1);
-                else if (w1 == 16) tmem_ld_32x16(t_acc + c0 + 32, r1);
-                tmem_ld_wait();
-#pragma unroll
-                for (int q = 0; q < 32; ++q)
-                    if (q < w0) sts_f32(srow + (uint32_t)(c0 + q) * 4u, __uint_as_float(r0[q]));
-#pragma unroll
-                for (int q = 0; q < 32; ++q)
-                    if (q < w1) sts_f32(srow + (uint32_t)(c0 + 32 + q) * 4u, __uint_as_float(r1[q]));
-            }
-            tc_fence_before();
-            mbar_arrive(smem_u32(&tmem_empty_bar[acc]));          // accumulator drained
-            named_bar_sync(1, 128);                                // every row of S is written
-            // ---- shift-add over the seven horizontal taps + bias / activation + store ----------------
             const int o = o_first + t * kNxOut + m;               // flattened padded position of this thread's output
             const int orow = o / p.Wp, ocol = o - orow * p.Wp;
             const bool valid = (m < kNxOut) && orow >= 3 && orow < p.Hp - 3 && ocol >= 3 && ocol < p.Wp - 3;
-            if (valid) {
-                const long long yoff = (long long)n * p.y_sN + (long long)(orow - 3) * p.y_sH +
-                                       (long long)(ocol - 3) * p.y_sW + nt * p.y_c0_step;
-                for (int c0 = 0; c0 < p.c_store; c0 += 8) {
-                    // all 56 staged values first (the loads are ordered volatile asm: adding as they arrive would
-                    // expose one shared-memory latency per value), then the sums in tap order
-                    float tv[7][8];
+            const long long yoff = (long long)n * p.y_sN + (long long)(orow - 3) * p.y_sH +
+                                   (long long)(ocol - 3) * p.y_sW + nt * p.y_c0_step;
+            for (int hf = 0; hf < p.halves; ++hf) {
+                // ---- accumulator -> staging buffer (row m) --------------------------------------------------
+                if (p.halves == 1) {        // all NT columns, two 32-column TMEM loads in flight
+                    for (int c0 = 0; c0 < p.NT; c0 += 64) {
+                        uint32_t r0[32], r1[32];
+                        const int w0 = p.NT - c0 >= 32 ? 32 : 16;
+                        const int rem = p.NT - c0 - 32;
+                        const int w1 = rem >= 32 ? 32 : (rem >= 16 ? 16 : 0);
+                        if (w0 == 32) tmem_ld_32x32(t_acc + c0, r0);
+                        else tmem_ld_32x16(t_acc + c0, r0);
+                        if (w1 == 32) tmem_ld_32x32(t_acc + c0 + 32, r1);
+                        else if (w1 == 16) tmem_ld_32x16(t_acc + c0 + 32, r1);
+                        tmem_ld_wait();
 #pragma unroll
-                    for (int kw = 0; kw < 7; ++kw) {
-                        const uint32_t src = s_base + (uint32_t)((m + kw) * s_pitch + kw * p.CoW + c0) * 4u;
+                        for (int q = 0; q < 32; ++q)
+                            if (q < w0) sts_f32(srow + (uint32_t)(c0 + q) * 4u, __uint_as_float(r0[q]));
 #pragma unroll
-                        for (int q = 0; q < 8; ++q) tv[kw][q] = lds_f32(src + 4u * q);
+                        for (int q = 0; q < 32; ++q)
+                            if (q < w1) sts_f32(srow + (uint32_t)(c0 + 32 + q) * 4u, __uint_as_float(r1[q]));
                     }
-                    float v[8];
+                } else {                    // CoW = 32: the 16 channels of this pass from each of the seven column groups
+                    for (int kw = 0; kw < 7; kw += 2) {
+                        uint32_t r0[32], r1[32];
+                        tmem_ld_32x16(t_acc + kw * p.CoW + hf * ch_half, r0);
+                        if (kw + 1 < 7) tmem_ld_32x16(t_acc + (kw + 1) * p.CoW + hf * ch_half, r1);
+                        tmem_ld_wait();
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) v[q] = 0.f;
+                        for (int q = 0; q < 16; ++q) sts_f32(srow + (uint32_t)(kw * ch_half + q) * 4u, __uint_as_float(r0[q]));
+                        if (kw + 1 < 7) {
 #pragma unroll
-                    for (int kw = 0; kw < 7; ++kw)
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) v[q] += tv[kw][q];
-                    if (p.bias != nullptr) {
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) v[q] += lds_f32(bias_s + 4u * (uint32_t)(nt * p.y_c0_step + c0 + q));
-                    }
-                    if (p.act == SSCG_ACT_TANH) {
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) v[q] = tanhf(v[q]);
-                    } else if (p.act == SSCG_ACT_RELU) {
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) v[q] = fmaxf(v[q], 0.f);
-                    }
-                    if (p.y_fp32) {
-                        float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.y) + yoff + c0);
-                        dst[0] = make_float4(v[0], v[1], v[2], v[3]);
-                        dst[1] = make_float4(v[4], v[5], v[6], v[7]);
-                    } else {
-                        uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.y) + yoff + c0);
-                        *dst = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
-                                          pack_bf16x2(v[6], v[7]));
+                            for (int q = 0; q < 16; ++q)
+                                sts_f32(srow + (uint32_t)((kw + 1) * ch_half + q) * 4u, __uint_as_float(r1[q]));
+                        }
                     }
                 }
+                if (hf == p.halves - 1) {
+                    tc_fence_before();
+                    mbar_arrive(smem_u32(&tmem_empty_bar[acc]));      // accumulator drained
+                }
+                named_bar_sync(1, 128);                                // every row of S is written
+                // ---- shift-add over the seven horizontal taps + bias / activation + store ----------------
+                if (valid) {
+                    for (int c0 = 0; c0 < ch_half && hf * ch_half + c0 < p.c_store; c0 += 8) {
+                        // all 56 staged values first (the loads are ordered volatile asm: adding as they arrive would
+                        // expose one shared-memory latency per value), then the sums in tap order
+                        float tv[7][8];
+#pragma unroll
+                        for (int kw = 0; kw < 7; ++kw) {
+                            const uint32_t src = s_base + (uint32_t)((m + kw) * s_pitch + kw * ch_half + c0) * 4u;
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) tv[kw][q] = lds_f32(src + 4u * q);
+                        }
+                        float v[8];
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) v[q] = 0.f;
+#pragma unroll
+                        for (int kw = 0; kw < 7; ++kw)
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) v[q] += tv[kw][q];
+                        const int cch = hf * ch_half + c0;             // first output channel of this vector
+                        if (p.bias != nullptr) {
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) v[q] += lds_f32(bias_s + 4u * (uint32_t)(nt * p.y_c0_step + cch + q));
+                        }
+                        if (p.act == SSCG_ACT_TANH) {
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) v[q] = tanhf(v[q]);
+                        } else if (p.act == SSCG_ACT_RELU) {
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) v[q] = fmaxf(v[q], 0.f);
+                        }
+                        if (p.y_fp32) {
+                            float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.y) + yoff + cch);
+                            dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+                            dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+                        } else {
+                            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.y) + yoff + cch);
+                            *dst = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                                              pack_bf16x2(v[6], v[7]));
+                        }
+                    }
+                }
+                named_bar_sync(2, 128);                                // S may be overwritten by the next pass / tile
             }
-            named_bar_sync(2, 128);                                // S may be overwritten by the next tile
         }
         tc_fence_before();
     }
@@ -309,13 +351,41 @@ extern "C" int sscg_conv7_nexp(const SscgConv7Args* a, void* stream_) {
     d.bias = a->bias; d.act = a->act;
     d.row_bytes = 32 * a->ksteps;
     const int a_bytes = kNxTileM * d.row_bytes, b_bytes = d.NT * d.row_bytes;
-    const int stage_bytes = ((a_bytes + 1023) & ~1023) + ((b_bytes + 1023) & ~1023);
-    const int s_bytes = ((kNxTileM * (d.NT + 1) * 4 + 15) & ~15) + 512;
-    int stages = (225 * 1024 - 1024 - s_bytes) / stage_bytes;
+    const int a_al = (a_bytes + 1023) & ~1023, b_al = (b_bytes + 1023) & ~1023;
+    int sms = 148, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int grid = sms < d.total_tiles ? sms : d.total_tiles;
+    const int budget = 225 * 1024 - 1024;
+    auto s_bytes_of = [&](int halves) {
+        const int cols = halves == 1 ? d.NT : 7 * (a->CoW / halves);
+        return ((kNxTileM * (cols + 1) * 4 + 15) & ~15) + 512;
+    };
+    // Weight-stationary when the seven slabs of an N tile, the staging buffer and >= 2 operand stages fit: the slabs
+    // were re-streamed for every 122-pixel tile (100 of 156 KB per tile for the head's data gradient).  CoW = 32 may
+    // halve the staging buffer (two shift-add passes of 16 channels) to make room.
+    d.wstat = 0;
+    d.halves = 1;
+    if (!getenv("SSCG_NEXP_NO_WSTAT")) {
+        grid -= grid % d.n_ntiles;                       // every CTA must keep one N tile
+        for (int halves = 1; halves <= 2 && grid >= d.n_ntiles; ++halves) {
+            if (halves == 2 && (a->CoW != 32 || a->c_store % 8)) break;
+            if (7 * b_al + s_bytes_of(halves) + 2 * a_al <= budget) {
+                d.wstat = 1;
+                d.halves = halves;
+                break;
+            }
+        }
+        if (!d.wstat) grid = sms < d.total_tiles ? sms : d.total_tiles;
+    }
+    const int stage_bytes = d.wstat ? a_al : a_al + b_al;
+    const int s_bytes = s_bytes_of(d.halves);
+    const int fixed = s_bytes + (d.wstat ? 7 * b_al : 0);
+    int stages = (budget - fixed) / stage_bytes;
     if (stages > 4) stages = 4;
     if (stages < 2) return set_error("conv7_nexp: tile does not fit shared memory (NT=%d)", d.NT);
     d.stages = stages;
-    const int smem = 1024 + stages * stage_bytes + s_bytes;
+    const int smem = 1024 + stages * stage_bytes + fixed;
 
     CUtensorMap tmA, tmB;
     const long long rows = (long long)a->N * a->Hp * a->Wp;
@@ -329,10 +399,6 @@ extern "C" int sscg_conv7_nexp(const SscgConv7Args* a, void* stream_) {
         if (e != cudaSuccess) return set_error("conv7_nexp: cudaFuncSetAttribute(smem=%d): %s", smem, cudaGetErrorString(e));
         max_smem_set = smem;
     }
-    int sms = 148, dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    int grid = sms < d.total_tiles ? sms : d.total_tiles;
     {
         LaunchScope ls(a->tag, stream);
         conv_nexp_kernel<<<grid, 192, smem, stream>>>(tmA, tmB, d);

@@ -62,6 +62,10 @@ def key_conv7(a):
 
 
 def key_wgrad(a):
+    from sscg_b200 import _lib as L
+    if isinstance(a, L.Wgrad7Args):
+        flops = 2.0 * a.N * a.H * a.W * 49 * 64 * a.Cy
+        return "wgrad7 %dx%d Cy=%d (7x7 head, taps as columns)" % (a.H, a.W, a.Cy), flops, a.N * a.H * a.W * (64 + a.Cy) * 2
     px = a.dy.N * a.dy.H * a.dy.W
     flops = 2.0 * px * a.n_taps * a.Kc * a.Co_pad
     key = "wgrad %dx%d K=%d taps=%d M=%d BN=%d ks=%d" % (a.dy.H, a.dy.W, a.Kc, a.n_taps, a.Co_pad, a.BN, a.ksplit)
