@@ -15,7 +15,11 @@
 // runs through a 128 x (N + 1) fp32 staging buffer in shared memory (conflict-free for both the row-wise store
 // and the diagonal read).
 //
-// Roles as in conv_igemm.cu: warp 0 TMA producer, warp 1 MMA issuer (two TMEM accumulators), warps 2..5 epilogue.
+// Roles: warp 0 TMA producer, warp 1 MMA issuer (two TMEM accumulators), and TWO epilogue groups of four warps
+// (warps 2..5 and 6..9), one per accumulator, each with a staging buffer of its own: the epilogue of a tile — 115 KB
+// out of TMEM (64 B/clk), 230 KB through shared memory for the shift-add — takes ~5 k cycles against a 0.8 k main loop,
+// so a single group set the pace of the whole kernel (366 us for the head's data gradient at 16 x 256 x 256); two
+// groups overlap the TMEM phase of one tile with the shared-memory phase of the other.
 // Replaces (reference): the 7x7 nn.Conv2d head of arch/generators.py:84-85,89-90 (forward and cuDNN dgrad).
 #include "sscg_common.cuh"
 
@@ -33,8 +37,10 @@ struct NexpDev {
     int stages;
     int wstat;          // weight-stationary: the seven vertical-tap slabs of this CTA's N tile stay in shared memory for
                         // the whole launch (they were 2/3 of the L2 -> SM traffic of a tile); needs gridDim.x % n_ntiles == 0
-    int halves;         // 1: the staging buffer holds all NT columns; 2 (CoW = 32 only): the shift-add runs in two passes
-                        // of 16 channels each through a half-size staging buffer (room for the resident weights)
+    int halves;         // 1: the staging buffer holds all NT columns; p > 1: the shift-add runs in p passes of CoW / p
+                        // channels (a multiple of 8) through a buffer of 7 * CoW / p columns (room for resident weights)
+    int groups;         // epilogue groups (2 when two staging buffers fit, else 1)
+    int s_bytes;        // bytes of one staging buffer
     void* y;
     int y_fp32;
     long long y_sN, y_sH, y_sW;
@@ -69,7 +75,7 @@ __device__ __forceinline__ float lds_f32(uint32_t saddr) {
     return v;
 }
 
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 conv_nexp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ NexpDev p) {
     extern __shared__ uint8_t smem_raw[];
@@ -84,7 +90,7 @@ conv_nexp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int ch_half = p.CoW / p.halves;                                // channels per shift-add pass
     const int s_cols = p.halves == 1 ? p.NT : 7 * ch_half;               // staged columns per pass
     const int s_pitch = s_cols + 1;                     // odd: conflict-free row-wise stores and diagonal reads
-    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(S) + ((kNxTileM * s_pitch * 4 + 15) & ~15));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(S) + p.groups * p.s_bytes);
     uint64_t* full_bar = bars;
     uint64_t* empty_bar = bars + 4;
     uint64_t* tmem_full_bar = bars + 8;        // [2]
@@ -116,7 +122,7 @@ conv_nexp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tmem_alloc(smem_u32(tmem_ptr_smem), tmem_cols);
         tmem_relinquish();
     }
-    if (warp >= 2 && p.bias != nullptr) {
+    if (warp >= 2 && warp < 6 && p.bias != nullptr) {
         const int e = threadIdx.x - 64;
         if (e < p.n_ntiles * p.CoW && e < 64) bias_sm[e] = p.bias[e];
     }
@@ -191,9 +197,12 @@ conv_nexp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // ================================ epilogue ==============================================
         const int quad = warp & 3;
         const int m = quad * 32 + lane;            // TMEM lane = tile pixel
-        const uint32_t s_base = smem_u32(S);
+        const int grp = (warp - 2) >> 2;           // epilogue group 0 (warps 2..5) / 1 (warps 6..9)
+        if (grp >= p.groups) goto done;            // a single staging buffer fits: the second group idles
+        const uint32_t s_base = smem_u32(S) + (uint32_t)(grp * p.s_bytes);
         const uint32_t bias_s = smem_u32(bias_sm);
         const uint32_t srow = s_base + (uint32_t)(m * s_pitch) * 4u;
+        const uint32_t bar_a = 1 + 2 * grp, bar_b = 2 + 2 * grp;     // named barriers of this group
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
             const int nt = tile % p.n_ntiles;
@@ -201,6 +210,7 @@ conv_nexp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int t = rest % p.tiles_per_sample, n = rest / p.tiles_per_sample;
             const uint32_t acc = it & 1, acc_par = (it >> 1) & 1;
             ++it;
+            if (p.groups == 2 && (int)acc != grp) continue;         // with two groups, group g drains accumulator g
             mbar_wait(smem_u32(&tmem_full_bar[acc]), acc_par, 24);
             tc_fence_after();
             const uint32_t t_acc = tmem_base + acc * acc_cols + (static_cast<uint32_t>(quad * 32) << 16);
@@ -229,26 +239,23 @@ conv_nexp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         for (int q = 0; q < 32; ++q)
                             if (q < w1) sts_f32(srow + (uint32_t)(c0 + 32 + q) * 4u, __uint_as_float(r1[q]));
                     }
-                } else {                    // CoW = 32: the 16 channels of this pass from each of the seven column groups
-                    for (int kw = 0; kw < 7; kw += 2) {
-                        uint32_t r0[32], r1[32];
-                        tmem_ld_32x16(t_acc + kw * p.CoW + hf * ch_half, r0);
-                        if (kw + 1 < 7) tmem_ld_32x16(t_acc + (kw + 1) * p.CoW + hf * ch_half, r1);
+                } else {                    // the ch_half channels of this pass from each of the seven column groups
+                    for (int kw = 0; kw < 7; ++kw) {
+                        uint32_t r0[32];
+                        const uint32_t col = (uint32_t)(kw * p.CoW + hf * ch_half);
+                        if (ch_half == 16) tmem_ld_32x16(t_acc + col, r0);
+                        else tmem_ld_32x8(t_acc + col, r0);
                         tmem_ld_wait();
 #pragma unroll
-                        for (int q = 0; q < 16; ++q) sts_f32(srow + (uint32_t)(kw * ch_half + q) * 4u, __uint_as_float(r0[q]));
-                        if (kw + 1 < 7) {
-#pragma unroll
-                            for (int q = 0; q < 16; ++q)
-                                sts_f32(srow + (uint32_t)((kw + 1) * ch_half + q) * 4u, __uint_as_float(r1[q]));
-                        }
+                        for (int q = 0; q < 16; ++q)
+                            if (q < ch_half) sts_f32(srow + (uint32_t)(kw * ch_half + q) * 4u, __uint_as_float(r0[q]));
                     }
                 }
                 if (hf == p.halves - 1) {
                     tc_fence_before();
                     mbar_arrive(smem_u32(&tmem_empty_bar[acc]));      // accumulator drained
                 }
-                named_bar_sync(1, 128);                                // every row of S is written
+                named_bar_sync(bar_a, 128);                            // every row of S is written
                 // ---- shift-add over the seven horizontal taps + bias / activation + store ----------------
                 if (valid) {
                     for (int c0 = 0; c0 < ch_half && hf * ch_half + c0 < p.c_store; c0 += 8) {
@@ -291,11 +298,12 @@ conv_nexp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         }
                     }
                 }
-                named_bar_sync(2, 128);                                // S may be overwritten by the next pass / tile
+                named_bar_sync(bar_b, 128);                            // S may be overwritten by the next pass / tile
             }
         }
         tc_fence_before();
     }
+done:
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
@@ -359,33 +367,47 @@ extern "C" int sscg_conv7_nexp(const SscgConv7Args* a, void* stream_) {
     const int budget = 225 * 1024 - 1024;
     auto s_bytes_of = [&](int halves) {
         const int cols = halves == 1 ? d.NT : 7 * (a->CoW / halves);
-        return ((kNxTileM * (cols + 1) * 4 + 15) & ~15) + 512;
+        return ((kNxTileM * (cols + 1) * 4 + 15) & ~15) + 16;
     };
-    // Weight-stationary when the seven slabs of an N tile, the staging buffer and >= 2 operand stages fit: the slabs
-    // were re-streamed for every 122-pixel tile (100 of 156 KB per tile for the head's data gradient).  CoW = 32 may
-    // halve the staging buffer (two shift-add passes of 16 channels) to make room.
-    d.wstat = 0;
-    d.halves = 1;
-    if (!getenv("SSCG_NEXP_NO_WSTAT")) {
-        grid -= grid % d.n_ntiles;                       // every CTA must keep one N tile
-        for (int halves = 1; halves <= 2 && grid >= d.n_ntiles; ++halves) {
-            if (halves == 2 && (a->CoW != 32 || a->c_store % 8)) break;
-            if (7 * b_al + s_bytes_of(halves) + 2 * a_al <= budget) {
-                d.wstat = 1;
-                d.halves = halves;
-                break;
-            }
-        }
-        if (!d.wstat) grid = sms < d.total_tiles ? sms : d.total_tiles;
-    }
+    // Shared-memory plan, in order of preference:
+    //   two epilogue groups (one staging buffer each) + weight-stationary slabs (the seven slabs of this CTA's N tile stay
+    //   resident: they were re-streamed for every 122-pixel tile, 100 of 156 KB for the head's data gradient) + >= 3 stages,
+    //   then two groups without resident weights, then one group.  The staging buffer shrinks by running the shift-add
+    //   in `halves` passes of CoW / halves channels (a multiple of 8).
+    const int pass_opts[4] = {1, 2, 3, 4};
+    d.wstat = 0; d.halves = 1; d.groups = 1;
+    bool planned = false;
+    const int grid_w = grid - grid % d.n_ntiles;                 // every CTA keeps one N tile
+    const bool allow_wstat = !getenv("SSCG_NEXP_NO_WSTAT") && grid_w >= d.n_ntiles;
+    const int max_groups = getenv("SSCG_NEXP_ONE_GROUP") ? 1 : 2;
+    // (measured at 16 x 256 x 256: more than two passes cost more than a second epilogue group or resident weights
+    //  gain — 437 us with 2 groups / 4 passes against 366 us with 1 group / 2 passes for K = 32 x 7, N = 224 x 2; two
+    //  groups + resident weights + 2 passes: 369 -> 318 us for K = 16 x 7)
+    for (int max_pass = 2; max_pass <= 4 && !planned; max_pass += 2)
+        for (int ws = allow_wstat ? 1 : 0; ws >= 0 && !planned; --ws)
+            for (int groups = max_groups; groups >= 1 && !planned; --groups)
+                for (int pi = 0; pi < 4 && !planned; ++pi) {
+                    const int h = pass_opts[pi];
+                    if (h > max_pass || a->CoW % h || (a->CoW / h) % 8 || (h > 1 && (a->CoW / h) > 16)) continue;
+                    const int need = groups * s_bytes_of(h) + (ws ? 7 * b_al + 3 * a_al : 2 * (a_al + b_al));
+                    if (need <= budget) {
+                        d.groups = groups; d.wstat = ws; d.halves = h;
+                        planned = true;
+                    }
+                }
+    if (!planned) return set_error("conv7_nexp: tile does not fit shared memory (NT=%d)", d.NT);
+    if (d.wstat) grid = grid_w;
+    d.s_bytes = s_bytes_of(d.halves);
     const int stage_bytes = d.wstat ? a_al : a_al + b_al;
-    const int s_bytes = s_bytes_of(d.halves);
-    const int fixed = s_bytes + (d.wstat ? 7 * b_al : 0);
+    const int fixed = d.groups * d.s_bytes + (d.wstat ? 7 * b_al : 0) + 512;
     int stages = (budget - fixed) / stage_bytes;
     if (stages > 4) stages = 4;
     if (stages < 2) return set_error("conv7_nexp: tile does not fit shared memory (NT=%d)", d.NT);
     d.stages = stages;
     const int smem = 1024 + stages * stage_bytes + fixed;
+    if (getenv("SSCG_DEBUG"))
+        fprintf(stderr, "[sscg] conv7_nexp NT=%d K=%dx7: groups %d, wstat %d, passes %d, stages %d, smem %d\n", d.NT,
+                16 * a->ksteps, d.groups, d.wstat, d.halves, stages, smem);
 
     CUtensorMap tmA, tmB;
     const long long rows = (long long)a->N * a->Hp * a->Wp;
@@ -401,7 +423,7 @@ extern "C" int sscg_conv7_nexp(const SscgConv7Args* a, void* stream_) {
     }
     {
         LaunchScope ls(a->tag, stream);
-        conv_nexp_kernel<<<grid, 192, smem, stream>>>(tmA, tmB, d);
+        conv_nexp_kernel<<<grid, 320, smem, stream>>>(tmA, tmB, d);
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_error("conv7_nexp launch: %s", cudaGetErrorString(e));

@@ -168,6 +168,13 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[32])
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+        : "r"(taddr)
+        : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ----------------------------------------------------------------------------------------------
@@ -222,8 +229,8 @@ __device__ __forceinline__ void det_red_add(unsigned long long* acc, float p) {
     const float r = p - hi_f * 0.00390625f;                         // exact: the bits of p below 2^-8 (|r| <= 2^-9)
     const long long hi = __float2ll_rn(hi_f);
     const long long lo = __float2ll_rn(r * 72057594037927936.f);    // 2^56
-    atomicAdd(acc, static_cast<unsigned long long>(hi));            // result unused: compiles to RED
-    atomicAdd(acc + 1, static_cast<unsigned long long>(lo));
+    asm volatile("red.global.add.u64 [%0], %1;" ::"l"(acc), "l"(static_cast<unsigned long long>(hi)) : "memory");
+    asm volatile("red.global.add.u64 [%0], %1;" ::"l"(acc + 1), "l"(static_cast<unsigned long long>(lo)) : "memory");
 }
 // hi * 2^-8 + lo * 2^-56 as a float: each word as sign and magnitude, the magnitude from its 32-bit halves with fp32
 // FMAs (no fp64, no 64-bit conversions).  A pure function of the integers, hence as reproducible as they are;
