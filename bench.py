@@ -383,12 +383,15 @@ def run_ours(args):
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms.item())
     # ---- end-to-end region: pinned host buffers, H2D + D2H inside ---------------------------
+    # every step: H2D of its pinned batch + graph replay + D2H of the nine losses; the H2D of step i + 1 is issued on a
+    # copy stream while step i runs (GraphedStep.step_host(prefetch=...)), as an input pipeline would
+    pf = (lambda i: {"prefetch": host_batches[(i + 1) % 3]}) if use_graph else (lambda i: {})
     for i in range(2):
-        step_host(*host_batches[i % 3])
+        step_host(*host_batches[i % 3], **pf(i))
     barrier()
     t0 = time.perf_counter()
     for i in range(args.steps):
-        last = step_host(*host_batches[i % 3])
+        last = step_host(*host_batches[i % 3], **pf(i))
     torch.cuda.synchronize()
     t_e2e = torch.tensor([time.perf_counter() - t0], device=dev)
     if world > 1:

@@ -180,6 +180,31 @@ def test_graphed_step_matches_eager_losses():
         assert outs[0][k] == outs[1][k], (k, outs[0][k], outs[1][k])
 
 
+def test_step_host_prefetch_overlaps_without_changing_results():
+    """GraphedStep.step_host(prefetch=next batch): the next batch's host-to-device copy runs on a copy stream during the
+    step; results are bit-identical to the plain path."""
+    import sscg_b200  # noqa: F401
+    from sscg_b200.step import GraphedStep, SemiSupCycleGAN
+    g = torch.Generator().manual_seed(4)
+    batches = [((torch.rand(2, 3, 32, 32, generator=g) * 2 - 1).pin_memory(),
+                torch.randint(0, 5, (2, 1, 32, 32), generator=g).pin_memory(),
+                (torch.rand(2, 3, 32, 32, generator=g) * 2 - 1).pin_memory()) for _ in range(3)]
+    runs = []
+    for prefetch in (False, True):
+        torch.manual_seed(0)
+        np.random.seed(0)
+        m = SemiSupCycleGAN(n_classes=5, ngf=4, ndf=4, variant="classic", use_dropout=True, device="cuda:0", precision="bf16",
+                            graph_safe=True)
+        gs = GraphedStep(m, *[t.cuda() for t in batches[0]], warmup=2)
+        out = []
+        for i in range(5):
+            kw = {"prefetch": batches[(i + 1) % 3]} if prefetch else {}
+            out.append(gs.step_host(*batches[i % 3], **kw))
+        runs.append(out)
+    assert runs[0] == runs[1]
+    assert len({round(o["lab_loss_CE"], 6) for o in runs[0]}) > 1      # different batches were really consumed
+
+
 def test_bf16_step_is_reproducible_with_dropout():
     """Two runs of three bf16 training steps (dropout on) from the same seeds: identical losses, gradients, weights."""
     import sscg_b200  # noqa: F401
