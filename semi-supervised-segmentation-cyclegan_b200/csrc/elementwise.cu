@@ -464,6 +464,8 @@ static bool stream_geom(int N, int H, int W, int C, int ntens, int threads, Stre
     if (!stream_enabled() || C % 8 || N < 1 || H < 1 || W < 1) return false;
     const int CH = C / 8;
     if (CH > 64 || threads % CH) return false;
+    // the stage descriptors carry 32-bit byte offsets into the (haloed) tensors
+    if ((long long)N * (H + 16) * (W + 16) * C * 2 >= (1LL << 32)) return false;
     const long long row = (long long)W * C * 2;
     long long unit_max = budget / (3 * ntens);       // at least three stages in the ring
     if (unit_max > kStrUnitMax) unit_max = kStrUnitMax;
@@ -492,12 +494,12 @@ static bool stream_geom(int N, int H, int W, int C, int ntens, int threads, Stre
 template <typename KernelT>
 static int stream_prepare(KernelT kernel, int& done) {
     if (done) return 0;
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStrSmemBudget + 512);
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStrSmemBudget + 1024);
     if (e != cudaSuccess) return set_error("norm stream: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     done = 1;
     return 0;
 }
-static inline size_t stream_smem(const StreamGeom& g) { return (size_t)g.nst * g.stage_bytes + 512; }
+static inline size_t stream_smem(const StreamGeom& g) { return (size_t)g.nst * g.stage_bytes + 1024; }   // alignment + barriers + stage descriptors
 static inline int stream_grid(const StreamGeom& g) { return g.total < ew_sm_count() ? g.total : ew_sm_count(); }
 
 }  // namespace sscg
@@ -586,13 +588,26 @@ extern "C" int sscg_in_apply(const SscgApplyArgs* a, void* stream) {
         const bool res_ok = a->res.ptr == nullptr || a->res.sW == a->C;
         if (plain && halo_ok && res_ok && a->pad < a->H && a->pad < a->W &&
             stream_geom(a->N, a->H, a->W, a->C, a->res.ptr ? 2 : 1, kStrThreadsLight, sd.g)) {
-            static int prepared = 0;
-            if (int rc = stream_prepare(in_apply_stream_kernel<kStrThreadsLight>, prepared)) return rc;
+            static int prepared[4] = {0, 0, 0, 0};
+            if (int rc = stream_prepare(in_apply_stream_kernel<kStrThreadsLight, 0>, prepared[0])) return rc;
+            if (int rc = stream_prepare(in_apply_stream_kernel<kStrThreadsLight, 1>, prepared[1])) return rc;
+            if (int rc = stream_prepare(in_apply_stream_kernel<kStrThreadsLight, 2>, prepared[2])) return rc;
+            if (int rc = stream_prepare(in_apply_stream_kernel<kStrThreadsLight, 3>, prepared[3])) return rc;
             sd.a = *a;
+            int spec = 0;
+            if (a->stats) {
+                if (a->act == SSCG_ACT_RELU && !a->res.ptr) spec = a->drop_seed != 0 ? 2 : 1;
+                else if (a->act == SSCG_ACT_NONE && a->res.ptr && a->drop_seed == 0) spec = 3;
+            }
             {
                 LaunchScope ls_(7, static_cast<cudaStream_t>(stream));
-                in_apply_stream_kernel<kStrThreadsLight><<<stream_grid(sd.g), kStrThreadsLight + 32, stream_smem(sd.g),
-                                         static_cast<cudaStream_t>(stream)>>>(sd);
+                const dim3 grid(stream_grid(sd.g)), block(kStrThreadsLight + 32);
+                const size_t smem = stream_smem(sd.g);
+                cudaStream_t st = static_cast<cudaStream_t>(stream);
+                if (spec == 1) in_apply_stream_kernel<kStrThreadsLight, 1><<<grid, block, smem, st>>>(sd);
+                else if (spec == 2) in_apply_stream_kernel<kStrThreadsLight, 2><<<grid, block, smem, st>>>(sd);
+                else if (spec == 3) in_apply_stream_kernel<kStrThreadsLight, 3><<<grid, block, smem, st>>>(sd);
+                else in_apply_stream_kernel<kStrThreadsLight, 0><<<grid, block, smem, st>>>(sd);
             }
             SSCG_CHECK_LAUNCH("in_apply_stream");
             return 0;

@@ -430,8 +430,9 @@ def case_apply_bwd(N=2, H=12, W=12, Cc=64, pad=1, act=L.ACT_RELU, skip=True, dz_
 
 def case_stream_ab(N=3, H=16, W=64, Cc=256, pad=1, act=L.ACT_RELU, skip=True, residual=True, drop=True):
     """Bulk-pipelined InstanceNorm kernels (norm_stream.cuh) against the register-batched ones on the same
-    inputs, all-bf16 layouts, dropout on: forward output, dZ, folded total gradient and dRaw must be
-    bit-identical (same arithmetic); the plane sums may differ in summation order only."""
+    inputs, all-bf16 layouts, dropout on: forward output, dZ and the folded total gradient must be bit-identical
+    (same arithmetic; ReLU and the dropout scale on packed bf16 pairs are exact), dRaw within one bf16 ulp (FMA form);
+    the plane sums may differ in summation order only."""
     _setup()
     lib = L.lib()
     raw = (torch.randn(N, H, W, Cc, device=DEV) * 2 + 0.5).to(torch.bfloat16)
@@ -493,9 +494,16 @@ def case_stream_ab(N=3, H=16, W=64, Cc=256, pad=1, act=L.ACT_RELU, skip=True, re
         torch.cuda.synchronize()
         res.append((dz.clone(), gout.clone(), bst_own, draw.clone()))
     lib.sscg_set_stream_norm(2)
-    for i in (0, 1, 3):
+    for i in (0, 1):
         worst = max(worst, float((res[0][i].float() - res[1][i].float()).abs().max()))
     assert float(res[1][3].float().abs().max()) > 0
+    # dRaw: the pipelined kernel evaluates rstd * (dZ - m1 - zhat * m2) as two FMAs with per-channel constants
+    # (norm_stream.cuh) — same value up to fp32 rounding, i.e. at most one bf16 ulp apart after the final rounding,
+    # and on a small fraction of the elements only
+    d0, d1 = res[0][3].float(), res[1][3].float()
+    ulp = d0.abs().clamp_min(1e-3) * 2.0 ** -7
+    assert bool(((d0 - d1).abs() <= ulp).all()), float(((d0 - d1).abs() / ulp).max())
+    assert float(((d0 - d1) != 0).float().mean()) < 0.02
     # plane sums: same terms, different summation order
     b0, b1 = K.stats_decode(res[0][2]), K.stats_decode(res[1][2])
     rel = float((b1 - b0).abs().max() / b0.abs().max().clamp_min(1e-6))

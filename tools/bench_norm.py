@@ -60,5 +60,5 @@ if __name__ == "__main__":
     for cfg in [(16, 64, 64, 256, 1, False, False), (16, 64, 64, 256, 1, False, False, 0), (16, 64, 64, 256, 0, False, False, 0),
                 (16, 64, 64, 256, 0, False, False, 0, 0), (16, 64, 64, 256, 0, False, False, 0, 0, False),
                 (16, 64, 64, 256, 1, True, True), (16, 64, 64, 256, 1, True, True, 0, 0), (16, 256, 256, 64, 3, False, False),
-                (16, 128, 128, 128, 0, False, False)]:
+                (16, 128, 128, 128, 0, False, False)][slice(*[int(x) for x in os.environ.get("BN_CFG", "0:99").split(":")])]:
         print(json.dumps(run(*cfg)), flush=True)

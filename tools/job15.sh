@@ -1,0 +1,6 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_kernels_gpu.py tests/test_modules_gpu.py -m gpu -q -x > gpurun_out/pytest_k.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/pytest_k.log
+for v in old new mr h512_mr; do
+  SSCG_LIB=$PWD/variants/lib_$v.so timeout 300 python tools/bench_norm.py > gpurun_out/bn_$v.log 2>&1; echo "== $v rc=$?"; cat gpurun_out/bn_$v.log | cut -c1-250
+done
