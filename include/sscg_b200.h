@@ -147,6 +147,8 @@ typedef struct SscgWgradArgs {
 
 int sscg_conv_wgrad(const SscgWgradArgs* a, void* stream);
 int64_t sscg_conv_wgrad_ws_bytes(const SscgWgradArgs* a);
+/* CTAs of this tile shape that share an SM (1 or 2): size ksplit so that the grid fills ctas_per_sm * #SM slots. */
+int32_t sscg_conv_wgrad_ctas_per_sm(int32_t BN, int32_t split);
 
 /* sscg_conv_wgrad7 — weight gradient of the 7x7 stride-1 generator HEAD (64 -> <= 32 channels, arch/generators.py:84-85,
  * 89-90) with the seven horizontal taps as GEMM columns (csrc/conv_wgrad7.cu): replaces the window-mode launch of

@@ -39,7 +39,18 @@ struct WgradCfg {
     static constexpr int kBAtoms = BN / 64;
     static constexpr int kStageBytes = kPlanes * (kAAtoms + kBAtoms) * kWgAtomBytes;
     static constexpr int kMaxStages = (200 * 1024) / kStageBytes;
-    static constexpr int kStages = kMaxStages > 6 ? 6 : kMaxStages;
+    // Two CTAs per SM wherever each still gets a ring of >= 2 stages: a CTA owns ONE output tile, so its epilogue
+    // (TMEM -> partial tile, arrival wait, slice reduction: ~7 us of an 80 us launch) cannot overlap its own MMAs —
+    // the co-resident CTAs' MMAs fill that time (80.5 -> 75.4 us on the residual-block shape, 300 -> 162 us on the
+    // 64-channel stem, whose CTAs are short).
+    // measured on the step's shapes: three CTAs pay off for the 64-wide tile only (138 vs 162 us on the stem); with
+    // BN = 128 the third CTA leaves 2-stage rings and a 49-way split (84 vs 50 us), four are worse everywhere
+    static constexpr int stages_for(int n) { return ((228 * 1024) / n - 1024 - 1280) / kStageBytes; }
+    static constexpr int kCtasPerSm = BN > 256 ? 1
+                                      : (BN == 64 && stages_for(3) >= 2) ? 3
+                                      : (stages_for(2) >= 2) ? 2 : 1;
+    static constexpr int kStages = kCtasPerSm == 1 ? (kMaxStages > 6 ? 6 : kMaxStages)
+                                                   : (stages_for(kCtasPerSm) > 6 ? 6 : stages_for(kCtasPerSm));
     static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + 256;
     static constexpr int kTmemCols = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : BN <= 256 ? 256 : 512;
     static constexpr int kN0 = BN > 256 ? 256 : BN;     // one tcgen05.mma covers at most N = 256 columns
@@ -51,7 +62,7 @@ struct WgradCfg {
 constexpr int kWgCtrs = 1024;           // arrival counters at the head of the workspace
 
 template <int BN, int SPLIT>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(192, (WgradCfg<BN, SPLIT>::kCtasPerSm))
 conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ CUtensorMap tmDyLo,
                   const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmXLo,
                   const __grid_constant__ WgradDev p) {
@@ -304,6 +315,20 @@ static int launch_wgrad(const CUtensorMap& tmDy, const CUtensorMap& tmDyLo, cons
 }  // namespace sscg
 
 using namespace sscg;
+
+extern "C" int32_t sscg_conv_wgrad_ctas_per_sm(int32_t BN, int32_t split) {
+#define SSCG_WG(BN_) \
+    case BN_: return split == 3 ? WgradCfg<BN_, 3>::kCtasPerSm : WgradCfg<BN_, 1>::kCtasPerSm;
+    switch (BN) {
+        SSCG_WG(64)
+        SSCG_WG(128)
+        SSCG_WG(256)
+        case 192: return WgradCfg<192, 1>::kCtasPerSm;
+        case 448: return WgradCfg<448, 1>::kCtasPerSm;
+        default: return 1;
+    }
+#undef SSCG_WG
+}
 
 extern "C" int64_t sscg_conv_wgrad_ws_bytes(const SscgWgradArgs* a) {
     if (a->BN <= 0 || a->Kc % a->BN) return -1;

@@ -4,6 +4,7 @@ torch is used here only for device memory (tensor.data_ptr()) and the current st
 arithmetic kernel lives in libsscg_b200.so.
 """
 import ctypes as C
+import os
 
 import torch
 
@@ -182,7 +183,7 @@ def wgrad_args(dyview, dy_lo, xview, x_lo, table: TapTable, Kc, Co_pad, dw, w_ro
     if ksplit is None:
         blocks = dyview.N * ((dyview.H + a.TH - 1) // a.TH) * ((dyview.W + a.TW - 1) // a.TW)
         ctas = len(table.taps) * ((Co_pad + 127) // 128) * (Kc // BN)
-        ksplit = pick_ksplit(ctas, blocks)
+        ksplit = pick_ksplit(ctas, blocks, sms=148 * L.lib().sscg_conv_wgrad_ctas_per_sm(BN, split))
     a.ksplit = ksplit
     a.tag = tag
     _attach_ws(a, "ws", L.lib().sscg_conv_wgrad_ws_bytes(C.byref(a)), ws_pool, "wgrad")
