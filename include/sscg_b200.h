@@ -113,6 +113,11 @@ typedef struct SscgConvArgs {
      * positions with col >= Wo or row >= Ho are computed but not stored.  66 x 66 outputs then take 36 tiles per
      * sample instead of 45 (8 x 16 tiles).  0 = off.  Requires stride 1, one phase, TH = 1, TW = 128. */
     int32_t flat_pitch, flat_hw, flat_n;
+    /* Pixel-row mode for stems (0 = off, else bytes per pixel of x: 16, i.e. x.C == 8): `taps` holds ONE entry per
+     * filter row (as in the row-window layout, Kc == 64 = 8 pixels x 8 channels, weights [kh][Co_pad][(kw, c)]), x is
+     * the PLAIN haloed view; the kernel loads one (128 + 8)-pixel row box per filter row and addresses it as overlapping
+     * K-major rows.  Needs stride 1, one phase, TH = 1, TW = 128, BN = 64, split == 1. */
+    int32_t rw_pitch;
 } SscgConvArgs;
 
 int sscg_conv_igemm(const SscgConvArgs* a, void* stream);

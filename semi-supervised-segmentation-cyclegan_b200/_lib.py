@@ -45,6 +45,7 @@ class ConvArgs(C.Structure):
         ("TH", C.c_int32), ("TW", C.c_int32), ("BN", C.c_int32), ("tag", C.c_int32),
         ("shift_kw", C.c_int32), ("shift_brow_step", C.c_int32), ("shift_base_mode", C.c_int32),
         ("flat_pitch", C.c_int32), ("flat_hw", C.c_int32), ("flat_n", C.c_int32),
+        ("rw_pitch", C.c_int32),
     ]
 
 

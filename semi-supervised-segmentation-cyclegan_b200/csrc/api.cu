@@ -28,7 +28,8 @@ PFN_encodeTiled get_encode_tiled() {
     return fn;
 }
 
-int encode_view_4d(CUtensorMap* tm, const SscgView& v, const void* ptr, const uint32_t box[4], const uint32_t es[4]) {
+int encode_view_4d(CUtensorMap* tm, const SscgView& v, const void* ptr, const uint32_t box[4], const uint32_t es[4],
+                   int swizzle_bytes) {
     PFN_encodeTiled enc = get_encode_tiled();
     if (!enc) return 1;
     cuuint64_t dims[4] = {(cuuint64_t)v.C, (cuuint64_t)v.W, (cuuint64_t)v.H, (cuuint64_t)v.N};
@@ -38,8 +39,12 @@ int encode_view_4d(CUtensorMap* tm, const SscgView& v, const void* ptr, const ui
     if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (strides[0] & 15) || (strides[1] & 15) || (strides[2] & 15))
         return set_error("tensor map: view pointer/strides must be 16-byte aligned (ptr=%p sW=%lld sH=%lld sN=%lld)", ptr,
                          (long long)v.sW, (long long)v.sH, (long long)v.sN);
+    const CUtensorMapSwizzle sw = swizzle_bytes == 0    ? CU_TENSOR_MAP_SWIZZLE_NONE
+                                  : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                  : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                        : CU_TENSOR_MAP_SWIZZLE_128B;
     CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, b, s,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS)
         return set_error("cuTensorMapEncodeTiled(4d) failed: %d dims=(%llu,%llu,%llu,%llu) strides=(%llu,%llu,%llu) "

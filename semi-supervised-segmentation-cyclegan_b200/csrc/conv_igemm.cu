@@ -60,18 +60,26 @@ constexpr int kABytes = kTileM * 128;   // 128 pixels x 64 bf16
 // SKW > 0 selects the row-shift mode (1 x 128 pixel tiles, stride 1): one TMA box of 128 + SKW - 1
 // pixels per filter row and channel block is shared by the SKW horizontal taps, which read it through
 // descriptors whose start address is shifted by one 128-byte pixel row per tap.
-template <int BN, int SPLIT, int SKW = 0>
+//
+// RW > 0 selects the PIXEL-ROW mode for stems (few input channels, 1 x 128 pixel tiles, stride 1; RW = bytes per pixel of
+// the input buffer): the K axis of one filter row is the run of kw consecutive pixels x Cp channels, which IS the image
+// row.  One TMA box of 128 + 8 pixels lands densely (16 bytes per pixel for Cp = 8) and the A descriptor addresses it
+// as overlapping rows: M row m starts at pixel m (16-byte row pitch inside a core matrix, SBO = 128 B per 8 pixels),
+// the next 16-byte K chunk is the next pixel (LBO = 16 B).  The earlier row-WINDOW tensor map made TMA expand every
+// pixel's 128-byte window (8x the unique bytes: 1.5 GB of L2 -> SM traffic for a 17 MB input, the kernel's bound).
+template <int BN, int SPLIT, int SKW = 0, int RW = 0>
 struct IgemmCfg {
     static constexpr int kPlanes = (SPLIT == 3) ? 2 : 1;
     static constexpr int kBBytes = BN * 128;
-    static constexpr int kARows = SKW > 0 ? kTileM + SKW - 1 : kTileM;
-    static constexpr int kAStage = SKW > 0 ? ((kARows * 128 + 1023) / 1024) * 1024 : kABytes;
+    static constexpr int kARows = RW > 0 ? kTileM + 8 : (SKW > 0 ? kTileM + SKW - 1 : kTileM);
+    static constexpr int kARowBytes = RW > 0 ? RW : 128;
+    static constexpr int kAStage = (SKW > 0 || RW > 0) ? ((kARows * kARowBytes + 1023) / 1024) * 1024 : kABytes;
     static constexpr int kBStage = SKW > 0 ? SKW * kBBytes : kBBytes;
     static constexpr int kStageBytes = kPlanes * (kAStage + kBStage);
-    static constexpr int kTxBytes = kPlanes * (kARows * 128 + kBStage);
+    static constexpr int kTxBytes = kPlanes * (kARows * kARowBytes + kBStage);
     // wide tiles: as deep a ring as fits one CTA per SM; narrow tiles: 4 stages so that 2+ CTAs fit
     // SSCG_IGEMM_BN128_KB: ring budget of the BN = 128 tile (200: one CTA per SM with 6 stages; 100: 3 stages, two CTAs)
-    static constexpr int kMaxStages = ((BN > 128 || SKW > 0) ? 200 * 1024
+    static constexpr int kMaxStages = (RW > 0 ? 100 * 1024 : (BN > 128 || SKW > 0) ? 200 * 1024
                                        : (BN == 128 ? SSCG_IGEMM_BN128_KB * 1024 : 100 * 1024)) / kStageBytes;
     static constexpr int kStages = kMaxStages > 6 ? 6 : (kMaxStages < 2 ? 2 : kMaxStages);
     static constexpr int kAccCols = BN < 32 ? 32 : BN;          // columns per accumulator
@@ -120,15 +128,16 @@ __device__ __forceinline__ TileInfo decode_tile(const ConvDev& p, int tile, int 
     return t;
 }
 
-template <int BN, int SPLIT, int SKW>
+template <int BN, int SPLIT, int SKW, int RW>
 __global__ void __launch_bounds__(192, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
                   const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo,
                   const __grid_constant__ ConvDev p) {
-    using Cfg = IgemmCfg<BN, SPLIT, SKW>;
+    using Cfg = IgemmCfg<BN, SPLIT, SKW, RW>;
     constexpr int kStages = Cfg::kStages;
     constexpr int kPlanes = Cfg::kPlanes;
     static_assert(SKW == 0 || SPLIT == 1, "row-shift mode is bf16-mode only");
+    static_assert(RW == 0 || (RW == 16 && SPLIT == 1 && SKW == 0), "pixel-row mode: 16 bytes per pixel, bf16 mode");
 
     // ---- shared memory carve-up ----------------------------------------------------------------
     extern __shared__ uint8_t smem_raw[];
@@ -179,7 +188,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     const SscgTap tap = p.taps[t.tap0 + tp];
                     mbar_wait(smem_u32(&empty_bar[stage]), par ^ 1, 1);
                     const uint32_t fb = smem_u32(&full_bar[stage]);
-                    const bool half_tile = (SPLIT == 1 && SKW == 0) && t.bn != BN;
+                    const bool half_tile = (SPLIT == 1 && SKW == 0 && RW == 0) && t.bn != BN;
                     mbar_arrive_expect_tx(fb, half_tile ? Cfg::kTxBytes - Cfg::kBBytes / 2 : Cfg::kTxBytes);
                     uint8_t* st = smem + stage * Cfg::kStageBytes;
                     int cw = t.j0 * p.stride + tap.dw + p.org_w;
@@ -197,6 +206,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         for (int j = 0; j < (SKW > 0 ? SKW : 1); ++j)
                             tma_load_2d(smem_u32(st + Cfg::kAStage + j * Cfg::kBBytes), &tmB, fb, cb * 64,
                                         (tap.brow + j * p.shift_brow_step) * p.Co_pad + t.n0);
+                    } else if (RW > 0) {
+                        tma_load_2d(smem_u32(st + Cfg::kAStage), &tmB, fb, cb * 64, brow);
                     } else {
                         // half tiles read their 128 weight rows through the half-height box (passed in the tmBlo slot)
                         tma_load_2d(smem_u32(st + kPlanes * kABytes), half_tile ? &tmBlo : &tmB, fb, cb * 64, brow);
@@ -249,8 +260,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         if (++stage == kStages) { stage = 0; par ^= 1; }
                         continue;
                     }
-                    const uint32_t sb = sa + kPlanes * kABytes;
-                    const uint64_t da = make_smem_desc_sw128(sa, 0, 1024);
+                    const uint32_t sb = sa + (RW > 0 ? Cfg::kAStage : kPlanes * kABytes);
+                    // pixel-row mode: dense 16-byte pixels, no swizzle; K chunk = next pixel (LBO 16), 8 rows = 8 pixels (SBO 128)
+                    const uint64_t da = RW > 0 ? make_smem_desc(sa, 16, 128, 0) : make_smem_desc_sw128(sa, 0, 1024);
                     const uint64_t db = make_smem_desc_sw128(sb, 0, 1024);
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {   // 4 x (K = 16) per 64-wide K block; +32 B per step
@@ -423,22 +435,22 @@ static int sm_count() {
     return n;
 }
 
-template <int BN, int SPLIT, int SKW = 0>
+template <int BN, int SPLIT, int SKW = 0, int RW = 0>
 static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmAlo, const CUtensorMap& tmB,
                         const CUtensorMap& tmBlo, const ConvDev& d, cudaStream_t stream, int tag) {
-    using Cfg = IgemmCfg<BN, SPLIT, SKW>;
+    using Cfg = IgemmCfg<BN, SPLIT, SKW, RW>;
     static int occ = 0;
     if (occ == 0) {
-        cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel<BN, SPLIT, SKW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel<BN, SPLIT, SKW, RW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              Cfg::kSmemBytes);
         if (e != cudaSuccess) return set_error("conv_igemm: cudaFuncSetAttribute(smem=%d): %s", Cfg::kSmemBytes,
                                                cudaGetErrorString(e));
         // without an explicit carve-out the driver sizes shared memory for ONE block of this kernel and the
         // occupancy query answers 1 even when two blocks would fit the 228 KB
-        cudaFuncSetAttribute(conv_igemm_kernel<BN, SPLIT, SKW>, cudaFuncAttributePreferredSharedMemoryCarveout,
+        cudaFuncSetAttribute(conv_igemm_kernel<BN, SPLIT, SKW, RW>, cudaFuncAttributePreferredSharedMemoryCarveout,
                              cudaSharedmemCarveoutMaxShared);
         int o = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, conv_igemm_kernel<BN, SPLIT, SKW>, 192, Cfg::kSmemBytes);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, conv_igemm_kernel<BN, SPLIT, SKW, RW>, 192, Cfg::kSmemBytes);
         const int o_api = o;
         const int e_api = (int)e;
         if (e != cudaSuccess || o < 1) o = 1;
@@ -463,7 +475,7 @@ static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmAlo, const 
     if (grid > d.total_tiles) grid = d.total_tiles;
     {
         LaunchScope ls(tag, stream);
-        conv_igemm_kernel<BN, SPLIT, SKW><<<grid, 192, Cfg::kSmemBytes, stream>>>(tmA, tmAlo, tmB, tmBlo, d);
+        conv_igemm_kernel<BN, SPLIT, SKW, RW><<<grid, 192, Cfg::kSmemBytes, stream>>>(tmA, tmAlo, tmB, tmBlo, d);
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_error("conv_igemm<%d,%d> launch: %s", BN, SPLIT, cudaGetErrorString(e));
@@ -492,11 +504,17 @@ extern "C" int sscg_conv_igemm(const SscgConvArgs* a, void* stream_) {
             (a->BN != 16 && a->BN != 32 && a->BN != 64))
             return set_error("conv_igemm: row-shift mode needs kw=7, bf16, stride 1, 1x128 tiles, BN 16/32/64");
     }
+    const int rw = a->rw_pitch;
+    if (rw != 0) {
+        if (rw != 16 || a->x.C != 8 || a->x.sW != 8 || a->split != 1 || a->stride != 1 || a->n_phases != 1 || a->TH != 1 ||
+            a->TW != 128 || a->BN != 64 || a->Kc != 64 || skw != 0 || a->flat_pitch > 0)
+            return set_error("conv_igemm: pixel-row mode needs an 8-channel dense view, bf16, stride 1, 1x128 tiles, BN 64, Kc 64");
+    }
     CUtensorMap tmA, tmAlo, tmB, tmBlo;
-    const uint32_t boxA[4] = {64u, (uint32_t)(skw ? a->TW + skw - 1 : a->TW * a->stride),
+    const uint32_t boxA[4] = {rw ? 8u : 64u, (uint32_t)(rw ? a->TW + 8 : (skw ? a->TW + skw - 1 : a->TW * a->stride)),
                               (uint32_t)(a->TH * a->stride), 1u};
     const uint32_t esA[4] = {1u, (uint32_t)a->stride, (uint32_t)a->stride, 1u};
-    if (int rc = encode_view_4d(&tmA, a->x, a->x.ptr, boxA, esA)) return rc;
+    if (int rc = encode_view_4d(&tmA, a->x, a->x.ptr, boxA, esA, rw ? 0 : 128)) return rc;
     tmAlo = tmA;
     if (a->split == 3)
         if (int rc = encode_view_4d(&tmAlo, a->x, a->x_lo, boxA, esA)) return rc;
@@ -548,6 +566,7 @@ extern "C" int sscg_conv_igemm(const SscgConvArgs* a, void* stream_) {
     d.y_sN = a->y_sN; d.y_sH = a->y_sH; d.y_sW = a->y_sW; d.y_oh = a->y_oh; d.y_ow = a->y_ow;
     d.bias = a->bias; d.act = a->act; d.slope = a->slope; d.stats = reinterpret_cast<unsigned long long*>(a->stats);
     if (d.total_tiles <= 0) return 0;
+    if (rw == 16) return launch_igemm<64, 1, 0, 16>(tmA, tmAlo, tmB, tmBlo, d, stream, a->tag);
     if (skw == 7) {
         if (a->BN == 16) return launch_igemm<16, 1, 7>(tmA, tmAlo, tmB, tmBlo, d, stream, a->tag);
         if (a->BN == 64) return launch_igemm<64, 1, 7>(tmA, tmAlo, tmB, tmBlo, d, stream, a->tag);

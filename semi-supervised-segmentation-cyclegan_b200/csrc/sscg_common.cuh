@@ -27,7 +27,9 @@ struct LaunchScope {
 };
 
 // 4-D map over an NHWC bf16 view: dims (C, W, H, N), 128B swizzle, zero fill outside the view.
-int encode_view_4d(CUtensorMap* tm, const SscgView& v, const void* ptr, const uint32_t box[4], const uint32_t es[4]);
+// swizzle_bytes: 128 (default), 64, 32 or 0 (dense rows)
+int encode_view_4d(CUtensorMap* tm, const SscgView& v, const void* ptr, const uint32_t box[4], const uint32_t es[4],
+                   int swizzle_bytes = 128);
 // 2-D map over a row-major bf16 matrix [rows][cols]
 int encode_2d(CUtensorMap* tm, const void* ptr, int cols, int rows, int box_cols, int box_rows);
 

@@ -198,6 +198,19 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr, uint32_
     d |= static_cast<uint64_t>(2) << 61;   // SWIZZLE_128B
     return d;
 }
+// General form.  layout: 0 = no swizzle ("interleave": 8-row x 16-byte core matrices; LBO = distance between core matrices
+// along K, SBO = distance between 8-row groups along M/N), 2 / 4 / 6 = SWIZZLE_128B / 64B / 32B.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout,
+                                                   uint32_t base_offset = 0) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>(base_offset & 7u) << 49;
+    d |= static_cast<uint64_t>((saddr >> 4) & 0x3fff);
+    d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3fff) << 16;
+    d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3fff) << 32;
+    d |= static_cast<uint64_t>(1) << 46;   // version
+    d |= static_cast<uint64_t>(layout & 7u) << 61;
+    return d;
+}
 // Instruction descriptor (32-bit) for kind::f16 with bf16 A/B and fp32 D:
 //   [4,6) D fmt: 1 = f32   [7,10) A fmt: 1 = bf16   [10,13) B fmt: 1 = bf16
 //   [15] A major (0 = K, 1 = MN)   [16] B major   [17,23) N >> 3   [24,29) M >> 4

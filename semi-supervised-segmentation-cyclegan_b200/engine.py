@@ -316,6 +316,10 @@ class NetPlan:
             return G.taps_convT_fwd(s.k, s.k, s.stride, s.pad)
         return G.taps_conv_fwd(s.k, s.k, s.stride, 0 if s.in_halo else -s.pad)
 
+    def _pixel_row_ok(self, s: StageSpec, wt: StageWeights, buf: K.ActBuf):
+        return (s.kind == "window" and self.split == 1 and s.stride == 1 and buf.C == 8 and wt.Kc == 64 and wt.Co_pad == 64
+                and s.k <= 8 and os.environ.get("SSCG_PIXEL_ROW", "1") != "0")
+
     def _x_view(self, s: StageSpec, wt: StageWeights, buf: K.ActBuf):
         """(view, lo pointer) of the stage input as the forward GEMM reads it."""
         if s.kind == "window":
@@ -353,11 +357,16 @@ class NetPlan:
                 table = self._fwd_table(s)
                 if not self._direct(s):
                     dst = c.raw[i]
+                    kw = {}
+                    if self._pixel_row_ok(s, wt, c.act[i]):
+                        # stem over an 8-channel buffer: the image row itself is the K-major operand (conv_igemm.cu, RW)
+                        view, lo = c.act[i].view(interior=False), None
+                        kw = dict(rw_pitch=16, BN=64)
                     ca = K.conv_args(view, lo, table, wt.Kc, wt.w_fwd, wt.w_fwd_lo, wt.ntaps_fwd * wt.Co_pad, wt.Co_pad,
                                      dst.hi.data_ptr(), dst.fp32, (dst.sN, dst.sH, dst.sW), (0, 0), ho, wo,
                                      bias=None if s.norm else wt.bias_pad,
                                      stats=c.stats[c.stat_off[i]:] if s.norm else None, split=sp,
-                                     tag=1 if s.name.startswith("res") else 4)
+                                     tag=1 if s.name.startswith("res") else 4, **kw)
                     nxt = c.act[i + 1]
                     aa = L.ApplyArgs()
                     aa.raw, aa.raw_fp32 = dst.hi.data_ptr(), 1 if dst.fp32 else 0

@@ -127,7 +127,7 @@ def fill_taps(dst_taps, table: TapTable):
 
 def conv_args(xview, x_lo, table: TapTable, Kc, w, w_lo, w_rows, Co_pad, y_ptr, y_fp32, y_strides, y_off, Ho, Wo,
               bias=None, act=L.ACT_NONE, slope=0.2, stats=None, BN=None, tile=None, split=1, tag=4,
-              shift_kw=0, shift_brow_step=1, shift_base_mode=2, flat=None, ws_pool=None):
+              shift_kw=0, shift_brow_step=1, shift_base_mode=2, flat=None, ws_pool=None, rw_pitch=0):
     a = L.ConvArgs()
     a.x = xview
     a.x_lo = x_lo
@@ -157,6 +157,9 @@ def conv_args(xview, x_lo, table: TapTable, Kc, w, w_lo, w_rows, Co_pad, y_ptr, 
         a.TH, a.TW = 1, 128
     if flat is not None:          # (row pitch, positions per sample, samples) of the flattened zero-haloed input
         a.flat_pitch, a.flat_hw, a.flat_n = flat
+        a.TH, a.TW = 1, 128
+    a.rw_pitch = rw_pitch
+    if rw_pitch:
         a.TH, a.TW = 1, 128
     return a
 

@@ -120,8 +120,9 @@ def case_conv_fwd(N=2, H=16, W=16, Cin=64, Cout=64, k=3, stride=1, pad=1, reflec
     return err, scale, tol
 
 
-def case_conv_window(N=2, H=16, W=16, Cin=3, Cout=64, k=7, stride=1, pad=3, reflect=True):
-    """Row-window mode (small Cin): stem 7x7 / PatchGAN 4x4 s2 first layer."""
+def case_conv_window(N=2, H=16, W=16, Cin=3, Cout=64, k=7, stride=1, pad=3, reflect=True, pixel_row=False):
+    """Row-window mode (small Cin): stem 7x7 / PatchGAN 4x4 s2 first layer.  pixel_row: the same layer through the
+    pixel-row mode (plain 8-channel view, overlapping K-major rows, conv_igemm.cu RW)."""
     _setup()
     x = _bf(torch.randn(N, Cin, H, W, device=DEV))
     w = _bf(torch.randn(Cout, Cin, k, k, device=DEV) * 0.05)
@@ -136,8 +137,9 @@ def case_conv_window(N=2, H=16, W=16, Cin=3, Cout=64, k=7, stride=1, pad=3, refl
     Ho, Wo = G.conv_out(H, k, stride, pad), G.conv_out(W, k, stride, pad)
     y = torch.zeros(N, Ho, Wo, Co_pad, device=DEV)
     table = G.taps_conv_fwd_window(k, stride, 0)
-    a = K.conv_args(buf.window_view(kwpad), None, table, kwpad, slab, None, k * Co_pad, Co_pad, y.data_ptr(), True,
-                    (Ho * Wo * Co_pad, Wo * Co_pad, Co_pad), (0, 0), Ho, Wo)
+    kw = dict(rw_pitch=16, BN=64) if pixel_row else {}
+    a = K.conv_args(buf.view(interior=False) if pixel_row else buf.window_view(kwpad), None, table, kwpad, slab, None,
+                    k * Co_pad, Co_pad, y.data_ptr(), True, (Ho * Wo * Co_pad, Wo * Co_pad, Co_pad), (0, 0), Ho, Wo, **kw)
     K.run_conv(a)
     torch.cuda.synchronize()
     xp = F.pad(x, (pad,) * 4, mode="reflect" if reflect else "constant")
@@ -768,6 +770,9 @@ CASES = {
     "win_stem_c3": lambda: case_conv_window(),
     "win_stem_c21": lambda: case_conv_window(Cin=21),
     "win_stem_c1": lambda: case_conv_window(Cin=1),
+    "pixrow_stem_c3": lambda: case_conv_window(pixel_row=True),
+    "pixrow_stem_c1_wide": lambda: case_conv_window(N=3, H=20, W=200, Cin=1, pixel_row=True),     # ragged second tile
+    "pixrow_stem_c3_256": lambda: case_conv_window(N=2, H=32, W=256, Cin=3, pixel_row=True),
     "win_d0_c3": lambda: case_conv_window(Cin=3, k=4, stride=2, pad=1, reflect=False),
     "win_d0_c21": lambda: case_conv_window(Cin=21, k=4, stride=2, pad=1, reflect=False),
     # transposed conv
