@@ -371,6 +371,10 @@ int sscg_confusion(const int64_t* label_true, const int64_t* label_pred, int64_t
 /* utility */
 int sscg_fill_zero(void* ptr, int64_t bytes, void* stream);
 const char* sscg_last_error(void);
+/* Programmatic dependent launch of the library's kernels (default off; SSCG_PDL=1 in the environment turns it on):
+ * a kernel may be scheduled while its predecessor in the stream drains and blocks (griddepcontrol.wait) before it
+ * touches global memory. */
+int sscg_set_pdl(int32_t on);
 int sscg_device_error(void);   /* reads (and clears) the device-side protocol error flag; 0 = none */
 int sscg_version(void);
 

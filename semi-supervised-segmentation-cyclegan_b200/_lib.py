@@ -123,6 +123,7 @@ _SIGNATURES = {
     "sscg_conv_wgrad": [C.POINTER(WgradArgs), C.c_void_p],
     "sscg_conv_wgrad_ws_bytes": [C.POINTER(WgradArgs)],
     "sscg_conv_wgrad_ctas_per_sm": [C.c_int32, C.c_int32],
+    "sscg_set_pdl": [C.c_int32],
     "sscg_conv_wgrad7": [C.POINTER(Wgrad7Args), C.c_void_p],
     "sscg_conv_wgrad7_ws_bytes": [C.POINTER(Wgrad7Args)],
     "sscg_pack_nchw": [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,

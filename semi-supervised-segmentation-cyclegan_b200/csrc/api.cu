@@ -84,6 +84,16 @@ static struct {
     int tag[kProfMax];
 } g_prof;
 
+static int g_pdl = -1;
+bool pdl_enabled() {
+    if (g_pdl < 0) {
+        const char* e = getenv("SSCG_PDL");
+        g_pdl = (e && e[0] == '1') ? 1 : 0;     // measured: no gain under the power cap -> opt-in
+    }
+    return g_pdl != 0;
+}
+void pdl_set(int on) { g_pdl = on ? 1 : 0; }
+
 LaunchScope::LaunchScope(int tag, cudaStream_t s) : slot(-1), stream(s) {
     ++g_launches;
     if (g_prof.on && ((g_prof.mask >> (tag & 15)) & 1u) && g_prof.n < kProfMax) {
@@ -99,6 +109,7 @@ LaunchScope::~LaunchScope() {
 }  // namespace sscg
 
 extern "C" uint64_t sscg_launch_count(void) { return sscg::g_launches; }
+extern "C" int sscg_set_pdl(int32_t on) { sscg::pdl_set(on); return 0; }
 
 extern "C" int sscg_prof_begin(uint32_t tag_mask) {
     using namespace sscg;

@@ -175,6 +175,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
+    pdl_wait();          // the prologue above overlaps the predecessor's tail (launch_k, sscg_common.cuh)
+    pdl_launch();
 
     if (warp == 0) {
         // ================================ TMA producer ==========================================
@@ -475,7 +477,7 @@ static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmAlo, const 
     if (grid > d.total_tiles) grid = d.total_tiles;
     {
         LaunchScope ls(tag, stream);
-        conv_igemm_kernel<BN, SPLIT, SKW, RW><<<grid, 192, Cfg::kSmemBytes, stream>>>(tmA, tmAlo, tmB, tmBlo, d);
+        launch_k(conv_igemm_kernel<BN, SPLIT, SKW, RW>, grid, 192, Cfg::kSmemBytes, stream, tmA, tmAlo, tmB, tmBlo, d);
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_error("conv_igemm<%d,%d> launch: %s", BN, SPLIT, cudaGetErrorString(e));

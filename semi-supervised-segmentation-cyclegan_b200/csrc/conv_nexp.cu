@@ -122,6 +122,8 @@ conv_nexp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tmem_alloc(smem_u32(tmem_ptr_smem), tmem_cols);
         tmem_relinquish();
     }
+    pdl_wait();          // barrier init / TMEM allocation above overlap the predecessor's tail (launch_k, sscg_common.cuh)
+    pdl_launch();
     if (warp >= 2 && warp < 6 && p.bias != nullptr) {
         const int e = threadIdx.x - 64;
         if (e < p.n_ntiles * p.CoW && e < 64) bias_sm[e] = p.bias[e];
@@ -423,7 +425,7 @@ extern "C" int sscg_conv7_nexp(const SscgConv7Args* a, void* stream_) {
     }
     {
         LaunchScope ls(a->tag, stream);
-        conv_nexp_kernel<<<grid, 320, smem, stream>>>(tmA, tmB, d);
+        launch_k(conv_nexp_kernel, grid, 320, smem, stream, tmA, tmB, d);
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_error("conv7_nexp launch: %s", cudaGetErrorString(e));

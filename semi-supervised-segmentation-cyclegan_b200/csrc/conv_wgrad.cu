@@ -115,6 +115,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
+    pdl_wait();          // the prologue above overlaps the predecessor's tail (launch_k, sscg_common.cuh)
+    pdl_launch();
 
     // stage layout: [A hi atoms (2)] [B hi atoms] [A lo atoms (2)] [B lo atoms]
     constexpr int kAOff = 0;
@@ -305,7 +307,7 @@ static int launch_wgrad(const CUtensorMap& tmDy, const CUtensorMap& tmDyLo, cons
     }
     {
         LaunchScope ls(tag, stream);
-        conv_wgrad_kernel<BN, SPLIT><<<grid, 192, Cfg::kSmemBytes, stream>>>(tmDy, tmDyLo, tmX, tmXLo, d);
+        launch_k(conv_wgrad_kernel<BN, SPLIT>, grid, 192, Cfg::kSmemBytes, stream, tmDy, tmDyLo, tmX, tmXLo, d);
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_error("conv_wgrad<%d,%d> launch: %s", BN, SPLIT, cudaGetErrorString(e));

@@ -114,6 +114,8 @@ conv_wgrad7_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
+    pdl_wait();          // the prologue above overlaps the predecessor's tail (launch_k, sscg_common.cuh)
+    pdl_launch();
     const bool has_work = cta_in_g < p.units_per_g;
 
     if (warp == 0) {
@@ -327,7 +329,7 @@ extern "C" int sscg_conv_wgrad7(const SscgWgrad7Args* a, void* stream_) {
     }
     {
         LaunchScope ls(a->tag, stream);
-        conv_wgrad7_kernel<<<sms, 192, smem, stream>>>(tmX, tmDy, d);
+        launch_k(conv_wgrad7_kernel, sms, 192, smem, stream, tmX, tmDy, d);
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_error("conv_wgrad7 launch: %s", cudaGetErrorString(e));

@@ -125,6 +125,8 @@ template <bool ONEHOT>
 __global__ void pack_kernel(const float* __restrict__ src, const long long* __restrict__ labels, int N, int C, int H,
                             int W, void* __restrict__ dst_, void* __restrict__ dst_lo_, int Cp, int pad,
                             int pad_mode, int dst_fp32) {
+    pdl_wait();
+    pdl_launch();
     __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(dst_);
     __nv_bfloat16* dst_lo = reinterpret_cast<__nv_bfloat16*>(dst_lo_);
     const int Hp = H + 2 * pad, Wp = W + 2 * pad;
@@ -170,6 +172,8 @@ __global__ void unpack_fold_kernel(const void* __restrict__ src, int src_fp32, i
 
 __global__ void unpack_kernel(const float* __restrict__ src, int N, int C, int H, int W, int Cp,
                               float* __restrict__ dst) {
+    pdl_wait();
+    pdl_launch();
     const long long total = (long long)N * H * W;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
@@ -187,6 +191,8 @@ __global__ void unpack_kernel(const float* __restrict__ src, int N, int C, int H
 
 __global__ void unpack_fold_kernel(const void* __restrict__ src, int src_fp32, int N, int C, int H, int W, int Cp,
                                    int pad, int pad_mode, float* __restrict__ dst) {
+    pdl_wait();
+    pdl_launch();
     const int Hp = H + 2 * pad, Wp = W + 2 * pad;
     const long long total = (long long)N * H * W;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
@@ -218,6 +224,8 @@ __global__ void unpack_fold_kernel(const void* __restrict__ src, int src_fp32, i
 // bias gradient of a conv without normalisation: grad[c] += scale * sum_n bstats[n][c][0]
 __global__ void bias_grad_kernel(const long long* __restrict__ bstats, int N, int C, int Cp, float* __restrict__ grad,
                                  float scale) {
+    pdl_wait();
+    pdl_launch();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     float s = 0.f;
@@ -262,6 +270,8 @@ __host__ __device__ __forceinline__ int wslab_ntaps(const SscgWprepArgs& a) {
 }
 
 __global__ void wprep_kernel(const __grid_constant__ SscgWprepArgs a) {
+    pdl_wait();
+    pdl_launch();
     const long long total = (long long)wslab_ntaps(a) * a.rows_pad * a.Kc;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
@@ -279,6 +289,8 @@ __global__ void wprep_kernel(const __grid_constant__ SscgWprepArgs a) {
 
 __global__ void wgrad_unpack_kernel(const __grid_constant__ SscgWprepArgs a, const float* __restrict__ slab,
                                     float* __restrict__ grad, float scale) {
+    pdl_wait();
+    pdl_launch();
     const long long total = (long long)wslab_ntaps(a) * a.rows_pad * a.Kc;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
@@ -305,6 +317,8 @@ __device__ __forceinline__ int wbatch_find(const SscgWbatchEntry* __restrict__ t
 // tap (L1) instead of touching 9-49x the useful bytes, and every store of a warp is one contiguous run.
 // `start` / `total` count (row, k) positions: rows_pad * Kc per entry.
 __global__ void wprep_batch_kernel(const SscgWbatchEntry* __restrict__ tab, int count, long long total) {
+    pdl_wait();
+    pdl_launch();
     for (long long gidx = blockIdx.x * (long long)blockDim.x + threadIdx.x; gidx < total;
          gidx += (long long)gridDim.x * blockDim.x) {
         const SscgWbatchEntry& e = tab[wbatch_find(tab, count, gidx)];
@@ -325,6 +339,8 @@ __global__ void wprep_batch_kernel(const SscgWbatchEntry* __restrict__ tab, int 
     }
 }
 __global__ void wgrad_unpack_batch_kernel(const SscgWbatchEntry* __restrict__ tab, int count, long long total, float scale) {
+    pdl_wait();
+    pdl_launch();
     for (long long gidx = blockIdx.x * (long long)blockDim.x + threadIdx.x; gidx < total;
          gidx += (long long)gridDim.x * blockDim.x) {
         const SscgWbatchEntry& e = tab[wbatch_find(tab, count, gidx)];
@@ -364,6 +380,8 @@ __device__ __forceinline__ InterpTap interp_tap(int o, float scale, int in_size)
 }
 __global__ void __launch_bounds__(256) interp_fwd_kernel(const float* __restrict__ x, int NC, int Hi, int Wi,
                                                          float* __restrict__ y, int Ho, int Wo, float sh, float sw) {
+    pdl_wait();
+    pdl_launch();
     const long long total = (long long)NC * Ho * Wo;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
@@ -378,6 +396,8 @@ __global__ void __launch_bounds__(256) interp_fwd_kernel(const float* __restrict
 }
 __global__ void __launch_bounds__(256) interp_bwd_kernel(const float* __restrict__ dy, int NC, int Hi, int Wi,
                                                          float* __restrict__ dx, int Ho, int Wo, float sh, float sw) {
+    pdl_wait();
+    pdl_launch();
     const long long total = (long long)NC * Hi * Wi;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
@@ -518,7 +538,7 @@ extern "C" int sscg_pack_nchw(const float* src, int32_t N, int32_t C, int32_t H,
     const long long total = (long long)N * (H + 2 * pad) * (W + 2 * pad);
     {
         LaunchScope ls_(9, static_cast<cudaStream_t>(stream));
-        pack_kernel<false><<<ew_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        launch_k(pack_kernel<false>, ew_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream), 
             src, nullptr, N, C, H, W, dst, dst_lo, Cp, pad, pad_mode, dst_fp32);
     }
     SSCG_CHECK_LAUNCH("pack_nchw");
@@ -531,7 +551,7 @@ extern "C" int sscg_onehot_pack(const int64_t* labels, int32_t N, int32_t C, int
     const long long total = (long long)N * (H + 2 * pad) * (W + 2 * pad);
     {
         LaunchScope ls_(9, static_cast<cudaStream_t>(stream));
-        pack_kernel<true><<<ew_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        launch_k(pack_kernel<true>, ew_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream), 
             nullptr, reinterpret_cast<const long long*>(labels), N, C, H, W, dst, dst_lo, Cp, pad, pad_mode, 0);
     }
     SSCG_CHECK_LAUNCH("onehot_pack");
@@ -543,7 +563,7 @@ extern "C" int sscg_unpack_nhwc(const float* src, int32_t N, int32_t C, int32_t 
     const long long total = (long long)N * H * W;
     {
         LaunchScope ls_(9, static_cast<cudaStream_t>(stream));
-        unpack_kernel<<<ew_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, N, C, H, W, Cp, dst);
+        launch_k(unpack_kernel, ew_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream), src, N, C, H, W, Cp, dst);
     }
     SSCG_CHECK_LAUNCH("unpack_nhwc");
     return 0;
@@ -555,7 +575,7 @@ extern "C" int sscg_unpack_fold(const void* src, int32_t src_fp32, int32_t N, in
     const long long total = (long long)N * H * W;
     {
         LaunchScope ls_(9, static_cast<cudaStream_t>(stream));
-        unpack_fold_kernel<<<ew_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, src_fp32, N, C, H, W, Cp,
+        launch_k(unpack_fold_kernel, ew_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream), src, src_fp32, N, C, H, W, Cp,
                                                                                              pad, pad_mode, dst);
     }
     SSCG_CHECK_LAUNCH("unpack_fold");
@@ -566,7 +586,7 @@ extern "C" int sscg_bias_grad(const void* bstats, int32_t N, int32_t C, int32_t 
                               void* stream) {
     {
         LaunchScope ls_(9, static_cast<cudaStream_t>(stream));
-        bias_grad_kernel<<<(C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        launch_k(bias_grad_kernel, (C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream), 
             reinterpret_cast<const long long*>(bstats), N, C, Cp, grad, scale);
     }
     SSCG_CHECK_LAUNCH("bias_grad");
@@ -604,10 +624,10 @@ extern "C" int sscg_in_apply(const SscgApplyArgs* a, void* stream) {
                 const dim3 grid(stream_grid(sd.g)), block(kStrThreadsLight + 32);
                 const size_t smem = stream_smem(sd.g);
                 cudaStream_t st = static_cast<cudaStream_t>(stream);
-                if (spec == 1) in_apply_stream_kernel<kStrThreadsLight, 1><<<grid, block, smem, st>>>(sd);
-                else if (spec == 2) in_apply_stream_kernel<kStrThreadsLight, 2><<<grid, block, smem, st>>>(sd);
-                else if (spec == 3) in_apply_stream_kernel<kStrThreadsLight, 3><<<grid, block, smem, st>>>(sd);
-                else in_apply_stream_kernel<kStrThreadsLight, 0><<<grid, block, smem, st>>>(sd);
+                if (spec == 1) launch_k(in_apply_stream_kernel<kStrThreadsLight, 1>, grid, block, smem, st, sd);
+                else if (spec == 2) launch_k(in_apply_stream_kernel<kStrThreadsLight, 2>, grid, block, smem, st, sd);
+                else if (spec == 3) launch_k(in_apply_stream_kernel<kStrThreadsLight, 3>, grid, block, smem, st, sd);
+                else launch_k(in_apply_stream_kernel<kStrThreadsLight, 0>, grid, block, smem, st, sd);
             }
             SSCG_CHECK_LAUNCH("in_apply_stream");
             return 0;
@@ -620,9 +640,9 @@ extern "C" int sscg_in_apply(const SscgApplyArgs* a, void* stream) {
     {
         LaunchScope ls_(7, static_cast<cudaStream_t>(stream));
         if (a->raw_fp32 || a->res_lo || a->dst_lo)
-            in_apply_kernel<true><<<dim3(gridx, a->N), 256, 0, static_cast<cudaStream_t>(stream)>>>(d);
+            launch_k(in_apply_kernel<true>, dim3(gridx, a->N), 256, 0, static_cast<cudaStream_t>(stream), d);
         else
-            in_apply_kernel<false><<<dim3(gridx, a->N), 256, 0, static_cast<cudaStream_t>(stream)>>>(d);
+            launch_k(in_apply_kernel<false>, dim3(gridx, a->N), 256, 0, static_cast<cudaStream_t>(stream), d);
     }
     SSCG_CHECK_LAUNCH("in_apply");
     return 0;
@@ -654,9 +674,9 @@ extern "C" int sscg_in_bwd_prep(const SscgBwdArgs* a, void* stream) {
                 const dim3 grid(stream_grid(sd.g)), block(kStrThreadsHeavy + 32);
                 const size_t smem = stream_smem(sd.g);
                 cudaStream_t st = static_cast<cudaStream_t>(stream);
-                if (spec == 1) in_bwd_prep_stream_kernel<kStrThreadsHeavy, 1><<<grid, block, smem, st>>>(sd);
-                else if (spec == 2) in_bwd_prep_stream_kernel<kStrThreadsHeavy, 2><<<grid, block, smem, st>>>(sd);
-                else in_bwd_prep_stream_kernel<kStrThreadsHeavy, 0><<<grid, block, smem, st>>>(sd);
+                if (spec == 1) launch_k(in_bwd_prep_stream_kernel<kStrThreadsHeavy, 1>, grid, block, smem, st, sd);
+                else if (spec == 2) launch_k(in_bwd_prep_stream_kernel<kStrThreadsHeavy, 2>, grid, block, smem, st, sd);
+                else launch_k(in_bwd_prep_stream_kernel<kStrThreadsHeavy, 0>, grid, block, smem, st, sd);
             }
             SSCG_CHECK_LAUNCH("in_bwd_prep_stream");
             return 0;
@@ -669,9 +689,9 @@ extern "C" int sscg_in_bwd_prep(const SscgBwdArgs* a, void* stream) {
     {
         LaunchScope ls_(8, static_cast<cudaStream_t>(stream));
         if (a->raw_fp32 || a->dyp_fp32 || a->skip_fp32 || a->g_fp32 || a->dz_fp32 || a->dz_lo)
-            in_bwd_prep_kernel<true><<<dim3(gridx, a->N), 256, 0, static_cast<cudaStream_t>(stream)>>>(d);
+            launch_k(in_bwd_prep_kernel<true>, dim3(gridx, a->N), 256, 0, static_cast<cudaStream_t>(stream), d);
         else
-            in_bwd_prep_kernel<false><<<dim3(gridx, a->N), 256, 0, static_cast<cudaStream_t>(stream)>>>(d);
+            launch_k(in_bwd_prep_kernel<false>, dim3(gridx, a->N), 256, 0, static_cast<cudaStream_t>(stream), d);
     }
     SSCG_CHECK_LAUNCH("in_bwd_prep");
     return 0;
@@ -688,8 +708,8 @@ extern "C" int sscg_in_bwd_apply(const SscgBwdArgs* a, void* draw, void* draw_lo
             sd.a = *a; sd.draw = draw;
             {
                 LaunchScope ls_(8, static_cast<cudaStream_t>(stream));
-                in_bwd_apply_stream_kernel<kStrThreadsLight><<<stream_grid(sd.g), kStrThreadsLight + 32, stream_smem(sd.g),
-                                             static_cast<cudaStream_t>(stream)>>>(sd);
+                launch_k(in_bwd_apply_stream_kernel<kStrThreadsLight>, stream_grid(sd.g), kStrThreadsLight + 32, stream_smem(sd.g),
+                                             static_cast<cudaStream_t>(stream), sd);
             }
             SSCG_CHECK_LAUNCH("in_bwd_apply_stream");
             return 0;
@@ -702,9 +722,9 @@ extern "C" int sscg_in_bwd_apply(const SscgBwdArgs* a, void* draw, void* draw_lo
     {
         LaunchScope ls_(8, static_cast<cudaStream_t>(stream));
         if (a->raw_fp32 || a->dz_fp32 || draw_lo)
-            in_bwd_apply_kernel<true><<<dim3(gridx, a->N), 256, 0, static_cast<cudaStream_t>(stream)>>>(d);
+            launch_k(in_bwd_apply_kernel<true>, dim3(gridx, a->N), 256, 0, static_cast<cudaStream_t>(stream), d);
         else
-            in_bwd_apply_kernel<false><<<dim3(gridx, a->N), 256, 0, static_cast<cudaStream_t>(stream)>>>(d);
+            launch_k(in_bwd_apply_kernel<false>, dim3(gridx, a->N), 256, 0, static_cast<cudaStream_t>(stream), d);
     }
     SSCG_CHECK_LAUNCH("in_bwd_apply");
     return 0;
@@ -718,7 +738,7 @@ extern "C" int sscg_interp_bilinear_fwd(const float* x, int32_t N, int32_t C, in
     if (!x || !y || N < 1 || C < 1 || Hi < 1 || Wi < 1 || Ho < 1 || Wo < 1) return set_error("interp_bilinear_fwd: bad arguments");
     {
         LaunchScope ls_(9, static_cast<cudaStream_t>(stream));
-        interp_fwd_kernel<<<ew_grid((long long)N * C * Ho * Wo, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        launch_k(interp_fwd_kernel, ew_grid((long long)N * C * Ho * Wo, 256), 256, 0, static_cast<cudaStream_t>(stream), 
             x, N * C, Hi, Wi, y, Ho, Wo, interp_scale(Hi, Ho), interp_scale(Wi, Wo));
     }
     SSCG_CHECK_LAUNCH("interp_bilinear_fwd");
@@ -729,7 +749,7 @@ extern "C" int sscg_interp_bilinear_bwd(const float* dy, int32_t N, int32_t C, i
     if (!dy || !dx || N < 1 || C < 1 || Hi < 1 || Wi < 1 || Ho < 1 || Wo < 1) return set_error("interp_bilinear_bwd: bad arguments");
     {
         LaunchScope ls_(9, static_cast<cudaStream_t>(stream));
-        interp_bwd_kernel<<<ew_grid((long long)N * C * Hi * Wi, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        launch_k(interp_bwd_kernel, ew_grid((long long)N * C * Hi * Wi, 256), 256, 0, static_cast<cudaStream_t>(stream), 
             dy, N * C, Hi, Wi, dx, Ho, Wo, interp_scale(Hi, Ho), interp_scale(Wi, Wo));
     }
     SSCG_CHECK_LAUNCH("interp_bilinear_bwd");
@@ -740,7 +760,7 @@ extern "C" int sscg_wprep(const SscgWprepArgs* a, void* stream) {
     const long long total = (long long)wslab_ntaps(*a) * a->rows_pad * a->Kc;
     {
         LaunchScope ls_(9, static_cast<cudaStream_t>(stream));
-        wprep_kernel<<<ew_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(*a);
+        launch_k(wprep_kernel, ew_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream), *a);
     }
     SSCG_CHECK_LAUNCH("wprep");
     return 0;
@@ -750,7 +770,7 @@ extern "C" int sscg_wgrad_unpack(const SscgWprepArgs* a, const float* slab, floa
     const long long total = (long long)wslab_ntaps(*a) * a->rows_pad * a->Kc;
     {
         LaunchScope ls_(9, static_cast<cudaStream_t>(stream));
-        wgrad_unpack_kernel<<<ew_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(*a, slab, grad, scale);
+        launch_k(wgrad_unpack_kernel, ew_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream), *a, slab, grad, scale);
     }
     SSCG_CHECK_LAUNCH("wgrad_unpack");
     return 0;
@@ -760,7 +780,7 @@ extern "C" int sscg_wprep_batch(const SscgWbatchEntry* table_dev, int32_t count,
     if (!table_dev || count < 1 || total < 1) return set_error("wprep_batch: bad arguments");
     {
         LaunchScope ls_(9, static_cast<cudaStream_t>(stream));
-        wprep_batch_kernel<<<ew_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(table_dev, count, total);
+        launch_k(wprep_batch_kernel, ew_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream), table_dev, count, total);
     }
     SSCG_CHECK_LAUNCH("wprep_batch");
     return 0;
@@ -771,7 +791,7 @@ extern "C" int sscg_wgrad_unpack_batch(const SscgWbatchEntry* table_dev, int32_t
     if (!table_dev || count < 1 || total < 1) return set_error("wgrad_unpack_batch: bad arguments");
     {
         LaunchScope ls_(9, static_cast<cudaStream_t>(stream));
-        wgrad_unpack_batch_kernel<<<ew_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(table_dev, count, total,
+        launch_k(wgrad_unpack_batch_kernel, ew_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream), table_dev, count, total,
                                                                                                   scale);
     }
     SSCG_CHECK_LAUNCH("wgrad_unpack_batch");

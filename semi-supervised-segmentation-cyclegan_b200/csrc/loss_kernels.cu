@@ -73,6 +73,8 @@ __global__ void __launch_bounds__(256) seg_head_fwd_kernel(const float* __restri
                                                            long long HW, long long ignore_index,
                                                            float* __restrict__ probs, long long* __restrict__ argmax,
                                                            float* __restrict__ loss_out, float* __restrict__ ws) {
+    pdl_wait();
+    pdl_launch();
     const long long total = (long long)N * HW;
     float local = 0.f, counted = 0.f;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
@@ -135,6 +137,8 @@ __global__ void __launch_bounds__(256) seg_head_bwd_kernel(const float* __restri
                                                            const float* __restrict__ count,
                                                            const float* __restrict__ dprobs, int N, int C,
                                                            long long HW, float* __restrict__ dlogits) {
+    pdl_wait();
+    pdl_launch();
     const long long total = (long long)N * HW;
     const float ce = (dloss != nullptr && labels != nullptr) ? (*dloss) / (*count) : 0.f;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
@@ -174,6 +178,8 @@ __global__ void __launch_bounds__(256) seg_head_bwd_kernel(const float* __restri
 // loss_out = scale * sum (x - target)^2
 __global__ void __launch_bounds__(256) lsgan_fwd_kernel(const float* __restrict__ x, long long n, float target,
                                                         float scale, float* __restrict__ loss_sum, float* __restrict__ ws) {
+    pdl_wait();
+    pdl_launch();
     float local = 0.f;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const float d = x[i] - target;
@@ -184,6 +190,8 @@ __global__ void __launch_bounds__(256) lsgan_fwd_kernel(const float* __restrict_
 // dx = dloss * 2 (x - target) / n      (dloss: device scalar, gradient of the MEAN)
 __global__ void __launch_bounds__(256) lsgan_bwd_kernel(const float* __restrict__ x, long long n, float target,
                                                         const float* __restrict__ dloss, float* __restrict__ dx) {
+    pdl_wait();
+    pdl_launch();
     const float sc = 2.f * (*dloss) / (float)n;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         dx[i] = sc * (x[i] - target);
@@ -194,6 +202,8 @@ template <bool VEC>
 __global__ void __launch_bounds__(256) l1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ y,
                                                      long long n, float scale, float* __restrict__ loss_sum,
                                                      float* __restrict__ ws) {
+    pdl_wait();
+    pdl_launch();
     float local = 0.f;
     if (VEC) {
         const long long n4 = n >> 2;
@@ -214,6 +224,8 @@ __global__ void __launch_bounds__(256) l1_fwd_kernel(const float* __restrict__ x
 __global__ void __launch_bounds__(256) l1_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y,
                                                      long long n, const float* __restrict__ dloss,
                                                      float* __restrict__ dx) {
+    pdl_wait();
+    pdl_launch();
     const float sc = (*dloss) / (float)n;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const float d = x[i] - y[i];
@@ -232,6 +244,8 @@ __global__ void __launch_bounds__(256) adam_flat_kernel(float* __restrict__ p, c
                                                         float* __restrict__ m, float* __restrict__ v, long long n,
                                                         const float* __restrict__ lr, float beta1, float beta2,
                                                         float eps, const float* __restrict__ step) {
+    pdl_wait();
+    pdl_launch();
     const float t = *step;
     const float bc1 = 1.f - powf(beta1, t);
     const float bc2 = 1.f - powf(beta2, t);
@@ -271,6 +285,8 @@ __global__ void __launch_bounds__(256) adam_flat_kernel(float* __restrict__ p, c
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) confusion_kernel(const long long* __restrict__ lt, const long long* __restrict__ lp,
                                                         long long n, int C, unsigned long long* __restrict__ hist) {
+    pdl_wait();
+    pdl_launch();
     __shared__ unsigned int s_hist[kMaxClasses * kMaxClasses];
     for (int i = threadIdx.x; i < C * C; i += blockDim.x) s_hist[i] = 0u;
     __syncthreads();
@@ -296,7 +312,7 @@ extern "C" int sscg_seg_head_fwd(const float* logits, const int64_t* labels, int
     if (g > 148 * 8) g = 148 * 8;
     {
         LaunchScope ls_(10, static_cast<cudaStream_t>(stream));
-        seg_head_fwd_kernel<<<(int)g, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        launch_k(seg_head_fwd_kernel, (int)g, 256, 0, static_cast<cudaStream_t>(stream), 
             logits, reinterpret_cast<const long long*>(labels), N, C, HW, (long long)ignore_index, probs,
             reinterpret_cast<long long*>(argmax), loss_out, reinterpret_cast<float*>(ws));
     }
@@ -314,7 +330,7 @@ extern "C" int sscg_seg_head_bwd(const float* probs, const int64_t* labels, cons
     if (g > 148 * 8) g = 148 * 8;
     {
         LaunchScope ls_(10, static_cast<cudaStream_t>(stream));
-        seg_head_bwd_kernel<<<(int)g, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        launch_k(seg_head_bwd_kernel, (int)g, 256, 0, static_cast<cudaStream_t>(stream), 
             probs, reinterpret_cast<const long long*>(labels), dloss, count, dprobs, N, C, HW, dlogits);
     }
     cudaError_t e = cudaGetLastError();
@@ -339,7 +355,7 @@ extern "C" int sscg_lsgan_fwd(const float* x, int64_t n, float target, float sca
     if (!x || !loss_sum || !ws || n < 1) return set_error("lsgan_fwd: bad arguments");
     {
         LaunchScope ls_(10, static_cast<cudaStream_t>(stream));
-        lsgan_fwd_kernel<<<loss_grid(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, n, target, scale, loss_sum,
+        launch_k(lsgan_fwd_kernel, loss_grid(n), 256, 0, static_cast<cudaStream_t>(stream), x, n, target, scale, loss_sum,
                                                                                      reinterpret_cast<float*>(ws));
     }
     SSCG_LOSS_LAUNCH_CHECK("lsgan_fwd");
@@ -349,7 +365,7 @@ extern "C" int sscg_lsgan_bwd(const float* x, int64_t n, float target, const flo
     if (!x || !dloss || !dx || n < 1) return set_error("lsgan_bwd: bad arguments");
     {
         LaunchScope ls_(10, static_cast<cudaStream_t>(stream));
-        lsgan_bwd_kernel<<<loss_grid(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, n, target, dloss, dx);
+        launch_k(lsgan_bwd_kernel, loss_grid(n), 256, 0, static_cast<cudaStream_t>(stream), x, n, target, dloss, dx);
     }
     SSCG_LOSS_LAUNCH_CHECK("lsgan_bwd");
     return 0;
@@ -361,10 +377,10 @@ extern "C" int sscg_l1_fwd(const float* x, const float* y, int64_t n, float scal
     {
         LaunchScope ls_(10, static_cast<cudaStream_t>(stream));
         if (vec)
-            l1_fwd_kernel<true><<<loss_grid(n >> 2), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+            launch_k(l1_fwd_kernel<true>, loss_grid(n >> 2), 256, 0, static_cast<cudaStream_t>(stream), 
                 x, y, n, scale, loss_sum, reinterpret_cast<float*>(ws));
         else
-            l1_fwd_kernel<false><<<loss_grid(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+            launch_k(l1_fwd_kernel<false>, loss_grid(n), 256, 0, static_cast<cudaStream_t>(stream), 
                 x, y, n, scale, loss_sum, reinterpret_cast<float*>(ws));
     }
     SSCG_LOSS_LAUNCH_CHECK("l1_fwd");
@@ -374,7 +390,7 @@ extern "C" int sscg_l1_bwd(const float* x, const float* y, int64_t n, const floa
     if (!x || !y || !dloss || !dx || n < 1) return set_error("l1_bwd: bad arguments");
     {
         LaunchScope ls_(10, static_cast<cudaStream_t>(stream));
-        l1_bwd_kernel<<<loss_grid(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, y, n, dloss, dx);
+        launch_k(l1_bwd_kernel, loss_grid(n), 256, 0, static_cast<cudaStream_t>(stream), x, y, n, dloss, dx);
     }
     SSCG_LOSS_LAUNCH_CHECK("l1_bwd");
     return 0;
@@ -387,7 +403,7 @@ extern "C" int sscg_adam_flat(float* p, const float* g, float* m, float* v, int6
         return set_error("adam_flat: buffers must be 16-byte aligned");
     {
         LaunchScope ls_(11, static_cast<cudaStream_t>(stream));
-        adam_flat_kernel<<<loss_grid(n >> 2), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, g, m, v, n, lr, beta1, beta2,
+        launch_k(adam_flat_kernel, loss_grid(n >> 2), 256, 0, static_cast<cudaStream_t>(stream), p, g, m, v, n, lr, beta1, beta2,
                                                                                          eps, step);
     }
     SSCG_LOSS_LAUNCH_CHECK("adam_flat");
@@ -400,7 +416,7 @@ extern "C" int sscg_confusion(const int64_t* label_true, const int64_t* label_pr
     if (n_class < 1 || n_class > kMaxClasses) return set_error("confusion: n_class=%d must be in [1, %d]", n_class, kMaxClasses);
     {
         LaunchScope ls_(10, static_cast<cudaStream_t>(stream));
-        confusion_kernel<<<loss_grid(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        launch_k(confusion_kernel, loss_grid(n), 256, 0, static_cast<cudaStream_t>(stream), 
             reinterpret_cast<const long long*>(label_true), reinterpret_cast<const long long*>(label_pred), n, n_class,
             reinterpret_cast<unsigned long long*>(hist));
     }

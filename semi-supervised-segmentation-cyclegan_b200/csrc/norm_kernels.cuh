@@ -85,6 +85,8 @@ constexpr int kApplyBatch = SSCG_APPLY_BATCH;
 
 template <bool ANYF32>
 __global__ void __launch_bounds__(256, SSCG_APPLY_MINB) in_apply_kernel(const __grid_constant__ ApplyDev p) {
+    pdl_wait();
+    pdl_launch();
     const SscgApplyArgs& a = p.a;
     const int n = blockIdx.y;
     const int chunk = threadIdx.x % p.CH;
@@ -217,6 +219,8 @@ constexpr int kPrepBatch = SSCG_PREP_BATCH;
 // First half of the backward: writes dZ (and the folded total gradient), produces the plane sums.
 template <bool ANYF32>
 __global__ void __launch_bounds__(256, SSCG_PREP_MINB) in_bwd_prep_kernel(const __grid_constant__ BwdDev p) {
+    pdl_wait();
+    pdl_launch();
     const SscgBwdArgs& a = p.a;
     __shared__ float s_red[256 * 16];
     const int n = blockIdx.y;
@@ -378,6 +382,8 @@ constexpr int kBwdApplyBatch = SSCG_BAPPLY_BATCH;
 
 template <bool ANYF32>
 __global__ void __launch_bounds__(256, SSCG_BAPPLY_MINB) in_bwd_apply_kernel(const __grid_constant__ BwdDev p) {
+    pdl_wait();
+    pdl_launch();
     const SscgBwdArgs& a = p.a;
     const int n = blockIdx.y;
     const int chunk = threadIdx.x % p.CH;

@@ -215,6 +215,8 @@ __global__ void SSCG_STR_BOUNDS(kStrThreads) in_apply_stream_kernel(const __grid
     const SscgApplyArgs& a = p.a;
     const StreamGeom& g = p.g;
     const StreamRing ring = stream_ring_init<kStrThreads>(smem_raw, g);
+    pdl_wait();          // everything above overlaps the predecessor's tail (sscg_common.cuh, launch_k)
+    pdl_launch();
     const int u0 = (int)((long long)blockIdx.x * g.total / gridDim.x);
     const int u1 = (int)((long long)(blockIdx.x + 1) * g.total / gridDim.x);
     const int cnt = u1 - u0;
@@ -410,6 +412,8 @@ __global__ void SSCG_STR_BOUNDS(kStrThreads) in_bwd_prep_stream_kernel(const __g
     const SscgBwdArgs& a = p.a;
     const StreamGeom& g = p.g;
     const StreamRing ring = stream_ring_init<kStrThreads>(smem_raw, g);
+    pdl_wait();          // everything above overlaps the predecessor's tail (sscg_common.cuh, launch_k)
+    pdl_launch();
     const int u0 = (int)((long long)blockIdx.x * g.total / gridDim.x);
     const int u1 = (int)((long long)(blockIdx.x + 1) * g.total / gridDim.x);
     const int cnt = u1 - u0;
@@ -419,6 +423,9 @@ __global__ void SSCG_STR_BOUNDS(kStrThreads) in_bwd_prep_stream_kernel(const __g
     const bool need_raw = norm || act != SSCG_ACT_NONE;
     const bool has_skip = SPEC == 1 ? false : (SPEC == 2 ? true : (a.skip.ptr != nullptr));
     const bool has_gout = SPEC == 1 ? false : (SPEC == 2 ? true : (a.g_out != nullptr));
+    // without activation and dropout dZ IS the folded total gradient: the caller may pass the same buffer for both
+    // (second conv of a residual block) and the value is stored once
+    const bool store_gout = has_gout && a.g_out != a.dz;
     const bool fold = (a.pad_mode == SSCG_PAD_REFLECT) && a.pad > 0;
     const int off_skip = g.slot0, off_raw = g.slot0 + (has_skip ? 1 : 0) * g.ub;
     // The gradient row is staged WITH the halo columns next to it (first / last unit of a row), so the
@@ -574,7 +581,7 @@ __global__ void SSCG_STR_BOUNDS(kStrThreads) in_bwd_prep_stream_kernel(const __g
 #pragma unroll
                         for (int q = 0; q < 8; ++q) gv[q] += t[q];
                     }
-                    if (has_gout) *reinterpret_cast<uint4*>(gout0 + so) = pack8(gv);
+                    if (store_gout) *reinterpret_cast<uint4*>(gout0 + so) = pack8(gv);
                     if (drop && !packed_drop) {
                         // keep -> x2, drop -> x0: bit q moved to the exponent position of 2.0f (0x40000000)
 #pragma unroll
@@ -640,6 +647,8 @@ __global__ void SSCG_STR_BOUNDS(kStrThreads) in_bwd_apply_stream_kernel(const __
     const SscgBwdArgs& a = p.a;
     const StreamGeom& g = p.g;
     const StreamRing ring = stream_ring_init<kStrThreads>(smem_raw, g);
+    pdl_wait();          // everything above overlaps the predecessor's tail (sscg_common.cuh, launch_k)
+    pdl_launch();
     const int u0 = (int)((long long)blockIdx.x * g.total / gridDim.x);
     const int u1 = (int)((long long)(blockIdx.x + 1) * g.total / gridDim.x);
     const int cnt = u1 - u0;

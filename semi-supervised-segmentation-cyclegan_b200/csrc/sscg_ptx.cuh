@@ -198,6 +198,12 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr, uint32_
     d |= static_cast<uint64_t>(2) << 61;   // SWIZZLE_128B
     return d;
 }
+// Programmatic dependent launch (see launch_k in sscg_common.cuh): block until the predecessor grid has completed and
+// its memory operations are visible / allow the successor grid to be scheduled.  Both are no-ops for a launch without
+// the attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // General form.  layout: 0 = no swizzle ("interleave": 8-row x 16-byte core matrices; LBO = distance between core matrices
 // along K, SBO = distance between 8-row groups along M/N), 2 / 4 / 6 = SWIZZLE_128B / 64B / 32B.
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout,

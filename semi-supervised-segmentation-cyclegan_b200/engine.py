@@ -541,6 +541,10 @@ class NetPlan:
             ba.raw, ba.raw_fp32 = raw.hi.data_ptr(), 1 if raw.fp32 else 0
             ba.stats = c.stats[c.stat_off[i]:].data_ptr()
             ba.dz, ba.dz_fp32, ba.dz_lo = self.dz.data_ptr(), 1 if sp == 3 else 0, None
+            if (gout_t is not None and sp == 1 and s.act == L.ACT_NONE and not s.dropout and not ba.g_fp32
+                    and os.environ.get("SSCG_DZ_ALIAS", "1") != "0"):
+                # no activation, no dropout: dZ equals the folded total gradient — one buffer, one store
+                ba.dz = ba.g_out
             use_apply = True
         else:
             # activation applied in the GEMM epilogue: its output carries the sign (LeakyReLU) / value (tanh);

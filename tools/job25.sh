@@ -1,0 +1,15 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 1200 python -m pytest tests -m gpu -q -x > gpurun_out/pytest_all.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_all.log
+timeout 300 python tools/determinism_probe.py > gpurun_out/det.log 2>&1; echo "det rc=$?"; cat gpurun_out/det.log | cut -c1-300
+for rep in 1 2; do
+for v in 0 1; do
+SSCG_PDL=$v timeout 900 python bench.py --steps 20 --warmup 5 --no-gpu-baseline --no-cpu-baseline > gpurun_out/bench_pdl$v.json 2> gpurun_out/bench_pdl$v.err; echo "bench pdl=$v rc=$?"; tail -3 gpurun_out/bench_pdl$v.err
+python - <<PY
+import json
+d=json.loads(open("gpurun_out/bench_pdl$v.json").read().strip().splitlines()[-1])
+print("pdl=$v", d["value"], d["ms_per_step"], "e2e", d["e2e"]["value"], d["roofline"]["frac"], d["clocks"])
+k=d.get("kernel_time_ms_per_step"); print({a: round(b,2) for a,b in k.items()}, round(sum(k.values()),2))
+PY
+done
+done
