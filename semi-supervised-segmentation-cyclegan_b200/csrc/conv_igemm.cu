@@ -128,6 +128,36 @@ __device__ __forceinline__ TileInfo decode_tile(const ConvDev& p, int tile, int 
     return t;
 }
 
+// Schedule of one CTA: a CONTIGUOUS range of the full-tile entries, then its share of the half-N tail entries (which
+// keep the strided order: they are the balancing last wave).  Consecutive tiles mostly belong to one sample, so the CTA
+// keeps the plane sums of its tiles in registers and adds them to the global accumulators once per sample change: with
+// one flush per tile the 64-bit reductions cost 6 of the 67 us of a residual-block convolution (524 K per launch) and
+// 45 of the 164 us of the 64-channel stem, whose 512 tiles per sample all hit the same 256 words.
+struct TileWalk {
+    int cur, end, tail, total, step;
+    __device__ __forceinline__ explicit TileWalk(const ConvDev& p) {
+        // four-phase launches (transposed conv / stride-2 gathers) keep the strided order for ALL entries: their
+        // phases have 1, 2, 2 and 4 taps, and a contiguous range would fall into one phase (72 -> 90 us)
+        const int F = p.n_phases == 4 ? 0 : (p.tail_from >= 0 ? p.tail_from : p.total_tiles);
+        const int G = (int)gridDim.x, b = (int)blockIdx.x;
+        const int q = F / G, r = F - q * G;
+        cur = b * q + (b < r ? b : r);
+        end = cur + q + (b < r ? 1 : 0);
+        tail = F + b;
+        total = p.total_tiles;
+        step = G;
+    }
+    __device__ __forceinline__ int next() {      // -1: done
+        if (cur < end) return cur++;
+        if (tail < total) {
+            const int t = tail;
+            tail += step;
+            return t;
+        }
+        return -1;
+    }
+};
+
 template <int BN, int SPLIT, int SKW, int RW>
 __global__ void __launch_bounds__(192, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
@@ -182,7 +212,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         // ================================ TMA producer ==========================================
         if (lane == 0) {
             int stage = 0; uint32_t par = 0;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            TileWalk tw(p);
+            for (int tile = tw.next(); tile >= 0; tile = tw.next()) {
                 const TileInfo t = decode_tile(p, tile, BN);
                 if (!t.valid) continue;
                 int tp = 0, cb = 0;
@@ -230,7 +261,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             constexpr uint32_t idesc_half = make_idesc_bf16(kTileM, BN < 32 ? 16 : BN / 2, 0, 0);
             int stage = 0; uint32_t par = 0;
             uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            TileWalk tw(p);
+            for (int tile = tw.next(); tile >= 0; tile = tw.next()) {
                 const TileInfo t = decode_tile(p, tile, BN);
                 if (!t.valid) continue;
                 const uint32_t acc = it & 1, acc_par = (it >> 1) & 1;
@@ -292,7 +324,26 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         constexpr int kChunks = (BN + 31) / 32;
         constexpr int kCols = BN >= 32 ? 32 : BN;
         uint32_t it = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        // running plane sums of this thread's columns (threads 0..127 of the epilogue own columns e, e + 128)
+        float run1[2] = {0.f, 0.f}, run2[2] = {0.f, 0.f};
+        int run_n = -1, run_n0 = 0, run_bn = 0;
+        auto flush_stats = [&]() {
+            if (run_n < 0) return;
+            const int e = threadIdx.x - 64;
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const int col = e + 128 * k;
+                if (col < run_bn) {
+                    // binned integer accumulators (sscg_ptx.cuh): order-independent, hence reproducible, plane sums
+                    unsigned long long* dst = p.stats + ((long long)run_n * p.Co_pad + run_n0 + col) * (2 * kDetWords);
+                    det_red_add(dst, run1[k]);
+                    det_red_add(dst + kDetWords, run2[k]);
+                }
+                run1[k] = run2[k] = 0.f;
+            }
+        };
+        TileWalk tw(p);
+        for (int tile = tw.next(); tile >= 0; tile = tw.next()) {
             const TileInfo t = decode_tile(p, tile, BN);
             if (!t.valid) continue;
             const uint32_t acc = it & 1, acc_par = (it >> 1) & 1;
@@ -399,22 +450,29 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
             if (p.stats != nullptr) {
                 named_bar_sync(1, 128);               // all four quadrants wrote their partials
+                if (t.n != run_n || t.n0 != run_n0 || t.bn != run_bn) {
+                    flush_stats();
+                    run_n = t.n; run_n0 = t.n0; run_bn = t.bn;
+                }
                 const int e = threadIdx.x - 64;       // 0..127
-                for (int col = e; col < t.bn; col += 128) {
-                    float a = 0.f, b = 0.f;
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        a += s_stat[(q * BN + col) * 2 + 0];
-                        b += s_stat[(q * BN + col) * 2 + 1];
+                for (int k = 0; k < 2; ++k) {
+                    const int col = e + 128 * k;
+                    if (col < t.bn) {
+                        float a = 0.f, b = 0.f;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            a += s_stat[(q * BN + col) * 2 + 0];
+                            b += s_stat[(q * BN + col) * 2 + 1];
+                        }
+                        run1[k] += a;
+                        run2[k] += b;
                     }
-                    // binned integer accumulators (sscg_ptx.cuh): order-independent, hence reproducible, plane sums
-                    unsigned long long* dst = p.stats + ((long long)t.n * p.Co_pad + t.n0 + col) * (2 * kDetWords);
-                    det_red_add(dst, a);
-                    det_red_add(dst + kDetWords, b);
                 }
                 named_bar_sync(2, 128);               // s_stat may be overwritten by the next tile
             }
         }
+        if (p.stats != nullptr) flush_stats();
         tc_fence_before();
     }
     __syncthreads();
