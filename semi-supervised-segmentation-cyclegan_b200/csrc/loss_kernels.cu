@@ -68,6 +68,35 @@ __device__ __forceinline__ void grid_sum2_store(float a, float b, float* ws, flo
 // argmax [N][H][W] int64 (or null); loss_out[2] = (sum of -log p[label] over the counted pixels, their number).
 // nn.CrossEntropyLoss semantics (model.py:272): pixels whose label equals ignore_index are not counted; any other label
 // outside [0, C) raises the device error flag (torch device-asserts there) and is not counted either.
+// V consecutive pixels per thread (vector loads of 4 * V bytes per class plane: one warp instruction then covers
+// 128 * V contiguous bytes of a plane instead of 128 — the one-pixel version ran at 1.5-2.2 TB/s); the arithmetic per
+// pixel is unchanged.  V > 1 needs HW % V == 0 and 4 * V-byte aligned planes (checked by the launchers).
+template <int V>
+__device__ __forceinline__ void ldv(const float* p, float (&o)[V]);
+template <>
+__device__ __forceinline__ void ldv<1>(const float* p, float (&o)[1]) { o[0] = *p; }
+template <>
+__device__ __forceinline__ void ldv<2>(const float* p, float (&o)[2]) {
+    const float2 t = *reinterpret_cast<const float2*>(p);
+    o[0] = t.x; o[1] = t.y;
+}
+template <>
+__device__ __forceinline__ void ldv<4>(const float* p, float (&o)[4]) {
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w;
+}
+template <int V>
+__device__ __forceinline__ void stv(float* p, const float (&o)[V]);
+template <>
+__device__ __forceinline__ void stv<1>(float* p, const float (&o)[1]) { *p = o[0]; }
+template <>
+__device__ __forceinline__ void stv<2>(float* p, const float (&o)[2]) { *reinterpret_cast<float2*>(p) = make_float2(o[0], o[1]); }
+template <>
+__device__ __forceinline__ void stv<4>(float* p, const float (&o)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(o[0], o[1], o[2], o[3]);
+}
+
+template <int V>
 __global__ void __launch_bounds__(256) seg_head_fwd_kernel(const float* __restrict__ logits,
                                                            const long long* __restrict__ labels, int N, int C,
                                                            long long HW, long long ignore_index,
@@ -75,54 +104,74 @@ __global__ void __launch_bounds__(256) seg_head_fwd_kernel(const float* __restri
                                                            float* __restrict__ loss_out, float* __restrict__ ws) {
     pdl_wait();
     pdl_launch();
-    const long long total = (long long)N * HW;
+    const long long total = (long long)N * HW / V;          // groups of V pixels (a group never straddles samples)
     float local = 0.f, counted = 0.f;
-    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-         idx += (long long)gridDim.x * blockDim.x) {
+    for (long long gidx = blockIdx.x * (long long)blockDim.x + threadIdx.x; gidx < total;
+         gidx += (long long)gridDim.x * blockDim.x) {
+        const long long idx = gidx * V;
         const long long n = idx / HW, pix = idx - n * HW;
         const float* src = logits + n * C * HW + pix;
-        float v[kMaxClasses];
-        float mx = -INFINITY;
-        int am = 0;
+        // three streaming passes over the class planes (max / argmax, sum of exponentials, probabilities); the second and
+        // third hit the caches.  Holding the 21 logits of the pixels in registers limits the resident threads instead.
+        float mx[V];
+        int am[V];
 #pragma unroll
-        for (int c = 0; c < kMaxClasses; ++c) {
-            if (c < C) {
-                v[c] = src[c * HW];
-                if (v[c] > mx) { mx = v[c]; am = c; }      // strict '>' keeps the FIRST maximum (torch.max rule)
+        for (int i = 0; i < V; ++i) { mx[i] = -INFINITY; am[i] = 0; }
+#pragma unroll 7
+        for (int c = 0; c < C; ++c) {
+            float v[V];
+            ldv<V>(src + c * HW, v);
+#pragma unroll
+            for (int i = 0; i < V; ++i)
+                if (v[i] > mx[i]) { mx[i] = v[i]; am[i] = c; }      // strict '>' keeps the FIRST maximum (torch.max rule)
+        }
+        float vl[V];
+        bool count_it[V];
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+            vl[i] = 0.f;
+            count_it[i] = false;
+            if (labels != nullptr && loss_out != nullptr) {
+                const long long lab = labels[idx + i];
+                if (lab >= 0 && lab < C) {
+                    count_it[i] = true;
+                    vl[i] = src[lab * HW + i];
+                } else if (lab != ignore_index) {
+                    atomicCAS(&g_sscg_dev_error, 0u, (31u << 16) | 0x80000000u);     // label outside [0, C)
+                }
             }
         }
-        float vl = 0.f;
-        bool count_it = false;
-        if (labels != nullptr && loss_out != nullptr) {
-            const long long lab = labels[idx];
-            if (lab >= 0 && lab < C) {
-                count_it = true;
+        float sum[V];
 #pragma unroll
-                for (int c = 0; c < kMaxClasses; ++c)
-                    if (c == (int)lab) vl = v[c];
-            } else if (lab != ignore_index) {
-                atomicCAS(&g_sscg_dev_error, 0u, (31u << 16) | 0x80000000u);     // label outside [0, C)
-            }
-        }
-        float sum = 0.f;
+        for (int i = 0; i < V; ++i) sum[i] = 0.f;
+#pragma unroll 7
+        for (int c = 0; c < C; ++c) {
+            float v[V];
+            ldv<V>(src + c * HW, v);
 #pragma unroll
-        for (int c = 0; c < kMaxClasses; ++c) {
-            if (c < C) {
-                v[c] = __expf(v[c] - mx);
-                sum += v[c];
-            }
+            for (int i = 0; i < V; ++i) sum[i] += __expf(v[i] - mx[i]);
         }
-        const float inv = 1.f / sum;
         if (probs != nullptr) {
-            float* dst = probs + n * C * HW + pix;
+            float inv[V];
 #pragma unroll
-            for (int c = 0; c < kMaxClasses; ++c)
-                if (c < C) dst[c * HW] = v[c] * inv;
+            for (int i = 0; i < V; ++i) inv[i] = 1.f / sum[i];
+            float* dst = probs + n * C * HW + pix;
+#pragma unroll 7
+            for (int c = 0; c < C; ++c) {
+                float v[V], o[V];
+                ldv<V>(src + c * HW, v);
+#pragma unroll
+                for (int i = 0; i < V; ++i) o[i] = __expf(v[i] - mx[i]) * inv[i];
+                stv<V>(dst + c * HW, o);
+            }
         }
-        if (argmax != nullptr) argmax[idx] = am;
-        if (count_it) {
-            local += logf(sum) + mx - vl;                  // -log softmax(label) from the logits (log-sum-exp form)
-            counted += 1.f;
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+            if (argmax != nullptr) argmax[idx + i] = am[i];
+            if (count_it[i]) {
+                local += logf(sum[i]) + mx[i] - vl[i];             // -log softmax(label) from the logits (log-sum-exp form)
+                counted += 1.f;
+            }
         }
     }
     if (loss_out != nullptr) grid_sum2_store(local, counted, ws, loss_out, 1.f, true);
@@ -131,6 +180,7 @@ __global__ void __launch_bounds__(256) seg_head_fwd_kernel(const float* __restri
 // dlogits = ce_scale * (p - onehot(label)) + p * (dp - sum_c p*dp)
 //   dloss: device scalar (upstream gradient of the MEAN cross-entropy), count: device scalar (number of counted
 //          pixels, loss_out[1] of the forward), or null;   dprobs: upstream gradient w.r.t. the probabilities, or null
+template <int V>
 __global__ void __launch_bounds__(256) seg_head_bwd_kernel(const float* __restrict__ probs,
                                                            const long long* __restrict__ labels,
                                                            const float* __restrict__ dloss,
@@ -139,30 +189,52 @@ __global__ void __launch_bounds__(256) seg_head_bwd_kernel(const float* __restri
                                                            long long HW, float* __restrict__ dlogits) {
     pdl_wait();
     pdl_launch();
-    const long long total = (long long)N * HW;
+    const long long total = (long long)N * HW / V;
     const float ce = (dloss != nullptr && labels != nullptr) ? (*dloss) / (*count) : 0.f;
-    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-         idx += (long long)gridDim.x * blockDim.x) {
+    for (long long gidx = blockIdx.x * (long long)blockDim.x + threadIdx.x; gidx < total;
+         gidx += (long long)gridDim.x * blockDim.x) {
+        const long long idx = gidx * V;
         const long long n = idx / HW, pix = idx - n * HW;
         const long long base = n * C * HW + pix;
-        float p[kMaxClasses], dp[kMaxClasses];
-        float dot = 0.f;
+        // two passes over the class planes (the second one hits the caches): holding p and dp of 4 pixels x 21 classes
+        // in registers needs 255 of them plus spills
+        float dot[V];
 #pragma unroll
-        for (int c = 0; c < kMaxClasses; ++c) {
-            if (c < C) {
-                p[c] = probs[base + c * HW];
-                dp[c] = dprobs != nullptr ? dprobs[base + c * HW] : 0.f;
-                dot += p[c] * dp[c];
+        for (int i = 0; i < V; ++i) dot[i] = 0.f;
+        if (dprobs != nullptr) {
+#pragma unroll 7
+            for (int c = 0; c < C; ++c) {
+                float p[V], dp[V];
+                ldv<V>(probs + base + c * HW, p);
+                ldv<V>(dprobs + base + c * HW, dp);
+#pragma unroll
+                for (int i = 0; i < V; ++i) dot[i] += p[i] * dp[i];
             }
         }
-        const long long lab = labels != nullptr ? labels[idx] : -1;
-        const float cew = (lab >= 0 && lab < C) ? ce : 0.f;        // ignored pixels carry no cross-entropy gradient
+        long long lab[V];
+        float cew[V];
 #pragma unroll
-        for (int c = 0; c < kMaxClasses; ++c) {
-            if (c < C) {
-                float g = p[c] * (dp[c] - dot);
-                g += cew * (p[c] - (c == (int)lab ? 1.f : 0.f));
-                dlogits[base + c * HW] = g;
+        for (int i = 0; i < V; ++i) {
+            lab[i] = labels != nullptr ? labels[idx + i] : -1;
+            cew[i] = (lab[i] >= 0 && lab[i] < C) ? ce : 0.f;        // ignored pixels carry no cross-entropy gradient
+        }
+#pragma unroll 7
+        for (int c = 0; c < C; ++c) {
+            {
+                float p[V], dp[V], g[V];
+                ldv<V>(probs + base + c * HW, p);
+                if (dprobs != nullptr) {
+                    ldv<V>(dprobs + base + c * HW, dp);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < V; ++i) dp[i] = 0.f;
+                }
+#pragma unroll
+                for (int i = 0; i < V; ++i) {
+                    g[i] = p[i] * (dp[i] - dot[i]);
+                    g[i] += cew[i] * (p[i] - (c == (int)lab[i] ? 1.f : 0.f));
+                }
+                stv<V>(dlogits + base + c * HW, g);
             }
         }
     }
@@ -302,19 +374,34 @@ __global__ void __launch_bounds__(256) confusion_kernel(const long long* __restr
 
 using namespace sscg;
 
+// measured at 16 / 32 x 21 x 256 x 256 (tools/bench_seg.py): forward 122 / 123 / 142 us with 1 / 2 / 4 pixels per thread,
+// backward 204 / 199 / 137 us
+constexpr int kSegVecFwd = 4, kSegVecBwd = 4;
+static bool seg_vec_ok(int kSegVec, int64_t HW, const void* a, const void* b, const void* c) {
+    if (kSegVec == 1 || HW % kSegVec) return false;
+    const uintptr_t m = 4 * kSegVec - 1;
+    return !((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c)) & m);
+}
+
 extern "C" int sscg_seg_head_fwd(const float* logits, const int64_t* labels, int32_t N, int32_t C, int64_t HW,
                                  int64_t ignore_index, float* probs, int64_t* argmax, float* loss_out, void* ws,
                                  void* stream) {
     if (C < 1 || C > kMaxClasses) return set_error("seg_head_fwd: C=%d must be in [1, %d]", C, kMaxClasses);
     if (loss_out != nullptr && ws == nullptr) return set_error("seg_head_fwd: the loss needs a workspace of SSCG_LOSS_WS_BYTES");
-    const long long total = (long long)N * HW;
+    const bool vec = seg_vec_ok(kSegVecFwd, HW, logits, probs, nullptr);
+    const long long total = (long long)N * HW / (vec ? kSegVecFwd : 1);
     long long g = (total + 255) / 256;
     if (g > 148 * 8) g = 148 * 8;
     {
         LaunchScope ls_(10, static_cast<cudaStream_t>(stream));
-        launch_k(seg_head_fwd_kernel, (int)g, 256, 0, static_cast<cudaStream_t>(stream), 
-            logits, reinterpret_cast<const long long*>(labels), N, C, HW, (long long)ignore_index, probs,
-            reinterpret_cast<long long*>(argmax), loss_out, reinterpret_cast<float*>(ws));
+        if (vec)
+            launch_k(seg_head_fwd_kernel<kSegVecFwd>, (int)g, 256, 0, static_cast<cudaStream_t>(stream),
+                logits, reinterpret_cast<const long long*>(labels), N, C, HW, (long long)ignore_index, probs,
+                reinterpret_cast<long long*>(argmax), loss_out, reinterpret_cast<float*>(ws));
+        else
+            launch_k(seg_head_fwd_kernel<1>, (int)g, 256, 0, static_cast<cudaStream_t>(stream),
+                logits, reinterpret_cast<const long long*>(labels), N, C, HW, (long long)ignore_index, probs,
+                reinterpret_cast<long long*>(argmax), loss_out, reinterpret_cast<float*>(ws));
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_error("seg_head_fwd launch: %s", cudaGetErrorString(e));
@@ -325,13 +412,18 @@ extern "C" int sscg_seg_head_bwd(const float* probs, const int64_t* labels, cons
                                  const float* dprobs, int32_t N, int32_t C, int64_t HW, float* dlogits, void* stream) {
     if (C < 1 || C > kMaxClasses) return set_error("seg_head_bwd: C=%d must be in [1, %d]", C, kMaxClasses);
     if (dloss != nullptr && labels != nullptr && count == nullptr) return set_error("seg_head_bwd: dloss needs the pixel count");
-    const long long total = (long long)N * HW;
+    const bool vec = seg_vec_ok(kSegVecBwd, HW, probs, dprobs, dlogits);
+    const long long total = (long long)N * HW / (vec ? kSegVecBwd : 1);
     long long g = (total + 255) / 256;
     if (g > 148 * 8) g = 148 * 8;
     {
         LaunchScope ls_(10, static_cast<cudaStream_t>(stream));
-        launch_k(seg_head_bwd_kernel, (int)g, 256, 0, static_cast<cudaStream_t>(stream), 
-            probs, reinterpret_cast<const long long*>(labels), dloss, count, dprobs, N, C, HW, dlogits);
+        if (vec)
+            launch_k(seg_head_bwd_kernel<kSegVecBwd>, (int)g, 256, 0, static_cast<cudaStream_t>(stream),
+                probs, reinterpret_cast<const long long*>(labels), dloss, count, dprobs, N, C, HW, dlogits);
+        else
+            launch_k(seg_head_bwd_kernel<1>, (int)g, 256, 0, static_cast<cudaStream_t>(stream),
+                probs, reinterpret_cast<const long long*>(labels), dloss, count, dprobs, N, C, HW, dlogits);
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_error("seg_head_bwd launch: %s", cudaGetErrorString(e));
