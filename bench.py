@@ -469,7 +469,9 @@ def run_ours(args):
     res_ms, res_n = prof.get("res_conv_fwd", (0.0, 0))
     roof = None
     traffic, traffic_src = None, None
-    tpath = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")     # dram bytes of the same kernel from `ncu --set full`
+    import glob
+    tfiles = sorted(glob.glob(os.path.join(ROOT, "profiles", "r[0-9][0-9]_ncu_traffic.json")))
+    tpath = tfiles[-1] if tfiles else ""                               # dram bytes of the same kernel from `ncu --set full` (latest round)
     if os.path.exists(tpath) and args.batch == 16 and args.config == 2:
         with open(tpath) as f:
             tj = json.load(f)

@@ -21,7 +21,8 @@ def to_bytes(v, unit):
 
 
 def main(out, reps):
-    lines = ["# ncu --set full captures (--clock-control none), one training step of configs[1] (bs 16, 256x256, bf16)\n",
+    lines = ["# ncu --set full captures (--clock-control none): one generator forward + backward (tools/profile_gen.py) or one "
+             "training step (tools/profile_step.py) of configs[1] (bs 16, 256x256, bf16)\n",
              "Per kernel: the first captured launch of every distinct (name, grid) and how many launches of it were captured.\n"]
     traffic = None
     for rep in reps:
@@ -34,10 +35,10 @@ def main(out, reps):
         for r in rows[2:]:
             name = r[hdr.index("Kernel Name")]
             m = re.search(r"(\w+_kernel(<[^>]*>)?)", name)
-            short = m.group(1) if m else name[:60]
+            short = (m.group(1) if m else name[:60]).replace("(int)", "").replace("(bool)", "")
             key = (short, r[hdr.index("launch__grid_size")] if "launch__grid_size" in hdr else "")
             seen.setdefault(key, [r, 0])[1] += 1
-            if short.startswith("conv_igemm_kernel<256, 1, 0>") and "full_fwd" in rep:
+            if short.startswith("conv_igemm_kernel<256, 1, 0") and ("full_fwd" in rep or "res_fwd" in rep):
                 # launch order of a generator forward: ... down2 (first <256> launch), then the residual-block convs:
                 # keep the LAST captured one = a 3x3 256->256 @64x64 residual conv, the kernel bench.py's roofline names
                 i, j = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
@@ -65,7 +66,8 @@ def main(out, reps):
     with open(out, "w") as f:
         f.write("\n".join(lines) + "\n")
     if traffic:
-        with open(os.path.join(os.path.dirname(out), "r01_ncu_traffic.json"), "w") as f:
+        prefix = os.path.basename(out).split("_")[0]          # rNN
+        with open(os.path.join(os.path.dirname(out), prefix + "_ncu_traffic.json"), "w") as f:
             json.dump(traffic, f, indent=1)
 
 
