@@ -113,10 +113,10 @@ typedef struct SscgConvArgs {
      * positions with col >= Wo or row >= Ho are computed but not stored.  66 x 66 outputs then take 36 tiles per
      * sample instead of 45 (8 x 16 tiles).  0 = off.  Requires stride 1, one phase, TH = 1, TW = 128. */
     int32_t flat_pitch, flat_hw, flat_n;
-    /* Pixel-row mode for stems (0 = off, else bytes per pixel of x: 16, i.e. x.C == 8): `taps` holds ONE entry per
-     * filter row (as in the row-window layout, Kc == 64 = 8 pixels x 8 channels, weights [kh][Co_pad][(kw, c)]), x is
-     * the PLAIN haloed view; the kernel loads one (128 + 8)-pixel row box per filter row and addresses it as overlapping
-     * K-major rows.  Needs stride 1, one phase, TH = 1, TW = 128, BN = 64, split == 1. */
+    /* Pixel-row mode for stems (0 = off, else bytes per pixel of x: 16 * G for x.C == 8 * G channels, G = 1..4): `taps`
+     * holds ONE entry per filter row, Kc == 64 * G, weights in sscg_wprep mode 5 ([kh][Co_pad][(g, kw, c8)]), x is the PLAIN
+     * haloed view; per filter row and channel group the kernel loads one dense (128 + 8)-pixel x 8-channel row box and
+     * addresses it as overlapping K-major rows.  Needs stride 1, one phase, TH = 1, TW = 128, BN = 64, split == 1. */
     int32_t rw_pitch;
 } SscgConvArgs;
 
@@ -271,6 +271,8 @@ typedef struct SscgWprepArgs {
                               3: N-expanded 7x7 forward  [kh][nt][NT: kw * CoW + (co - nt * CoW)][Kc(ci)]
                               4: N-expanded 7x7 dgrad    [kh][nt][NT: kw * CoW + (ci - nt * CoW)][Kc(co)], taps flipped
                                  (sscg_conv7_nexp; CoW is passed in Cp, rows_pad = NT = round_up(7 * CoW, 16))
+                              5: fwd pixel-row [kh][Co_pad][Kc: 64 * g + 8 * kw + (ci - 8 * g)], channel groups g of 8
+                                 (sscg_conv_igemm rw_pitch; Kc = 64 * Cp / 8, KW <= 8)
                             */
     int32_t Cp;            /* channel pitch of the activation in window mode; CoW in modes 3 / 4 */
     int32_t rows_pad;      /* Co_pad (mode 0,1) or Ci_pad (mode 2) */

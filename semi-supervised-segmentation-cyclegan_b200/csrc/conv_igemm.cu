@@ -61,8 +61,9 @@ constexpr int kABytes = kTileM * 128;   // 128 pixels x 64 bf16
 // pixels per filter row and channel block is shared by the SKW horizontal taps, which read it through
 // descriptors whose start address is shifted by one 128-byte pixel row per tap.
 //
-// RW > 0 selects the PIXEL-ROW mode for stems (few input channels, 1 x 128 pixel tiles, stride 1; RW = bytes per pixel of
-// the input buffer): the K axis of one filter row is the run of kw consecutive pixels x Cp channels, which IS the image
+// RW > 0 selects the PIXEL-ROW mode for stems (few input channels, 1 x 128 pixel tiles, stride 1; RW = 16 = bytes per pixel of
+// ONE 8-channel group of the input buffer; inputs with 16 / 24 / 32 channels run one K block per group, the TMA box
+// picking the group's 8 channels out of every pixel): the K axis of one filter row is the run of kw consecutive pixels x Cp channels, which IS the image
 // row.  One TMA box of 128 + 8 pixels lands densely (16 bytes per pixel for Cp = 8) and the A descriptor addresses it
 // as overlapping rows: M row m starts at pixel m (16-byte row pitch inside a core matrix, SBO = 128 B per 8 pixels),
 // the next 16-byte K chunk is the next pixel (LBO = 16 B).  The earlier row-WINDOW tensor map made TMA expand every
@@ -233,7 +234,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         cn = 0;
                     }
                     const int brow = tap.brow * p.Co_pad + t.n0;
-                    tma_load_4d(smem_u32(st), &tmA, fb, cb * 64, cw, ch, cn);
+                    tma_load_4d(smem_u32(st), &tmA, fb, RW > 0 ? cb * 8 : cb * 64, cw, ch, cn);   // RW: channel group cb
                     if (SKW > 0) {   // one weight box per horizontal tap of this filter row
 #pragma unroll
                         for (int j = 0; j < (SKW > 0 ? SKW : 1); ++j)
@@ -566,9 +567,11 @@ extern "C" int sscg_conv_igemm(const SscgConvArgs* a, void* stream_) {
     }
     const int rw = a->rw_pitch;
     if (rw != 0) {
-        if (rw != 16 || a->x.C != 8 || a->x.sW != 8 || a->split != 1 || a->stride != 1 || a->n_phases != 1 || a->TH != 1 ||
-            a->TW != 128 || a->BN != 64 || a->Kc != 64 || skw != 0 || a->flat_pitch > 0)
-            return set_error("conv_igemm: pixel-row mode needs an 8-channel dense view, bf16, stride 1, 1x128 tiles, BN 64, Kc 64");
+        const int G = rw / 16;
+        if (rw % 16 || G < 1 || G > 4 || a->x.C != 8 * G || a->x.sW != 8 * G || a->split != 1 || a->stride != 1 ||
+            a->n_phases != 1 || a->TH != 1 || a->TW != 128 || a->BN != 64 || a->Kc != 64 * G || skw != 0 || a->flat_pitch > 0)
+            return set_error("conv_igemm: pixel-row mode needs a dense view of 8 * G channels (G = 1..4), bf16, stride 1, "
+                             "1x128 tiles, BN 64, Kc = 64 * G");
     }
     CUtensorMap tmA, tmAlo, tmB, tmBlo;
     const uint32_t boxA[4] = {rw ? 8u : 64u, (uint32_t)(rw ? a->TW + 8 : (skw ? a->TW + skw - 1 : a->TW * a->stride)),
@@ -626,7 +629,7 @@ extern "C" int sscg_conv_igemm(const SscgConvArgs* a, void* stream_) {
     d.y_sN = a->y_sN; d.y_sH = a->y_sH; d.y_sW = a->y_sW; d.y_oh = a->y_oh; d.y_ow = a->y_ow;
     d.bias = a->bias; d.act = a->act; d.slope = a->slope; d.stats = reinterpret_cast<unsigned long long*>(a->stats);
     if (d.total_tiles <= 0) return 0;
-    if (rw == 16) return launch_igemm<64, 1, 0, 16>(tmA, tmAlo, tmB, tmBlo, d, stream, a->tag);
+    if (rw != 0) return launch_igemm<64, 1, 0, 16>(tmA, tmAlo, tmB, tmBlo, d, stream, a->tag);
     if (skw == 7) {
         if (a->BN == 16) return launch_igemm<16, 1, 7>(tmA, tmAlo, tmB, tmBlo, d, stream, a->tag);
         if (a->BN == 64) return launch_igemm<64, 1, 7>(tmA, tmAlo, tmB, tmBlo, d, stream, a->tag);

@@ -255,6 +255,11 @@ __device__ __forceinline__ long long wslab_src_index(const SscgWprepArgs& a, int
     } else if (a.mode == 1) {
         kh = t; kw = k / a.Cp; ci = k - kw * a.Cp; co = r;
         if (kw >= a.KW) return -1;
+    } else if (a.mode == 5) {
+        // pixel-row order: K = 64 * g + 8 * kw + c8 (channel group g of 8 channels, 8 pixels per group row)
+        const int g = k >> 6, rr = k & 63;
+        kh = t; kw = rr >> 3; ci = g * 8 + (rr & 7); co = r;
+        if (kw >= a.KW) return -1;
     } else {
         kh = t / a.KW; kw = t - kh * a.KW;
         if (a.mode == 0) { co = r; ci = k; } else { ci = r; co = k; }
@@ -266,7 +271,7 @@ __device__ __forceinline__ long long wslab_src_index(const SscgWprepArgs& a, int
 __host__ __device__ __forceinline__ int wslab_ntaps(const SscgWprepArgs& a) {
     if (a.mode == 3) return a.KH * ((a.Co + a.Cp - 1) / a.Cp);
     if (a.mode == 4) return a.KH * ((a.Ci + a.Cp - 1) / a.Cp);
-    return a.mode == 1 ? a.KH : a.KH * a.KW;
+    return (a.mode == 1 || a.mode == 5) ? a.KH : a.KH * a.KW;
 }
 
 __global__ void wprep_kernel(const __grid_constant__ SscgWprepArgs a) {

@@ -66,6 +66,10 @@ class StageWeights:
         # channel pitch of the stage input: the packed network input is padded to 8 channels, internal
         # activations carry the producing GEMM's N padding
         self.Cp_in = G.pad_in_channels(s.Cin) if first else G.pad_out_channels(s.Cin)
+        # stride-1 stem over <= 32 input channels in bf16 mode: pixel-row forward (conv_igemm.cu, RW): the forward slab is
+        # ordered (channel group, kw, channel in group); weight / data gradients keep the row-window order
+        self.pixel_row = (s.kind == "window" and not split and s.stride == 1 and self.Cp_in in (8, 16, 24, 32) and k <= 8
+                          and G.pad_out_channels(s.Cout) == 64 and os.environ.get("SSCG_PIXEL_ROW", "1") != "0")
         if s.kind == "window":
             self.Kc = G.round_up(k * self.Cp_in, 64)
             self.ntaps_fwd = k
@@ -79,8 +83,10 @@ class StageWeights:
         bf = torch.bfloat16
         self.w_fwd = torch.zeros(self.ntaps_fwd * self.Co_pad * self.Kc, dtype=bf, device=device)
         self.w_fwd_lo = torch.zeros_like(self.w_fwd) if split else None
-        self.prep_fwd = K.wprep_args(s.weight, self.transposed, s.Cout, s.Cin, k, k, fmode, self.Cp_in, self.Co_pad,
-                                     self.Kc, self.w_fwd, self.w_fwd_lo)
+        if self.pixel_row:
+            assert self.Kc == 8 * self.Cp_in          # 64 K-columns per group of 8 channels
+        self.prep_fwd = K.wprep_args(s.weight, self.transposed, s.Cout, s.Cin, k, k, 5 if self.pixel_row else fmode,
+                                     self.Cp_in, self.Co_pad, self.Kc, self.w_fwd, self.w_fwd_lo)
         # dgrad: rows = input channels (padded to a legal N tile), K = output-channel pitch
         self.need_dgrad = need_dgrad
         self.Ci_pad = G.pad_out_channels(self.Cp_in)
@@ -317,8 +323,7 @@ class NetPlan:
         return G.taps_conv_fwd(s.k, s.k, s.stride, 0 if s.in_halo else -s.pad)
 
     def _pixel_row_ok(self, s: StageSpec, wt: StageWeights, buf: K.ActBuf):
-        return (s.kind == "window" and self.split == 1 and s.stride == 1 and buf.C == 8 and wt.Kc == 64 and wt.Co_pad == 64
-                and s.k <= 8 and os.environ.get("SSCG_PIXEL_ROW", "1") != "0")
+        return wt.pixel_row and buf.C == wt.Cp_in
 
     def _x_view(self, s: StageSpec, wt: StageWeights, buf: K.ActBuf):
         """(view, lo pointer) of the stage input as the forward GEMM reads it."""
@@ -361,7 +366,7 @@ class NetPlan:
                     if self._pixel_row_ok(s, wt, c.act[i]):
                         # stem over an 8-channel buffer: the image row itself is the K-major operand (conv_igemm.cu, RW)
                         view, lo = c.act[i].view(interior=False), None
-                        kw = dict(rw_pitch=16, BN=64)
+                        kw = dict(rw_pitch=2 * wt.Cp_in, BN=64)
                     ca = K.conv_args(view, lo, table, wt.Kc, wt.w_fwd, wt.w_fwd_lo, wt.ntaps_fwd * wt.Co_pad, wt.Co_pad,
                                      dst.hi.data_ptr(), dst.fp32, (dst.sN, dst.sH, dst.sW), (0, 0), ho, wo,
                                      bias=None if s.norm else wt.bias_pad,

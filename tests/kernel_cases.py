@@ -39,7 +39,7 @@ def _fill_act(buf: K.ActBuf, x_nchw, pad_mode):
 
 
 def _wslab(w, transposed, mode, Cp, rows_pad, Kc, KH, KW, Co, Ci, split=False):
-    ntaps = KH if mode == 1 else KH * KW
+    ntaps = KH if mode in (1, 5) else KH * KW
     dst = torch.zeros(ntaps * rows_pad * Kc, dtype=torch.bfloat16, device=DEV)
     dst_lo = torch.zeros_like(dst) if split else None
     a = K.wprep_args(w, transposed, Co, Ci, KH, KW, mode, Cp, rows_pad, Kc, dst, dst_lo)
@@ -133,11 +133,13 @@ def case_conv_window(N=2, H=16, W=16, Cin=3, Cout=64, k=7, stride=1, pad=3, refl
     Co_pad = G.pad_out_channels(Cout)
     buf = K.ActBuf(N, H, W, Cp, pad, DEV)
     _fill_act(buf, x, L.PAD_REFLECT if reflect else L.PAD_ZERO)
-    slab, _, _ = _wslab(w, False, 1, Cp, Co_pad, kwpad, k, k, Cout, Cin)
+    slab, _, _ = _wslab(w, False, 5 if pixel_row else 1, Cp, Co_pad, kwpad, k, k, Cout, Cin)
     Ho, Wo = G.conv_out(H, k, stride, pad), G.conv_out(W, k, stride, pad)
     y = torch.zeros(N, Ho, Wo, Co_pad, device=DEV)
     table = G.taps_conv_fwd_window(k, stride, 0)
-    kw = dict(rw_pitch=16, BN=64) if pixel_row else {}
+    kw = dict(rw_pitch=2 * Cp, BN=64) if pixel_row else {}
+    if pixel_row:
+        assert kwpad == 8 * Cp
     a = K.conv_args(buf.view(interior=False) if pixel_row else buf.window_view(kwpad), None, table, kwpad, slab, None,
                     k * Co_pad, Co_pad, y.data_ptr(), True, (Ho * Wo * Co_pad, Wo * Co_pad, Co_pad), (0, 0), Ho, Wo, **kw)
     K.run_conv(a)
@@ -773,6 +775,9 @@ CASES = {
     "pixrow_stem_c3": lambda: case_conv_window(pixel_row=True),
     "pixrow_stem_c1_wide": lambda: case_conv_window(N=3, H=20, W=200, Cin=1, pixel_row=True),     # ragged second tile
     "pixrow_stem_c3_256": lambda: case_conv_window(N=2, H=32, W=256, Cin=3, pixel_row=True),
+    "pixrow_stem_c21": lambda: case_conv_window(N=2, H=20, W=200, Cin=21, pixel_row=True),       # 3 channel groups
+    "pixrow_stem_c12": lambda: case_conv_window(N=1, H=16, W=128, Cin=12, pixel_row=True),       # 2 groups
+    "pixrow_stem_c30": lambda: case_conv_window(N=2, H=16, W=140, Cin=30, pixel_row=True),       # 4 groups
     "win_d0_c3": lambda: case_conv_window(Cin=3, k=4, stride=2, pad=1, reflect=False),
     "win_d0_c21": lambda: case_conv_window(Cin=21, k=4, stride=2, pad=1, reflect=False),
     # transposed conv
