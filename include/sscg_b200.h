@@ -148,6 +148,9 @@ typedef struct SscgWgradArgs {
     int32_t tag;           /* profiling class (0..15) */
     void* ws;              /* ksplit > 1: workspace of sscg_conv_wgrad_ws_bytes() bytes (arrival counters, zero before
                             * the first launch and left zero by every launch, + partial tiles) */
+    int32_t rw_pitch;      /* pixel-row mode for stride-1 stems (0 = off, else 16 * G for x.C == 8 * G channels): x is the
+                            * PLAIN haloed view, `taps` holds one entry per filter row, dWt columns are in sscg_wprep mode 5
+                            * order (group, kw, channel in group); needs TH = 1, TW = 64, BN = Kc = 64 * G, split == 1 */
 } SscgWgradArgs;
 
 int sscg_conv_wgrad(const SscgWgradArgs* a, void* stream);

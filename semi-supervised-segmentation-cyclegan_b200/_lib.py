@@ -57,7 +57,7 @@ class WgradArgs(C.Structure):
         ("Co_pad", C.c_int32), ("split", C.c_int32),
         ("dw", C.c_void_p), ("w_rows", C.c_int32),
         ("TH", C.c_int32), ("TW", C.c_int32), ("BN", C.c_int32), ("ksplit", C.c_int32), ("tag", C.c_int32),
-        ("ws", C.c_void_p),
+        ("ws", C.c_void_p), ("rw_pitch", C.c_int32),
     ]
 
 

@@ -61,7 +61,13 @@ struct WgradCfg {
 
 constexpr int kWgCtrs = 1024;           // arrival counters at the head of the workspace
 
-template <int BN, int SPLIT>
+// RW: pixel-row mode for stride-1 stems (bf16 mode, 1 x 64 pixel blocks, BN = 64 * G columns for 8 * G input channels):
+// the X operand of a filter row is the image row itself.  Per channel group one dense box of 64 + 8 pixels x 8 channels
+// (16 bytes per pixel) is read as an MN-major operand with OVERLAPPING rows — K row = pixel (16-byte pitch), the next
+// 16-byte chunk along N = the next pixel (SBO 16), 8 K rows = 128 bytes (LBO; the no-swizzle MN-major roles of the two
+// offsets are the reverse of the K-major ones) — instead of a TMA-expanded 8 KB window
+// atom per group (see conv_igemm.cu, RW).  One N = 64 MMA per group and 16-pixel step.
+template <int BN, int SPLIT, bool RW>
 __global__ void __launch_bounds__(192, (WgradCfg<BN, SPLIT>::kCtasPerSm))
 conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ CUtensorMap tmDyLo,
                   const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmXLo,
@@ -126,7 +132,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
     if (warp == 0) {
         if (lane == 0) {
             int stage = 0; uint32_t par = 0;
-            const uint32_t tx = kPlanes * (a_atoms + kBAtoms) * kWgAtomBytes;
+            constexpr uint32_t kRwBox = (64 + 8) * 16;       // bytes of one pixel-row box
+            const uint32_t tx = RW ? a_atoms * kWgAtomBytes + kBAtoms * kRwBox : kPlanes * (a_atoms + kBAtoms) * kWgAtomBytes;
             for (int kb = 0; kb < nkb; ++kb) {
                 int b = pb0 + kb;
                 const int n = b / blocks_per_sample; b -= n * blocks_per_sample;
@@ -142,7 +149,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
                     tma_load_4d(smem_u32(st + kAOff + a * kWgAtomBytes), &tmDy, fb, m0 + a * 64, j0, i0, n);
 #pragma unroll
                 for (int q = 0; q < kBAtoms; ++q)
-                    tma_load_4d(smem_u32(st + kBOff + q * kWgAtomBytes), &tmX, fb, kt * BN + q * 64, cw, ch, n);
+                    tma_load_4d(smem_u32(st + kBOff + q * kWgAtomBytes), &tmX, fb, RW ? q * 8 : kt * BN + q * 64, cw, ch, n);
                 if (SPLIT == 3) {
                     for (int a = 0; a < a_atoms; ++a)
                         tma_load_4d(smem_u32(st + kLoOff + kAOff + a * kWgAtomBytes), &tmDyLo, fb, m0 + a * 64, j0, i0, n);
@@ -166,6 +173,21 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
                 // MN-major: LBO = stride between 64-wide channel atoms, SBO = stride between 8-pixel groups
                 const uint64_t da = make_smem_desc_sw128(st + kAOff, kWgAtomBytes, 1024);
                 const uint64_t db = make_smem_desc_sw128(st + kBOff, kWgAtomBytes, 1024);
+                if (RW) {
+                    constexpr uint32_t idesc64 = make_idesc_bf16(128, 64, 1, 1);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+#pragma unroll
+                        for (int q = 0; q < kBAtoms; ++q) {      // group q: columns 64 q .., rows of 16 bytes, +16 pixels = +256 B
+                            const uint64_t dq = make_smem_desc(st + kBOff + q * kWgAtomBytes, 128, 16, 0);   // MN-major: LBO = 8 K rows, SBO = next 16-byte chunk along N
+                            umma_bf16(tmem_base + 64 * q, da + 128 * k, dq + 16 * k, idesc64, acc);
+                        }
+                        acc = 1;
+                    }
+                    umma_commit(smem_u32(&empty_bar[stage]));
+                    if (++stage == kStages) { stage = 0; par ^= 1; }
+                    continue;
+                }
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {   // 16 pixels per MMA: +2048 B
                     umma_bf16(tmem_base, da + 128 * k, db + 128 * k, idesc, acc);
@@ -294,20 +316,20 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
     }
 }
 
-template <int BN, int SPLIT>
+template <int BN, int SPLIT, bool RW = false>
 static int launch_wgrad(const CUtensorMap& tmDy, const CUtensorMap& tmDyLo, const CUtensorMap& tmX,
                         const CUtensorMap& tmXLo, const WgradDev& d, dim3 grid, cudaStream_t stream, int tag) {
     using Cfg = WgradCfg<BN, SPLIT>;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(conv_wgrad_kernel<BN, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(conv_wgrad_kernel<BN, SPLIT, RW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              Cfg::kSmemBytes);
         if (e != cudaSuccess) return set_error("conv_wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         configured = true;
     }
     {
         LaunchScope ls(tag, stream);
-        launch_k(conv_wgrad_kernel<BN, SPLIT>, grid, 192, Cfg::kSmemBytes, stream, tmDy, tmDyLo, tmX, tmXLo, d);
+        launch_k(conv_wgrad_kernel<BN, SPLIT, RW>, grid, 192, Cfg::kSmemBytes, stream, tmDy, tmDyLo, tmX, tmXLo, d);
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_error("conv_wgrad<%d,%d> launch: %s", BN, SPLIT, cudaGetErrorString(e));
@@ -349,13 +371,26 @@ extern "C" int sscg_conv_wgrad(const SscgWgradArgs* a, void* stream_) {
     if (a->n_taps < 1 || a->n_taps > SSCG_MAX_TAPS) return set_error("conv_wgrad: bad n_taps");
     if (a->ksplit < 1) return set_error("conv_wgrad: ksplit must be >= 1");
 
+    const int rw = a->rw_pitch;
+    if (rw != 0) {
+        const int G = rw / 16;
+        if (rw % 16 || G < 1 || G > 4 || a->x.C != 8 * G || a->x.sW != 8 * G || a->split != 1 || a->stride != 1 || a->TH != 1 ||
+            a->TW != 64 || a->BN != 64 * G || a->Kc != 64 * G)
+            return set_error("conv_wgrad: pixel-row mode needs a dense view of 8 * G channels (G = 1..4), bf16, stride 1, "
+                             "1x64 pixel blocks, BN = Kc = 64 * G");
+    }
     CUtensorMap tmDy, tmDyLo, tmX, tmXLo;
     const uint32_t boxDy[4] = {64u, (uint32_t)a->TW, (uint32_t)a->TH, 1u};
     const uint32_t es1[4] = {1u, 1u, 1u, 1u};
     const uint32_t boxX[4] = {64u, (uint32_t)(a->TW * a->stride), (uint32_t)(a->TH * a->stride), 1u};
     const uint32_t esX[4] = {1u, (uint32_t)a->stride, (uint32_t)a->stride, 1u};
     if (int rc = encode_view_4d(&tmDy, a->dy, a->dy.ptr, boxDy, es1)) return rc;
-    if (int rc = encode_view_4d(&tmX, a->x, a->x.ptr, boxX, esX)) return rc;
+    if (rw != 0) {
+        const uint32_t boxR[4] = {8u, (uint32_t)(a->TW + 8), 1u, 1u};
+        if (int rc = encode_view_4d(&tmX, a->x, a->x.ptr, boxR, es1, 0)) return rc;
+    } else if (int rc = encode_view_4d(&tmX, a->x, a->x.ptr, boxX, esX)) {
+        return rc;
+    }
     tmDyLo = tmDy; tmXLo = tmX;
     if (a->split == 3) {
         if (int rc = encode_view_4d(&tmDyLo, a->dy, a->dy_lo, boxDy, es1)) return rc;
@@ -378,6 +413,14 @@ extern "C" int sscg_conv_wgrad(const SscgWgradArgs* a, void* stream_) {
         if ((long long)grid.y * grid.z * 2 > kWgCtrs) return set_error("conv_wgrad: too many output tiles for the arrival counters");
         d.ctr = reinterpret_cast<unsigned int*>(a->ws);
         d.part = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(a->ws) + kWgCtrs * 4);
+    }
+    if (rw != 0) {
+        switch (a->BN) {
+            case 64: return launch_wgrad<64, 1, true>(tmDy, tmDyLo, tmX, tmXLo, d, grid, stream, a->tag);
+            case 128: return launch_wgrad<128, 1, true>(tmDy, tmDyLo, tmX, tmXLo, d, grid, stream, a->tag);
+            case 192: return launch_wgrad<192, 1, true>(tmDy, tmDyLo, tmX, tmXLo, d, grid, stream, a->tag);
+            default: return launch_wgrad<256, 1, true>(tmDy, tmDyLo, tmX, tmXLo, d, grid, stream, a->tag);
+        }
     }
 #define SSCG_WG(BN_)                                                                          \
     case BN_:                                                                                  \

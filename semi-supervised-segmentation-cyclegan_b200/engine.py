@@ -107,7 +107,8 @@ class StageWeights:
             self.wg_rows = G.round_up(s.Cout, 64)
             self.wg_Kc = self.Kc
             self.wg_taps = self.ntaps_fwd
-            wmode = fmode
+            wmode = 5 if (self.pixel_row and os.environ.get("SSCG_PIXEL_ROW_WG", "1") != "0") else fmode
+        self.wg_pixel_row = (wmode == 5)       # weight-gradient slab in pixel-row column order (conv_wgrad.cu, RW)
         # 7x7 head conv (64 input channels, explicit halo): its weight gradient reads the activation as
         # a row window of k*64 contiguous elements, so one CTA handles a whole filter row and dY is
         # fetched once per row instead of once per tap
@@ -578,6 +579,10 @@ class NetPlan:
                                   split=sp, tag=6, ws_pool=self.ws_wg)
             else:
                 table = self._fwd_table(s)
+                wkw = {}
+                if wt.wg_pixel_row and c.act[i].C == wt.Cp_in:
+                    xview, xlo = c.act[i].view(interior=False), None
+                    wkw = dict(rw_pitch=2 * wt.Cp_in)
                 if wt.wg_window:
                     table = G.taps_conv_fwd_window(s.k, 1, 0)
                     xview, xlo = c.act[i].window_view(wt.wg_Kc), None
@@ -587,7 +592,7 @@ class NetPlan:
                     wa = K.wgrad7_args(c.act[i], self.draw_nx[i], wt.dw, tag=6, ws_pool=self.ws_wg7)
                 else:
                     wa = K.wgrad_args(dview, dlo, xview, xlo, table, wt.wg_Kc, wt.wg_rows, wt.dw, wt.wg_taps * wt.wg_rows,
-                                      split=sp, tag=3 if s.name.startswith("res") else 6, ws_pool=self.ws_wg)
+                                      split=sp, tag=3 if s.name.startswith("res") else 6, ws_pool=self.ws_wg, **wkw)
         # ---- 3. dgrad ------------------------------------------------------------------------
         da = None
         dkw = {}

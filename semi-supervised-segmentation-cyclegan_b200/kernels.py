@@ -165,7 +165,7 @@ def conv_args(xview, x_lo, table: TapTable, Kc, w, w_lo, w_rows, Co_pad, y_ptr, 
 
 
 def wgrad_args(dyview, dy_lo, xview, x_lo, table: TapTable, Kc, Co_pad, dw, w_rows, BN=None, tile=None, ksplit=None,
-               split=1, tag=6, ws_pool=None):
+               split=1, tag=6, ws_pool=None, rw_pitch=0):
     assert table.n_phases == 1
     a = L.WgradArgs()
     a.dy, a.dy_lo, a.x, a.x_lo = dyview, dy_lo, xview, x_lo
@@ -174,6 +174,9 @@ def wgrad_args(dyview, dy_lo, xview, x_lo, table: TapTable, Kc, Co_pad, dw, w_ro
     fill_taps(a.taps, table)
     a.Co_pad, a.split = Co_pad, split
     a.dw, a.w_rows = _ptr(dw), w_rows
+    a.rw_pitch = rw_pitch
+    if rw_pitch:
+        tile, BN = (1, 64), Kc
     if tile is None:
         tile = pick_tile(dyview.W, 64, dyview.H)
     a.TH, a.TW = tile

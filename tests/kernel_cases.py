@@ -251,7 +251,9 @@ def case_conv_wgrad(N=2, H=16, W=16, Cin=64, Cout=128, k=3, stride=1, pad=1, ksp
     return _result(grad, ref, 2e-4 * (N * Ho * Wo) ** 0.5)
 
 
-def case_wgrad_window(N=2, H=16, W=16, Cin=3, Cout=64, k=7, pad=3):
+def case_wgrad_window(N=2, H=16, W=16, Cin=3, Cout=64, k=7, pad=3, pixel_row=False):
+    """Weight gradient of a small-Cin stem through the row-window view, or (pixel_row) through the plain view with
+    overlapping MN-major rows (conv_wgrad.cu, RW; slab columns in sscg_wprep mode 5 order)."""
     _setup()
     x = _bf(torch.randn(N, Cin, H, W, device=DEV))
     dy = _bf(torch.randn(N, Cout, H, W, device=DEV))
@@ -264,7 +266,12 @@ def case_wgrad_window(N=2, H=16, W=16, Cin=3, Cout=64, k=7, pad=3):
     _fill_act(dyb, dy, L.PAD_ZERO)
     dw = torch.zeros(k * Co_pad * kwpad, device=DEV)
     table = G.taps_conv_fwd_window(k, 1, 0)
-    a = K.wgrad_args(dyb.view(interior=True), None, xb.window_view(kwpad), None, table, kwpad, Co_pad, dw, k * Co_pad)
+    if pixel_row:
+        assert kwpad == 8 * Cp
+        a = K.wgrad_args(dyb.view(interior=True), None, xb.view(interior=False), None, table, kwpad, Co_pad, dw, k * Co_pad,
+                         rw_pitch=2 * Cp)
+    else:
+        a = K.wgrad_args(dyb.view(interior=True), None, xb.window_view(kwpad), None, table, kwpad, Co_pad, dw, k * Co_pad)
     K.run_wgrad(a)
     torch.cuda.synchronize()
     dw1 = dw.clone()
@@ -273,7 +280,7 @@ def case_wgrad_window(N=2, H=16, W=16, Cin=3, Cout=64, k=7, pad=3):
     assert torch.equal(dw, 2 * dw1), "conv_wgrad (window) is not reproducible / does not accumulate"
     dw.copy_(dw1)
     grad = torch.zeros(Cout, Cin, k, k, device=DEV)
-    ua = K.wprep_args(grad, False, Cout, Cin, k, k, 1, Cp, Co_pad, kwpad, None)
+    ua = K.wprep_args(grad, False, Cout, Cin, k, k, 5 if pixel_row else 1, Cp, Co_pad, kwpad, None)
     K.run_wgrad_unpack(ua, dw, grad)
     torch.cuda.synchronize()
     xp = F.pad(x, (pad,) * 4, mode="reflect")
@@ -807,6 +814,10 @@ CASES = {
     "wgrad_ksplit1": lambda: case_conv_wgrad(ksplit=1),
     "wgrad_window_c3": lambda: case_wgrad_window(),
     "wgrad_window_c21": lambda: case_wgrad_window(Cin=21),            # Kc = 192 -> one 192-wide tile
+    "wgrad_pixrow_c3": lambda: case_wgrad_window(pixel_row=True),
+    "wgrad_pixrow_c21": lambda: case_wgrad_window(N=2, H=20, W=200, Cin=21, pixel_row=True),     # 3 groups, ragged rows
+    "wgrad_pixrow_c12": lambda: case_wgrad_window(N=3, H=16, W=128, Cin=12, pixel_row=True),
+    "wgrad_pixrow_c30": lambda: case_wgrad_window(N=1, H=24, W=70, Cin=30, pixel_row=True),
     "wgrad_window_c64_wide": lambda: case_wgrad_window(Cin=64, Cout=21),   # head conv: Kc = 448 -> 448-wide tile
     "wgrad_window_c64_wide_big": lambda: case_wgrad_window(N=2, H=24, W=40, Cin=64, Cout=3),
     "wgrad7_head_c21": lambda: case_wgrad7(),
